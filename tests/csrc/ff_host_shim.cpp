@@ -1,0 +1,28 @@
+// Host build of za_b200/csrc/ff.cuh + ec.cuh for CPU-side unit tests (no GPU needed).
+// Test infrastructure only: exercises the exact limb schedule the device runs,
+// on the emulated carry flag.
+#include "../../za_b200/csrc/ff.cuh"
+#include <string.h>
+using namespace za;
+extern "C" {
+uint64_t shim_lost_carries() { return host_cc().lost; }
+#define BINOP(name, T, expr) void name(const uint32_t* a, const uint32_t* b, uint32_t* r) { T x, y; memcpy(&x, a, sizeof(T)); memcpy(&y, b, sizeof(T)); T z = expr; memcpy(r, &z, sizeof(T)); }
+#define UNOP(name, T, expr) void name(const uint32_t* a, uint32_t* r) { T x; memcpy(&x, a, sizeof(T)); T z = expr; memcpy(r, &z, sizeof(T)); }
+BINOP(shim_fr_mul, Fr, x * y)
+BINOP(shim_fr_add, Fr, x + y)
+BINOP(shim_fr_sub, Fr, x - y)
+UNOP(shim_fr_neg, Fr, -x)
+UNOP(shim_fr_inv, Fr, inv(x))
+UNOP(shim_fr_to_mont, Fr, fp_to_mont(x))
+UNOP(shim_fr_from_mont, Fr, fp_from_mont(x))
+BINOP(shim_fq_mul, Fq, x * y)
+BINOP(shim_fq_add, Fq, x + y)
+BINOP(shim_fq_sub, Fq, x - y)
+UNOP(shim_fq_neg, Fq, -x)
+UNOP(shim_fq_inv, Fq, inv(x))
+UNOP(shim_fq_to_mont, Fq, fp_to_mont(x))
+UNOP(shim_fq_from_mont, Fq, fp_from_mont(x))
+BINOP(shim_fq2_mul, Fq2, x * y)
+UNOP(shim_fq2_sqr, Fq2, sqr(x))
+UNOP(shim_fq2_inv, Fq2, inv(x))
+}

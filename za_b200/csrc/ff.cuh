@@ -1,0 +1,404 @@
+// BN254 prime-field arithmetic on 8 x 32-bit limbs, Montgomery form (R = 2^256).
+//
+// Replaces (un-vendored) ff_ce's derived `Fr` / `Fq`
+// (`PrimeField` impls used at /root/reference/prover/src/groth16/format.rs:35,51,204)
+// for the device side of the Groth16 hot path.
+//
+// One source, two targets:
+//   * device (sm_100a): every limb operation is a PTX `mad.lo.cc / madc.hi.cc / addc`
+//     carry-chain instruction; ptxas pairs adjacent lo/hi into IMAD.WIDE.U32 + carry.
+//   * host: the same algorithm runs on an emulated carry flag, so the exact
+//     limb schedule that the GPU executes is unit-testable without a GPU
+//     (tests/test_ff_host.py) and is reused by the host-side proof assembly.
+//
+// The Montgomery product keeps two half-accumulators ("even"/"odd" limb
+// alignment) so that each 32x32->64 product lands in one aligned register pair
+// and every carry chain is a single pass.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define ZA_HD __host__ __device__ __forceinline__
+#define ZA_D __device__ __forceinline__
+#else
+#define ZA_HD inline
+#endif
+
+namespace za {
+
+// ---------------------------------------------------------------------------
+// carry-chain primitives
+// ---------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+
+ZA_D uint32_t p_mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZA_D uint32_t p_mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZA_D uint32_t p_add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZA_D uint32_t p_addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZA_D uint32_t p_addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZA_D uint32_t p_sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZA_D uint32_t p_subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZA_D uint32_t p_subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZA_D uint32_t p_mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ZA_D uint32_t p_mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ZA_D uint32_t p_madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ZA_D uint32_t p_madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ZA_D uint32_t p_madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+
+#else  // host emulation of the PTX carry flag
+
+// Number of times an instruction that cannot report a carry-out would have
+// produced one (must stay 0; checked by tests/test_ff_host.py).
+struct HostCC {
+    uint32_t cf = 0;
+    uint64_t lost = 0;
+};
+inline HostCC& host_cc() { static thread_local HostCC s; return s; }
+
+inline uint32_t p_mul_lo(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b); }
+inline uint32_t p_mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline uint32_t emu_add(uint64_t a, uint64_t b, uint64_t cin, bool set_cc) {
+    uint64_t s = a + b + cin;
+    if (set_cc) host_cc().cf = (uint32_t)(s >> 32);
+    else if (s >> 32) host_cc().lost++;
+    return (uint32_t)s;
+}
+inline uint32_t emu_sub(uint64_t a, uint64_t b, uint64_t bin, bool set_cc) {
+    uint64_t s = a - b - bin;
+    if (set_cc) host_cc().cf = (uint32_t)((s >> 32) & 1);
+    return (uint32_t)s;
+}
+inline uint32_t p_add_cc(uint32_t a, uint32_t b) { return emu_add(a, b, 0, true); }
+inline uint32_t p_addc_cc(uint32_t a, uint32_t b) { return emu_add(a, b, host_cc().cf, true); }
+inline uint32_t p_addc(uint32_t a, uint32_t b) { return emu_add(a, b, host_cc().cf, false); }
+inline uint32_t p_sub_cc(uint32_t a, uint32_t b) { return emu_sub(a, b, 0, true); }
+inline uint32_t p_subc_cc(uint32_t a, uint32_t b) { return emu_sub(a, b, host_cc().cf, true); }
+inline uint32_t p_subc(uint32_t a, uint32_t b) { return emu_sub(a, b, host_cc().cf, false); }
+inline uint32_t p_mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(p_mul_lo(a, b), c, 0, true); }
+inline uint32_t p_mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(p_mul_hi(a, b), c, 0, true); }
+inline uint32_t p_madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(p_mul_lo(a, b), c, host_cc().cf, true); }
+inline uint32_t p_madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(p_mul_hi(a, b), c, host_cc().cf, true); }
+inline uint32_t p_madc_hi(uint32_t a, uint32_t b, uint32_t c) { return emu_add(p_mul_hi(a, b), c, host_cc().cf, false); }
+
+#endif
+
+// ---------------------------------------------------------------------------
+// field parameters.  Moduli pinned in-tree by the reference:
+//   r: /root/reference/compiler/src/algebra/fs.rs:15-16, prover/src/groth16/ethereum.rs:173
+//   q: /root/reference/prover/src/groth16/ethereum.rs:37
+// R, R^2 and -p^-1 mod 2^32 are derived and re-derived by
+// tests/test_ff_host.py from the moduli with python integers.
+// ---------------------------------------------------------------------------
+struct FrParams {
+    static ZA_HD constexpr uint32_t mod(int i) {
+        constexpr uint32_t m[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                                   0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return m[i];
+    }
+    static ZA_HD constexpr uint32_t one(int i) {  // R mod r
+        constexpr uint32_t m[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+                                   0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return m[i];
+    }
+    static ZA_HD constexpr uint32_t r2(int i) {  // R^2 mod r
+        constexpr uint32_t m[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+                                   0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+        return m[i];
+    }
+    static constexpr uint32_t inv = 0xefffffffu;  // -r^-1 mod 2^32
+};
+
+struct FqParams {
+    static ZA_HD constexpr uint32_t mod(int i) {
+        constexpr uint32_t m[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u,
+                                   0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return m[i];
+    }
+    static ZA_HD constexpr uint32_t one(int i) {
+        constexpr uint32_t m[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+                                   0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return m[i];
+    }
+    static ZA_HD constexpr uint32_t r2(int i) {
+        constexpr uint32_t m[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u,
+                                   0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+        return m[i];
+    }
+    static constexpr uint32_t inv = 0xe4866389u;  // -q^-1 mod 2^32
+};
+
+// ---------------------------------------------------------------------------
+// Fp<P>: value in [0, p), Montgomery form, little-endian 32-bit limbs.
+// Memory image == ff_ce's 4 x u64 little-endian Montgomery limbs.
+// ---------------------------------------------------------------------------
+template <class P>
+struct alignas(16) Fp {
+    uint32_t v[8];
+
+    static ZA_HD Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = 0;
+        return r;
+    }
+    static ZA_HD Fp one() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = P::one(i);
+        return r;
+    }
+    static ZA_HD Fp r2() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = P::r2(i);
+        return r;
+    }
+    ZA_HD bool is_zero() const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o |= v[i];
+        return o == 0;
+    }
+    ZA_HD bool operator==(const Fp& b) const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o |= v[i] ^ b.v[i];
+        return o == 0;
+    }
+    ZA_HD bool operator!=(const Fp& b) const { return !(*this == b); }
+};
+
+// r = (x >= p) ? x - p : x      (x < 2p < 2^256)
+template <class P>
+ZA_HD void fp_final_sub(uint32_t* x) {
+    uint32_t t[8];
+    t[0] = p_sub_cc(x[0], P::mod(0));
+#pragma unroll
+    for (int i = 1; i < 8; i++) t[i] = p_subc_cc(x[i], P::mod(i));
+    uint32_t borrow = p_subc(0u, 0u);  // 0 or 0xffffffff
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = borrow ? x[i] : t[i];
+}
+
+template <class P>
+ZA_HD Fp<P> fp_add(const Fp<P>& a, const Fp<P>& b) {
+    Fp<P> r;
+    r.v[0] = p_add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = p_addc_cc(a.v[i], b.v[i]);
+    r.v[7] = p_addc(a.v[7], b.v[7]);
+    fp_final_sub<P>(r.v);
+    return r;
+}
+
+template <class P>
+ZA_HD Fp<P> fp_sub(const Fp<P>& a, const Fp<P>& b) {
+    Fp<P> r;
+    r.v[0] = p_sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) r.v[i] = p_subc_cc(a.v[i], b.v[i]);
+    uint32_t borrow = p_subc(0u, 0u);
+    r.v[0] = p_add_cc(r.v[0], P::mod(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = p_addc_cc(r.v[i], P::mod(i) & borrow);
+    // the carry out of the top limb cancels the earlier borrow and is discarded on purpose
+    r.v[7] = p_addc_cc(r.v[7], P::mod(7) & borrow);
+    return r;
+}
+
+template <class P>
+ZA_HD Fp<P> fp_neg(const Fp<P>& a) {
+    if (a.is_zero()) return a;
+    Fp<P> r;
+    r.v[0] = p_sub_cc(P::mod(0), a.v[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = p_subc_cc(P::mod(i), a.v[i]);
+    r.v[7] = p_subc(P::mod(7), a.v[7]);
+    return r;
+}
+
+template <class P>
+ZA_HD Fp<P> fp_dbl(const Fp<P>& a) { return fp_add<P>(a, a); }
+
+// One CIOS round: (E,O) += a*bi ; (E,O) += m*q ; implicit >>32 by role swap.
+// Value represented: sum E[j] 2^(32j) + sum O[j] 2^(32(j+1)).
+template <class P, bool FIRST>
+ZA_HD void fp_mad_redc(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi) {
+    if (FIRST) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            O[j] = p_mul_lo(a[j + 1], bi);
+            O[j + 1] = p_mul_hi(a[j + 1], bi);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            E[j] = p_mul_lo(a[j], bi);
+            E[j + 1] = p_mul_hi(a[j], bi);
+        }
+    } else {
+        // O still holds the previous round's low word (now weight 2^0) in O[1].
+        E[0] = p_add_cc(E[0], O[1]);
+#pragma unroll
+        for (int j = 0; j < 6; j += 2) {
+            O[j] = p_madc_lo_cc(a[j + 1], bi, O[j + 2]);
+            O[j + 1] = p_madc_hi_cc(a[j + 1], bi, O[j + 3]);
+        }
+        O[6] = p_madc_lo_cc(a[7], bi, 0u);
+        O[7] = p_madc_hi(a[7], bi, 0u);
+        E[0] = p_mad_lo_cc(a[0], bi, E[0]);
+        E[1] = p_madc_hi_cc(a[0], bi, E[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            E[j] = p_madc_lo_cc(a[j], bi, E[j]);
+            E[j + 1] = p_madc_hi_cc(a[j], bi, E[j + 1]);
+        }
+        O[7] = p_addc(O[7], 0u);
+    }
+    uint32_t q = p_mul_lo(E[0], P::inv);
+    O[0] = p_mad_lo_cc(P::mod(1), q, O[0]);
+    O[1] = p_madc_hi_cc(P::mod(1), q, O[1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+        O[j] = p_madc_lo_cc(P::mod(j + 1), q, O[j]);
+        O[j + 1] = (j == 6) ? p_madc_hi(P::mod(j + 1), q, O[j + 1]) : p_madc_hi_cc(P::mod(j + 1), q, O[j + 1]);
+    }
+    E[0] = p_mad_lo_cc(P::mod(0), q, E[0]);
+    E[1] = p_madc_hi_cc(P::mod(0), q, E[1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+        E[j] = p_madc_lo_cc(P::mod(j), q, E[j]);
+        E[j + 1] = p_madc_hi_cc(P::mod(j), q, E[j + 1]);
+    }
+    O[7] = p_addc(O[7], 0u);
+}
+
+template <class P>
+ZA_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+    uint32_t ev[8], od[8];
+    fp_mad_redc<P, true>(ev, od, a.v, b.v[0]);
+    fp_mad_redc<P, false>(od, ev, a.v, b.v[1]);
+#pragma unroll
+    for (int i = 2; i < 8; i += 2) {
+        fp_mad_redc<P, false>(ev, od, a.v, b.v[i]);
+        fp_mad_redc<P, false>(od, ev, a.v, b.v[i + 1]);
+    }
+    Fp<P> r;
+    r.v[0] = p_add_cc(ev[0], od[1]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = p_addc_cc(ev[i], od[i + 1]);
+    r.v[7] = p_addc(ev[7], 0u);
+    fp_final_sub<P>(r.v);
+    return r;
+}
+
+template <class P>
+ZA_HD Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul<P>(a, a); }
+
+// canonical (non-Montgomery) little-endian limbs  <->  Montgomery
+template <class P>
+ZA_HD Fp<P> fp_to_mont(const Fp<P>& canonical) { return fp_mul<P>(canonical, Fp<P>::r2()); }
+template <class P>
+ZA_HD Fp<P> fp_from_mont(const Fp<P>& a) {
+    Fp<P> o = Fp<P>::zero();
+    o.v[0] = 1;
+    return fp_mul<P>(a, o);
+}
+
+// a^e, e given as 8 little-endian 32-bit words (not secret; variable time)
+template <class P>
+ZA_HD Fp<P> fp_pow(const Fp<P>& a, const uint32_t* e) {
+    Fp<P> r = Fp<P>::one();
+    bool started = false;
+    for (int i = 255; i >= 0; i--) {
+        if (started) r = fp_sqr<P>(r);
+        if ((e[i >> 5] >> (i & 31)) & 1u) {
+            r = started ? fp_mul<P>(r, a) : a;
+            started = true;
+        }
+    }
+    return r;
+}
+
+// a^-1 = a^(p-2)   (0 -> 0)
+template <class P>
+ZA_HD Fp<P> fp_inv(const Fp<P>& a) {
+    uint32_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) e[i] = P::mod(i);
+    e[0] -= 2;  // both moduli end in ...01 / ...47: no borrow
+    return fp_pow<P>(a, e);
+}
+
+template <class P>
+ZA_HD Fp<P> fp_from_u64(uint64_t x) {
+    Fp<P> c = Fp<P>::zero();
+    c.v[0] = (uint32_t)x;
+    c.v[1] = (uint32_t)(x >> 32);
+    return fp_to_mont<P>(c);
+}
+
+// true iff canonical limbs < p
+template <class P>
+ZA_HD bool fp_is_canonical(const uint32_t* x) {
+    for (int i = 7; i >= 0; i--) {
+        if (x[i] < P::mod(i)) return true;
+        if (x[i] > P::mod(i)) return false;
+    }
+    return false;
+}
+
+typedef Fp<FrParams> Fr;
+typedef Fp<FqParams> Fq;
+
+// operator sugar shared by Fq and Fq2 so the curve templates read naturally
+template <class P> ZA_HD Fp<P> operator+(const Fp<P>& a, const Fp<P>& b) { return fp_add<P>(a, b); }
+template <class P> ZA_HD Fp<P> operator-(const Fp<P>& a, const Fp<P>& b) { return fp_sub<P>(a, b); }
+template <class P> ZA_HD Fp<P> operator*(const Fp<P>& a, const Fp<P>& b) { return fp_mul<P>(a, b); }
+template <class P> ZA_HD Fp<P> operator-(const Fp<P>& a) { return fp_neg<P>(a); }
+template <class P> ZA_HD Fp<P> sqr(const Fp<P>& a) { return fp_sqr<P>(a); }
+template <class P> ZA_HD Fp<P> dbl(const Fp<P>& a) { return fp_dbl<P>(a); }
+template <class P> ZA_HD Fp<P> inv(const Fp<P>& a) { return fp_inv<P>(a); }
+
+// ---------------------------------------------------------------------------
+// Fq2 = Fq[u]/(u^2+1)   (pairing_ce bn256::Fq2, used at format.rs:57-64)
+// ---------------------------------------------------------------------------
+struct Fq2 {
+    Fq c0, c1;
+    static ZA_HD Fq2 zero() { Fq2 r; r.c0 = Fq::zero(); r.c1 = Fq::zero(); return r; }
+    static ZA_HD Fq2 one() { Fq2 r; r.c0 = Fq::one(); r.c1 = Fq::zero(); return r; }
+    ZA_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    ZA_HD bool operator==(const Fq2& b) const { return c0 == b.c0 && c1 == b.c1; }
+    ZA_HD bool operator!=(const Fq2& b) const { return !(*this == b); }
+};
+ZA_HD Fq2 operator+(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; return r; }
+ZA_HD Fq2 operator-(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; return r; }
+ZA_HD Fq2 operator-(const Fq2& a) { Fq2 r; r.c0 = -a.c0; r.c1 = -a.c1; return r; }
+ZA_HD Fq2 dbl(const Fq2& a) { Fq2 r; r.c0 = dbl(a.c0); r.c1 = dbl(a.c1); return r; }
+// Karatsuba: 3 Fq products
+ZA_HD Fq2 operator*(const Fq2& a, const Fq2& b) {
+    Fq aa = a.c0 * b.c0;
+    Fq bb = a.c1 * b.c1;
+    Fq s = (a.c0 + a.c1) * (b.c0 + b.c1);
+    Fq2 r;
+    r.c0 = aa - bb;
+    r.c1 = s - aa - bb;
+    return r;
+}
+// complex squaring: 2 Fq products
+ZA_HD Fq2 sqr(const Fq2& a) {
+    Fq t = a.c0 * a.c1;
+    Fq2 r;
+    r.c0 = (a.c0 + a.c1) * (a.c0 - a.c1);
+    r.c1 = dbl(t);
+    return r;
+}
+ZA_HD Fq2 inv(const Fq2& a) {
+    Fq n = inv(sqr(a.c0) + sqr(a.c1));
+    Fq2 r;
+    r.c0 = a.c0 * n;
+    r.c1 = -(a.c1 * n);
+    return r;
+}
+
+}  // namespace za
