@@ -1,0 +1,157 @@
+/* za_b200 — C ABI of the B200-native Groth16 proving backend for za.
+ *
+ * This is the drop-in boundary.  The reference has no plugin API: its hot path sits
+ * behind (inner) the Rust calls that /root/reference/prover/src/groth16/prover.rs makes into
+ * bellman_ce/pairing_ce and (outer) the C ABI of binding/c.  A Rust toolchain is not available in the
+ * build image, so the seam is expressed as plain C: handles, caller-owned buffers, int status codes and
+ * za_last_error().  Each entry point names the reference interface it replaces.  INTEGRATION.md shows
+ * the `extern "C"` block a maintainer adds to the prover crate to bind them.
+ *
+ * Encodings at the seam
+ *   Fr scalar  : 32 bytes little-endian canonical integer (== FrRepr([u64;4]) memory image,
+ *                what `into_repr()` yields at bellman's multiexp boundary)
+ *   G1 affine  : 64 bytes  x || y, 32-byte LE canonical each; 64 zero bytes = infinity
+ *   G2 affine  : 128 bytes x.c0 || x.c1 || y.c0 || y.c1;     128 zero bytes = infinity
+ *   proof      : a (64) || b (128) || c (64)
+ *   Parameters : the exact byte stream bellman's Parameters::write produces (big-endian
+ *                uncompressed points, u32 BE counts) — /root/reference/prover/src/groth16/format.rs:250,285
+ *
+ * All functions return ZA_OK (0) or a negative ZA_ERR_* code; za_last_error() gives the text.
+ * Nothing here falls back to a CPU implementation: without a CUDA device every compute entry
+ * point fails with ZA_ERR_CUDA.
+ */
+#ifndef ZA_B200_H
+#define ZA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct za_ctx za_ctx;     /* one per GPU: stream, cached NTT domains, scratch */
+typedef struct za_bases za_bases; /* a device-resident array of G1 or G2 affine bases (Montgomery form) */
+typedef struct za_pk za_pk;       /* device-resident bellman Parameters (vk on host, queries on device) */
+typedef struct za_circuit za_circuit; /* device-resident constraint system + its density maps */
+
+enum {
+    ZA_OK = 0,
+    ZA_ERR_CUDA = -1,                 /* no device / CUDA failure */
+    ZA_ERR_INVALID = -2,              /* bad argument */
+    ZA_ERR_UNEXPECTED_IDENTITY = -3,  /* SynthesisError::UnexpectedIdentity */
+    ZA_ERR_POLY_DEGREE_TOO_LARGE = -4,/* SynthesisError::PolynomialDegreeTooLarge (domain >= 2^28) */
+    ZA_ERR_IO = -5,                   /* short / malformed Parameters stream, query too short */
+    ZA_ERR_NOT_ON_CURVE = -6,
+    ZA_ERR_NOT_IN_SUBGROUP = -7,
+    ZA_ERR_BAD_ENCODING = -8,
+    ZA_ERR_BUFFER_TOO_SMALL = -9,
+    ZA_ERR_NOT_CANONICAL = -10        /* a scalar >= r was passed */
+};
+
+#define ZA_VAR_AUX 0x80000000u /* constraint term variable: bit 31 set = aux index, else input index */
+
+/* What bellman's ConstraintSystem receives from CircomCircuit::synthesize
+ * (/root/reference/prover/src/groth16/prover.rs:45-103): the enforce(A, B, C) rows as three CSR
+ * matrices, terms in insertion order.  Input 0 is the constant `one`; C already carries the sign
+ * flip of prover.rs:98.  The input-consistency rows bellman appends are added internally. */
+typedef struct {
+    uint32_t num_inputs;      /* including `one` */
+    uint32_t num_aux;
+    uint32_t num_constraints;
+    const uint32_t *ptr[3];   /* [num_constraints + 1] term offsets for A, B, C */
+    const uint32_t *var[3];   /* variable of each term */
+    const uint8_t *coeff[3];  /* 32-byte LE canonical coefficient of each term */
+} za_r1cs;
+
+/* Optional intermediates of za_create_proof for element-wise parity checks; any pointer may be NULL. */
+typedef struct {
+    uint8_t *a_eval, *b_eval, *c_eval; /* (num_constraints + num_inputs) * 32 */
+    uint8_t *h_coeffs;                 /* (m - 1) * 32 */
+    uint8_t *msm_g1;                   /* 7 * 64: h, l, a_inputs, a_aux, b1_inputs, b1_aux, (unused) */
+    uint8_t *msm_g2;                   /* 2 * 128: b2_inputs, b2_aux */
+    uint8_t *a_aux_density, *b_input_density, *b_aux_density; /* one byte per variable */
+} za_trace;
+
+/* ---- context ------------------------------------------------------------------------------ */
+const char *za_last_error(void);
+int za_version(void);
+int za_device_count(void);
+int za_ctx_create(int device, za_ctx **out);
+void za_ctx_destroy(za_ctx *ctx);
+/* Issue all work of this context on `cuda_stream` (a cudaStream_t; NULL restores the context's own). */
+int za_ctx_set_stream(za_ctx *ctx, void *cuda_stream);
+int za_ctx_synchronize(za_ctx *ctx);
+/* Kernels launched through this context so far (bench.py reports the delta as gpu_launches). */
+uint64_t za_ctx_launch_count(const za_ctx *ctx);
+
+/* ---- EvaluationDomain --------------------------------------------------------------------
+ * Replaces bellman_ce domain.rs EvaluationDomain::{fft, ifft, coset_fft, icoset_fft} as used by
+ * create_proof (entered at prover.rs:173).  Natural order in and out, like bellman's.
+ * mode: 0 fft, 1 ifft, 2 coset_fft, 3 icoset_fft. */
+enum { ZA_NTT_FFT = 0, ZA_NTT_IFFT = 1, ZA_NTT_COSET_FFT = 2, ZA_NTT_ICOSET_FFT = 3 };
+/* host buffer of 2^log_n canonical scalars, transformed in place (H2D + D2H inside) */
+int za_ntt(za_ctx *ctx, uint8_t *data, int log_n, int mode);
+/* device-resident: `d_data` holds `batch` vectors of 2^log_n Montgomery-form Fr (32 B each), in place */
+int za_ntt_device(za_ctx *ctx, void *d_data, int log_n, int mode, int batch);
+/* canonical <-> Montgomery on device, n elements in place (dir 0: to Montgomery, 1: to canonical) */
+int za_fr_convert_device(za_ctx *ctx, void *d_data, size_t n, int dir);
+/* create_proof's H block: a, b, c evaluations (len each, canonical, host) -> h coefficients
+ * ((m-1) * 32 bytes, m = next power of two >= len).  checkpoints (optional, 8*m*32 bytes) receives
+ * a.ifft, a.coset_fft, b.ifft, b.coset_fft, c.ifft, c.coset_fft, (a*b-c)/Z, icoset_fft — computed by
+ * the unfused transforms so every intermediate vector can be compared with the reference's. */
+int za_h_poly(za_ctx *ctx, const uint8_t *a, const uint8_t *b, const uint8_t *c, size_t len,
+              uint8_t *h_out, uint8_t *checkpoints);
+/* device-resident fused version: d_a/d_b/d_c hold m Montgomery Fr each (zero padded), result
+ * (canonical form, m entries of which the first m-1 are the h scalars) is left in d_a. */
+int za_h_poly_device(za_ctx *ctx, void *d_a, void *d_b, void *d_c, int log_m);
+
+/* ---- multiexp ------------------------------------------------------------------------------
+ * Replaces bellman_ce multiexp.rs `multiexp(pool, (bases, skip), density, exponents)`.
+ * group: 1 = G1, 2 = G2. */
+int za_bases_upload(za_ctx *ctx, int group, const uint8_t *bases, size_t n, za_bases **out);
+void za_bases_free(za_bases *b);
+size_t za_bases_len(const za_bases *b);
+/* sum over i of scalars[i] * bases[offset + k(i)], where k(i) counts the set density entries before i
+ * (density == NULL: FullDensity, k(i) = i).  scalars: n_exp canonical 32-byte values on the host.
+ * out: affine point (64 or 128 bytes).  Errors like bellman: ZA_ERR_IO if the bases run out. */
+int za_multiexp(za_ctx *ctx, const za_bases *bases, size_t offset, const uint8_t *scalars, size_t n_exp,
+                const uint8_t *density, uint8_t *out);
+/* device-resident scalars (canonical 32-byte LE, n of them, FullDensity) */
+int za_multiexp_device(za_ctx *ctx, const za_bases *bases, size_t offset, const void *d_scalars, size_t n,
+                       uint8_t *out);
+/* Multi-GPU building block: like za_multiexp_device but returns the unnormalised partial
+ * sum as XYZZ coordinates in canonical form (4 x 32 bytes G1, 4 x 64 bytes G2) so that per-GPU partial
+ * results can be added on the host with za_point_sum. */
+int za_multiexp_partial_device(za_ctx *ctx, const za_bases *bases, size_t offset, const void *d_scalars,
+                               size_t n, uint8_t *out_xyzz);
+/* host: add `count` XYZZ partial sums and normalise to affine */
+int za_point_sum(int group, const uint8_t *xyzz, size_t count, uint8_t *out_affine);
+
+/* ---- Groth16 -------------------------------------------------------------------------------
+ * za_pk_load replaces bellman Parameters::read(reader, checked) (format.rs:285): parses the byte
+ * stream, converts to Montgomery form on the GPU, rejects off-curve points, points at infinity in the
+ * queries and (checked != 0) G2 points outside the r-torsion. */
+int za_pk_load(za_ctx *ctx, const uint8_t *params, size_t len, int checked, za_pk **out);
+void za_pk_free(za_pk *pk);
+/* counts[6] = |ic|, |h|, |l|, |a|, |b_g1|, |b_g2| */
+int za_pk_counts(const za_pk *pk, uint32_t *counts);
+/* vk_out: alpha_g1 (64) beta_g1 (64) beta_g2 (128) gamma_g2 (128) delta_g1 (64) delta_g2 (128) ic (64 each),
+ * interchange encoding — what JsonVerifyingKey::from_bellman (format.rs:143-160) reads from params.vk */
+int za_pk_vk(const za_pk *pk, uint8_t *vk_out, size_t size);
+/* The constraint system is what CircomCircuit::synthesize feeds bellman (prover.rs:45-103).  It is
+ * uploaded once per circuit: the CSR matrices, and the density maps of bellman's ProvingAssignment,
+ * which depend only on the constraint structure. */
+int za_circuit_upload(za_ctx *ctx, const za_r1cs *cs, za_circuit **out);
+void za_circuit_free(za_circuit *c);
+/* Replaces bellman groth16::create_proof(circuit, params, r, s) (create_random_proof at prover.rs:173
+ * is this with r, s drawn from the RNG).  inputs: num_inputs canonical scalars (inputs[0] = 1),
+ * aux: num_aux.  proof_out: 256 bytes. */
+int za_create_proof(za_ctx *ctx, const za_pk *pk, const za_circuit *circuit, const uint8_t *inputs, const uint8_t *aux,
+                    const uint8_t *r, const uint8_t *s, uint8_t *proof_out, za_trace *trace);
+/* JsonProofAndInput (format.rs:80-128): compact JSON, "0x"+64 hex coordinates, decimal public inputs.
+ * public_inputs: n canonical scalars. Returns ZA_ERR_BUFFER_TOO_SMALL if len >= size (binding/c lib.rs:23). */
+int za_proof_to_json(const uint8_t *proof, const uint8_t *public_inputs, size_t n_public, char *buf, size_t size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,6 +1,7 @@
 // Host build of za_b200/csrc/ff.cuh + ec.cuh for CPU-side unit tests (no GPU needed).
 // Test infrastructure only: exercises the exact limb schedule the device runs,
 // on the emulated carry flag.
+#define ZA_FF_EMULATE_PTX 1
 #include "../../za_b200/csrc/ff.cuh"
 #include <string.h>
 using namespace za;
@@ -25,4 +26,18 @@ UNOP(shim_fq_from_mont, Fq, fp_from_mont(x))
 BINOP(shim_fq2_mul, Fq2, x * y)
 UNOP(shim_fq2_sqr, Fq2, sqr(x))
 UNOP(shim_fq2_inv, Fq2, inv(x))
+}
+#include "../../za_b200/csrc/ec.cuh"
+extern "C" {
+static G1Affine ld_aff(const uint32_t* p) { G1Affine a; memcpy(&a, p, sizeof a); return a; }
+static void st_aff(uint32_t* p, const G1Affine& a) { memcpy(p, &a, sizeof a); }
+void shim_g1_add_mixed(const uint32_t* a, const uint32_t* b, uint32_t* r) {
+    G1XYZZ acc = G1XYZZ::from_affine(ld_aff(a)); xyzz_madd<Fq>(acc, ld_aff(b)); st_aff(r, xyzz_to_affine<Fq>(acc));
+}
+void shim_g1_add(const uint32_t* a, const uint32_t* b, uint32_t* r) {
+    G1XYZZ acc = G1XYZZ::from_affine(ld_aff(a)); xyzz_add<Fq>(acc, G1XYZZ::from_affine(ld_aff(b))); st_aff(r, xyzz_to_affine<Fq>(acc));
+}
+void shim_g1_mul(const uint32_t* a, const uint32_t* k, uint32_t* r) {
+    st_aff(r, xyzz_to_affine<Fq>(xyzz_mul<Fq>(G1XYZZ::from_affine(ld_aff(a)), k)));
+}
 }

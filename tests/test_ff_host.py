@@ -1,0 +1,106 @@
+"""CPU: the device limb schedule of za_b200/csrc/ff.cuh run on the host through the emulated PTX carry
+flag (ZA_FF_EMULATE_PTX), and the fast 64-bit host path, both against python integers."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+from tests import pyref as P
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc", "ff_host_shim.cpp")
+A = ctypes.c_uint32 * 8
+A2 = ctypes.c_uint32 * 16
+R = 1 << 256
+
+
+def _build(tag, defs):
+    out = os.path.join(HERE, "csrc", f"libffhost_{tag}.so")
+    deps = [SRC, os.path.join(HERE, "..", "za_b200", "csrc", "ff.cuh")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++"] + defs + [SRC, "-o", out])
+    L = ctypes.CDLL(out)
+    L.shim_lost_carries.restype = ctypes.c_uint64
+    return L
+
+
+@pytest.fixture(scope="module", params=["emu", "fast"])
+def shim(request):
+    return _build(request.param, ["-DZA_FF_EMULATE_PTX=1"] if request.param == "emu" else [])
+
+
+def tol(x): return A(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+def frl(a): return sum(int(a[i]) << (32 * i) for i in range(len(a)))
+
+
+def binop(L, fn, x, y):
+    o = A(); getattr(L, fn)(tol(x), tol(y), o); return frl(o)
+
+
+def unop(L, fn, x):
+    o = A(); getattr(L, fn)(tol(x), o); return frl(o)
+
+
+def test_derived_constants():
+    # R, R^2, -p^-1 of ff.cuh re-derived from the moduli
+    for p, one0, inv in ((P.R_MOD, 0x4ffffffb, 0xefffffff), (P.Q_MOD, 0xc58f0d9d, 0xe4866389)):
+        assert (R % p) & 0xFFFFFFFF == one0
+        assert (-pow(p, -1, 1 << 32)) % (1 << 32) == inv
+
+
+@pytest.mark.parametrize("name,p", [("fr", P.R_MOD), ("fq", P.Q_MOD)])
+def test_field_ops(shim, name, p):
+    rng = random.Random(1)
+    Ri = pow(R, -1, p)
+    edge = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, R % p, (R * R) % p, 1 << 253, p - (1 << 200)]
+    vals = edge + [rng.randrange(p) for _ in range(150)]
+    for x in vals:
+        for y in rng.sample(vals, 8) + edge:
+            assert binop(shim, f"shim_{name}_mul", x, y) == x * y * Ri % p
+            assert binop(shim, f"shim_{name}_add", x, y) == (x + y) % p
+            assert binop(shim, f"shim_{name}_sub", x, y) == (x - y) % p
+        assert unop(shim, f"shim_{name}_neg", x) == (-x) % p
+        assert unop(shim, f"shim_{name}_to_mont", x) == x * R % p
+        assert unop(shim, f"shim_{name}_from_mont", x) == x * Ri % p
+    for x in vals[:12]:
+        assert unop(shim, f"shim_{name}_inv", x * R % p) == (pow(x, -1, p) * R % p if x else 0)
+    assert shim.shim_lost_carries() == 0, "a carry was dropped by an instruction that cannot report it"
+
+
+def test_fq2_ops(shim):
+    rng = random.Random(2)
+    q = P.Q_MOD
+    def mont2(a): return (a[0] * R % q, a[1] * R % q)
+    def pack(a): return A2(*[(v >> (32 * i)) & 0xFFFFFFFF for v in a for i in range(8)])
+    def unpack(o): return (frl(o[:8]), frl(o[8:]))
+    for _ in range(50):
+        a = (rng.randrange(q), rng.randrange(q)); b = (rng.randrange(q), rng.randrange(q))
+        o = A2(); shim.shim_fq2_mul(pack(mont2(a)), pack(mont2(b)), o)
+        assert unpack(o) == mont2(P.f2_mul(a, b))
+        o = A2(); shim.shim_fq2_sqr(pack(mont2(a)), o)
+        assert unpack(o) == mont2(P.f2_mul(a, a))
+        o = A2(); shim.shim_fq2_inv(pack(mont2(a)), o)
+        assert unpack(o) == mont2(P.f2_inv(a))
+
+
+def test_curve_ops_host(shim):
+    """XYZZ formulas of ec.cuh on the host, including the exceptional cases."""
+    rng = random.Random(3)
+    q = P.Q_MOD
+    PT = ctypes.c_uint32 * 16
+    def pack(p): return PT(*([0] * 16)) if p is None else PT(*[((v * R % q) >> (32 * i)) & 0xFFFFFFFF for v in p for i in range(8)])
+    def unpack(o):
+        x, y = frl(o[:8]), frl(o[8:])
+        Ri = pow(R, -1, q)
+        return None if x == 0 and y == 0 else (x * Ri % q, y * Ri % q)
+    g = P.G1_GEN
+    p5, p7 = P.g1_mul(g, 5), P.g1_mul(g, 7)
+    cases = [(p5, p7), (p5, p5), (p5, P.ec_neg(P.Fq1Ops, p5)), (None, p7), (p5, None), (None, None)]
+    for a, b in cases:
+        o = PT(); shim.shim_g1_add_mixed(pack(a), pack(b), o); assert unpack(o) == P.g1_add(a, b), ("madd", a, b)
+        o = PT(); shim.shim_g1_add(pack(a), pack(b), o); assert unpack(o) == P.g1_add(a, b), ("add", a, b)
+    k = rng.randrange(P.R_MOD)
+    o = PT(); shim.shim_g1_mul(pack(p5), tol(k), o); assert unpack(o) == P.g1_mul(p5, k)
+    o = PT(); shim.shim_g1_mul(pack(p5), tol(P.R_MOD), o); assert unpack(o) is None

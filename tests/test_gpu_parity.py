@@ -1,0 +1,251 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact or fail — everything here is integer arithmetic."""
+import numpy as np
+import pytest
+
+from tests import oracle as O
+from tests import pyref as P
+from tests import circuits
+
+pytestmark = pytest.mark.gpu
+
+
+def test_library_reports_device(ctx):
+    from za_b200 import _lib
+    assert _lib.lib().za_device_count() >= 1
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 4, 5, 8, 10, 11, 12, 13, 16, 18])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_ntt_matches_oracle(ctx, log_n, mode):
+    n = 1 << log_n
+    d = O.random_frs(n, 100 + log_n)
+    got = ctx.ntt(d, mode)
+    exp = O.fft(d, log_n, mode, threads=8)
+    assert np.array_equal(got, exp)
+
+
+def test_ntt_edge_values(ctx):
+    # all zeros, all r-1, a single one
+    n = 1 << 12
+    z = np.zeros((n, 32), np.uint8)
+    assert np.array_equal(ctx.fft(z), z)
+    top = np.tile(np.frombuffer((P.R_MOD - 1).to_bytes(32, "little"), np.uint8), (n, 1))
+    assert np.array_equal(ctx.coset_fft(top), O.fft(top, 12, 2))
+    e = z.copy(); e[5, 0] = 1
+    assert np.array_equal(ctx.ifft(e), O.fft(e, 12, 1))
+
+
+def test_ntt_rejects_non_canonical(ctx):
+    import za_b200
+    bad = np.full((8, 32), 0xFF, np.uint8)
+    with pytest.raises(za_b200.ZaError):
+        ctx.fft(bad)
+
+
+def test_ntt_roundtrip_large(ctx):
+    # size-independent property at a BASELINE size: icoset_fft(coset_fft(x)) == x, ifft(fft(x)) == x
+    log_n = 22
+    d = O.random_frs(1 << log_n, 7)
+    assert np.array_equal(ctx.ifft(ctx.fft(d)), d)
+    assert np.array_equal(ctx.icoset_fft(ctx.coset_fft(d)), d)
+
+
+def test_ntt_spot_evaluation_large(ctx):
+    # fft output k is the polynomial evaluated at omega^k: check a few k by Horner in python ints
+    log_n = 14
+    n = 1 << log_n
+    d = O.random_frs(n, 9)
+    got = O.np_to_frs(ctx.fft(d))
+    coeffs = O.np_to_frs(d)
+    w = P.omega(log_n)
+    for k in (0, 1, 77, n - 1):
+        x = pow(w, k, P.R_MOD)
+        acc = 0
+        for c in reversed(coeffs):
+            acc = (acc * x + c) % P.R_MOD
+        assert got[k] == acc
+
+
+@pytest.mark.parametrize("length", [1, 3, 4, 5, 100, 2048, 5000, (1 << 16) - 3])
+def test_h_poly_matches_oracle(ctx, length):
+    a, b, c = (O.random_frs(length, s) for s in (1, 2, 3))
+    got, ck = ctx.h_poly(a, b, c, checkpoints=True)
+    exp, eck = O.h_poly(a, b, c, threads=8, checkpoints=True)
+    assert np.array_equal(ck, eck), "an intermediate EvaluationDomain vector differs"
+    assert np.array_equal(got, exp)
+    fused = ctx.h_poly(a, b, c)
+    assert np.array_equal(fused, exp), "fused pipeline differs from bellman's sequence"
+
+
+def _msm_case(ctx, group, n, scalars, density=None, offset=0, nbases=None):
+    import za_b200
+    nbases = nbases or n
+    pts = O.g1_multiples(nbases) if group == 1 else O.g2_multiples(nbases)
+    bases = za_b200.Bases(ctx, group, pts)
+    got = za_b200.multiexp(ctx, bases, scalars, density=density, offset=offset)
+    rc, exp = O.multiexp("g1" if group == 1 else "g2", pts[offset:], scalars, density=density, threads=8)
+    assert rc == 0
+    assert got == exp
+    return got
+
+
+@pytest.mark.parametrize("group", [1, 2])
+@pytest.mark.parametrize("n", [1, 2, 31, 64, 65, 100, 1000, 5000])
+def test_multiexp_matches_oracle_uniform(ctx, group, n):
+    _msm_case(ctx, group, n, O.random_frs(n, 40 + n))
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_multiexp_witness_like(ctx, group):
+    n = 20000 if group == 1 else 6000
+    _msm_case(ctx, group, n, circuits.witness_like(n, 5))
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_multiexp_edge_scalars(ctx, group):
+    n = 300
+    s = O.random_frs(n, 3)
+    s[0] = 0
+    s[1] = np.frombuffer((1).to_bytes(32, "little"), np.uint8)
+    s[2] = np.frombuffer((P.R_MOD - 1).to_bytes(32, "little"), np.uint8)      # maximum scalar: top signed window
+    s[3] = np.frombuffer((2 ** 253).to_bytes(32, "little"), np.uint8)
+    s[4] = np.frombuffer(((1 << 254) - 1 - ((1 << 254) - 1 - P.R_MOD + 1)).to_bytes(32, "little"), np.uint8)
+    s[5:40] = s[2]                                                            # many equal scalars -> one bucket, many adds
+    _msm_case(ctx, group, n, s)
+    zeros = np.zeros((n, 32), np.uint8)
+    assert _msm_case(ctx, group, n, zeros) == b"\0" * (64 if group == 1 else 128)
+
+
+def test_multiexp_duplicate_and_opposite_points(ctx):
+    # P = bucket (doubling branch) and P = -bucket (infinity branch) inside one bucket
+    import za_b200
+    n = 200
+    pts = O.g1_multiples(n)
+    pts[1::2] = pts[0::2]                      # every point twice
+    neg = pts[10].copy()
+    y = int.from_bytes(neg[32:].tobytes(), "little")
+    neg[32:] = np.frombuffer((P.Q_MOD - y).to_bytes(32, "little"), np.uint8)
+    pts[11] = neg                              # an opposite pair
+    s = O.random_frs(n, 77)
+    s[1::2] = s[0::2]                          # same scalar -> same buckets
+    bases = za_b200.Bases(ctx, 1, pts)
+    got = za_b200.multiexp(ctx, bases, s)
+    rc, exp = O.multiexp("g1", pts, s, threads=4)
+    assert rc == 0 and got == exp
+
+
+def test_multiexp_density_and_offset(ctx):
+    n_exp = 3000
+    rng = np.random.default_rng(1)
+    dens = (rng.random(n_exp) < 0.6).astype(np.uint8)
+    cnt = int(dens.sum())
+    for group in (1, 2):
+        _msm_case(ctx, group, n_exp, O.random_frs(n_exp, 11), density=dens, offset=7, nbases=cnt + 7)
+
+
+def test_multiexp_errors_like_bellman(ctx):
+    import za_b200
+    pts = O.g1_multiples(10)
+    bases = za_b200.Bases(ctx, 1, pts)
+    with pytest.raises(za_b200.ZaError) as e:            # bases run out -> io error (unexpected EOF)
+        za_b200.multiexp(ctx, bases, O.random_frs(11, 1))
+    assert e.value.code == -5
+    pts[3] = 0                                           # a base at infinity with a non-zero exponent
+    bases = za_b200.Bases(ctx, 1, pts)
+    with pytest.raises(za_b200.ZaError) as e:
+        za_b200.multiexp(ctx, bases, O.random_frs(10, 1))
+    assert e.value.code == -3
+    s = O.random_frs(10, 1); s[3] = 0                    # ... but a zero exponent skips it
+    rc, exp = O.multiexp("g1", pts, s)
+    assert rc == 0 and za_b200.multiexp(ctx, bases, s) == exp
+    off = O.g1_multiples(4); off[2, 0] ^= 1              # off-curve point
+    with pytest.raises(za_b200.ZaError) as e:
+        za_b200.Bases(ctx, 1, off)
+    assert e.value.code == -6
+
+
+def test_multiexp_linearity_large(ctx):
+    # bases (i+1)G: sum s_i (i+1) G == (sum s_i (i+1) mod r) G — one scalar multiplication checks 2^18 points
+    import za_b200
+    n = 1 << 18
+    pts = O.g1_multiples(n)
+    s = O.random_frs(n, 21)
+    bases = za_b200.Bases(ctx, 1, pts)
+    got = za_b200.multiexp(ctx, bases, s)
+    vals = s.view(np.uint64).reshape(n, 4)
+    tot = 0
+    for limb in range(4):
+        col = [int(x) for x in vals[:, limb]]
+        tot += sum(c * (i + 1) for i, c in enumerate(col)) << (64 * limb)
+    exp = O.g1_mul(P.G1_GEN, tot % P.R_MOD)
+    assert O.g1_tuple(got) == exp
+
+
+def _prove_case(ctx, cs_tuple, toxic, r, s, threads=8):
+    import za_b200
+    ni, na, ptr, var, coeff, inputs, aux = cs_tuple
+    ocs = O.CS(ni, na, ptr, var, coeff)
+    prm = O.Params.generate(ocs, toxic, threads=threads)
+    blob = prm.write()
+    rc, exp_proof, etr = prm.create_proof(ocs, inputs, aux, r, s, threads=threads, trace=True)
+    assert rc == 0
+    pk = za_b200.Parameters.read(ctx, blob, checked=True)
+    assert pk.counts() == prm.counts()
+    circ = za_b200.Circuit(ctx, ni, na, ptr, var, coeff)
+    proof, tr = za_b200.create_proof(ctx, pk, circ, inputs, aux, r, s, trace=True)
+    for k in ("a_eval", "b_eval", "c_eval", "a_aux_density", "b_input_density", "b_aux_density", "h_coeffs"):
+        assert np.array_equal(tr[k], etr[k]), k
+    assert np.array_equal(tr["msm_g1"][:6], etr["msm_g1"][:6]), "a G1 multiexp result differs"
+    assert np.array_equal(tr["msm_g2"], etr["msm_g2"]), "a G2 multiexp result differs"
+    assert proof == exp_proof
+    pub = [int.from_bytes(inputs[i].tobytes(), "little") for i in range(1, ni)]
+    assert prm.verify(proof, pub) == 1
+    bad = list(pub); bad[0] = (bad[0] + 1) % P.R_MOD
+    assert prm.verify(proof, bad) == 0
+    return proof, pub, prm
+
+
+def test_create_proof_example_circuit(ctx):
+    """Config 1: /root/reference/example/circuit.za with example/input.json (p=2, q=3, r=6)."""
+    import json, os, za_b200
+    cs = P.example_factor_circuit()
+    ocs = O.CS.from_rows(cs.num_inputs, cs.num_aux, cs.rows)
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "groth16_example.json")))
+    toxic = [int(x) for x in g["toxic"]]
+    inputs = O.frs_to_np([1, 6]).reshape(-1, 32); aux = O.frs_to_np([2, 3]).reshape(-1, 32)
+    proof, pub, prm = _prove_case(ctx, (2, 2, ocs.ptr, ocs.var, ocs.coeff, inputs, aux), toxic, int(g["r"]), int(g["s"]))
+    # against the committed closed-form golden proof and its json text
+    assert proof.hex() == g["proof_hex"]
+    assert za_b200.proof_to_json(proof, pub) == g["proof_json"]
+
+
+@pytest.mark.parametrize("nc", [5, 100, 1022, (1 << 12) - 2])
+def test_create_proof_mul_chain(ctx, nc):
+    toxic = [11 + nc, 12, 13, 14, 15 + nc]
+    _prove_case(ctx, circuits.mul_chain(nc, x0=7), toxic, r=123456789 + nc, s=987654321)
+
+
+def test_create_proof_config2_2pow16(ctx):
+    """Config 2: multiplication chain with 2^16 - 2 constraints (m = 2^16), end to end on one GPU."""
+    nc = (1 << 16) - 2
+    toxic = [0x5A410002, 3, 5, 7, 11]
+    _prove_case(ctx, circuits.mul_chain_fast(nc, x0=0x5A410002), toxic, r=2 ** 200 + 17, s=2 ** 100 + 3)
+
+
+def test_pk_load_rejects_bad_streams(ctx):
+    import za_b200
+    cs = P.example_factor_circuit()
+    ocs = O.CS.from_rows(cs.num_inputs, cs.num_aux, cs.rows)
+    blob = bytearray(O.Params.generate(ocs, [2, 3, 4, 5, 6]).write())
+    with pytest.raises(za_b200.ZaError) as e:
+        za_b200.Parameters.read(ctx, bytes(blob[:-10]))
+    assert e.value.code == -5
+    bad = bytearray(blob); bad[40] ^= 1                       # alpha_g1.y corrupted -> off curve
+    with pytest.raises(za_b200.ZaError) as e:
+        za_b200.Parameters.read(ctx, bytes(bad))
+    assert e.value.code in (-6, -8)
+    bad = bytearray(blob); bad[0] |= 0x80                     # compressed flag
+    with pytest.raises(za_b200.ZaError) as e:
+        za_b200.Parameters.read(ctx, bytes(bad))
+    assert e.value.code == -8

@@ -1,0 +1,198 @@
+"""CPU: the C oracle against the committed golden vectors (tests/golden/*.json, produced by the independent
+python-integer reference tests/pyref.py via tests/golden/make_golden.py) and against the constants and
+known-answer tests the reference tree itself holds."""
+import json
+import os
+
+import numpy as np
+
+from tests import oracle as O
+from tests import pyref as P
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    with open(os.path.join(G, name + ".json")) as f:
+        return json.load(f)
+
+
+def test_moduli_match_reference_tree():
+    # compiler/src/algebra/fs.rs:15-16 and prover/src/groth16/ethereum.rs:37,173 — read at survey time
+    assert P.R_MOD == 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    assert P.Q_MOD == 21888242871839275222246405745257275088696311157297823662689037894645226208583
+    assert O.field_op(0, 0, P.R_MOD - 1, 1) == 0 and O.field_op(1, 0, P.Q_MOD - 1, 1) == 0
+    # generators: ethereum.rs:22 (G1 = (1, 2)) and ethereum.rs:28-31 (G2)
+    assert O.g1_tuple(O.g1_generator()) == (1, 2)
+    assert O.g2_tuple(O.g2_generator()) == P.G2_GEN
+    assert O.lib().ora_g1_on_curve(O.g1_generator()) == 1 and O.lib().ora_g2_on_curve(O.g2_generator()) == 1
+    assert O.g1_mul(P.G1_GEN, P.R_MOD) is None and O.g2_mul(P.G2_GEN, P.R_MOD) is None
+
+
+def test_field_golden():
+    g = load("field")
+    for f, name in ((0, "fr"), (1, "fq")):
+        for row in g[name]:
+            a, b = int(row["a"]), int(row["b"])
+            assert O.field_op(f, 0, a, b) == int(row["add"])
+            assert O.field_op(f, 1, a, b) == int(row["sub"])
+            assert O.field_op(f, 2, a, b) == int(row["mul"])
+            assert O.field_op(f, 3, a) == int(row["inv"])
+            assert O.field_op(f, 4, a) == int(row["neg"])
+    # fs.rs:429-436 : 1/2 * 6 == 3
+    half = O.field_op(0, 3, 2)
+    assert O.field_op(0, 2, half, 6) == 3 == int(g["fs_rs_kat"]["half_times_six"])
+
+
+def test_babyjub_kat_from_reference_tree():
+    """interop/circuits/circomlib/za_test/babyjub.za:16-34 with circuits/babyjub.circom:23-50:
+    twisted-Edwards addition over Fr, a = 168700, d = 168696 — an Fr known-answer test the reference holds."""
+    a, d = 168700, 168696
+    x1 = 17777552123799933955779906779655732241715742912184938656739573121738514868268
+    y1 = 2626589144620713026669568689430873010625803728049924121243784502389097019475
+    x2 = 16540640123574156134436876038791482806971768689494387082833631921987005038935
+    y2 = 20819045374670962167435360035096875258406992893633759881276124905556507972311
+    ex = 7916061937171219682591368294088513039687205273691143098332585753343424131937
+    ey = 14035240266687799601661095864649209771790948434046947201833777492504781204499
+
+    def mul(u, v): return O.field_op(0, 2, u, v)
+    def add(u, v): return O.field_op(0, 0, u, v)
+    def sub(u, v): return O.field_op(0, 1, u, v)
+    def inv(u): return O.field_op(0, 3, u)
+    beta, gamma = mul(x1, y2), mul(y1, x2)
+    tau = mul(beta, gamma)
+    xo = mul(add(beta, gamma), inv(add(1, mul(d, tau))))
+    yo = mul(sub(mul(y1, y2), mul(a, mul(x1, x2))), inv(sub(1, mul(d, tau))))
+    assert (xo, yo) == (ex, ey)
+
+
+def test_curve_golden():
+    g = load("curve")
+    for row in g["g1"]:
+        assert O.g1_bytes(O.g1_mul(P.G1_GEN, int(row["k"]))).hex() == row["p"]
+    for row in g["g2"]:
+        assert O.g2_bytes(O.g2_mul(P.G2_GEN, int(row["k"]))).hex() == row["p"]
+
+
+def test_ntt_golden():
+    g = load("ntt")
+    for t in g["transforms"]:
+        log_n = t["log_n"]
+        d = O.frs_to_np([int(x) for x in t["input"]]).reshape(-1, 32)
+        for mode, key in enumerate(("fft", "ifft", "coset_fft", "icoset_fft")):
+            for threads in (1, 4):
+                assert O.np_to_frs(O.fft(d, log_n, mode, threads)) == [int(x) for x in t[key]], (log_n, key)
+    h = g["h_poly"]
+    arr = lambda k: O.frs_to_np([int(x) for x in h[k]]).reshape(-1, 32)
+    assert O.np_to_frs(O.h_poly(arr("a"), arr("b"), arr("c"))) == [int(x) for x in h["h"]]
+
+
+def test_parallel_fft_equals_serial():
+    d = O.random_frs(1 << 13, 3)
+    for mode in range(4):
+        assert np.array_equal(O.fft(d, 13, mode, 1), O.fft(d, 13, mode, 8))
+
+
+def test_msm_golden():
+    for case in load("msm"):
+        n = case["n"]
+        sc = O.frs_to_np([int(x) for x in case["scalars"]])
+        for threads in (1, 4):
+            rc, out = O.multiexp("g1", O.g1_multiples(n), sc, threads=threads)
+            assert rc == 0 and out.hex() == case["g1"]
+            rc, out = O.multiexp("g2", O.g2_multiples(n), sc, threads=threads)
+            assert rc == 0 and out.hex() == case["g2"]
+
+
+def test_msm_density_and_errors():
+    n = 50
+    bases = O.g1_multiples(n)
+    sc = O.random_frs(n, 4)
+    dens = np.array([i % 3 != 0 for i in range(n)], np.uint8)
+    rc, out = O.multiexp("g1", bases, sc, density=dens)
+    assert rc == 0
+    picked = [i for i in range(n) if dens[i]]
+    exp = P.msm(P.Fq1Ops, [O.g1_tuple(bases[k]) for k in range(len(picked))], [O.fr_int(sc[i]) for i in picked])
+    assert O.g1_tuple(out) == exp
+    rc, _ = O.multiexp("g1", bases[:10], sc)          # bases run out
+    assert rc == -4
+    b2 = bases.copy(); b2[5] = 0
+    rc, _ = O.multiexp("g1", b2, sc)                  # identity with non-zero exponent
+    assert rc == -1
+
+
+def test_pairing_bilinear():
+    a, b = 0x1234567, 0x7654321
+    e1 = O.pairing(P.g1_mul(P.G1_GEN, a), P.g2_mul(P.G2_GEN, b))
+    e2 = O.pairing(P.g1_mul(P.G1_GEN, a * b % P.R_MOD), P.G2_GEN)
+    e0 = O.pairing(P.G1_GEN, P.G2_GEN)
+    one = (1).to_bytes(32, "little") + b"\0" * 352
+    assert e1 == e2 and e0 != one and e0 != e1
+
+
+def test_groth16_example_golden():
+    """Config 1 (example/circuit.za + example/input.json): oracle generate_parameters + create_proof equals the
+    closed-form golden proof; proof verifies with the right public input and fails with a wrong one
+    (mirrors prover/src/groth16/prover.rs:294-305); pk write -> read round trip (prover.rs:308-373)."""
+    g = load("groth16_example")
+    cs = P.example_factor_circuit()
+    ocs = O.CS.from_rows(cs.num_inputs, cs.num_aux, cs.rows)
+    prm = O.Params.generate(ocs, [int(t) for t in g["toxic"]])
+    assert prm.counts() == dict(ic=2, h=3, l=2, a=3, b_g1=1, b_g2=1)          # SURVEY §3.3 worked example
+    inputs = O.frs_to_np([int(x) for x in g["inputs"]]); aux = O.frs_to_np([int(x) for x in g["aux"]])
+    rc, proof, tr = prm.create_proof(ocs, inputs, aux, int(g["r"]), int(g["s"]), trace=True)
+    assert rc == 0 and proof.hex() == g["proof_hex"]
+    assert O.np_to_frs(tr["a_eval"]) == [2, 1, 6] and O.np_to_frs(tr["b_eval"]) == [3, 0, 0] and O.np_to_frs(tr["c_eval"]) == [6, 0, 0]
+    assert list(tr["a_aux_density"]) == [1, 0] and list(tr["b_input_density"]) == [0, 0] and list(tr["b_aux_density"]) == [0, 1]
+    assert prm.verify(proof, [6]) == 1 and prm.verify(proof, [7]) == 0
+    blob = prm.write()
+    p2 = O.Params.read(blob, checked=True)
+    assert p2.write() == blob
+    rc, proof2 = p2.create_proof(ocs, inputs, aux, int(g["r"]), int(g["s"]), threads=4)
+    assert rc == 0 and proof2 == proof
+    vk = g["vk"]
+    assert blob[:64] == bytes.fromhex(vk["alpha_g1"])[31::-1] + bytes.fromhex(vk["alpha_g1"])[63:31:-1]   # BE x || BE y
+
+
+def test_prover_rs_unit_test_circuit():
+    """prover.rs:226-306 `c <== a*b`, a = 7, b = 3: verifies with 21, fails with 22."""
+    cs = P.mul_circuit_test()
+    ocs = O.CS.from_rows(cs.num_inputs, cs.num_aux, cs.rows)
+    prm = O.Params.generate(ocs, [5, 6, 7, 8, 9])
+    rc, proof = prm.create_proof(ocs, O.frs_to_np([1, 21]), O.frs_to_np([7, 3]), 1234, 5678)
+    assert rc == 0
+    assert prm.verify(proof, [21]) == 1
+    assert prm.verify(proof, [22]) == 0
+    assert prm.verify(proof, []) == -7          # MalformedVerifyingKey
+
+
+def test_params_read_rejects():
+    cs = P.example_factor_circuit()
+    ocs = O.CS.from_rows(cs.num_inputs, cs.num_aux, cs.rows)
+    blob = bytearray(O.Params.generate(ocs, [2, 3, 4, 5, 6]).write())
+    import pytest
+    with pytest.raises(RuntimeError):
+        O.Params.read(bytes(blob[:-1]))
+    bad = bytearray(blob); bad[40] ^= 1
+    with pytest.raises(RuntimeError):
+        O.Params.read(bytes(bad))
+    assert O.Params.read(bytes(bad), checked=False) is not None     # unchecked read does not validate the curve equation
+
+
+def test_mul_chain_closed_form_vs_oracle():
+    """A second circuit family (config 2 shape, tiny): oracle prover == closed-form python proof."""
+    from tests import circuits
+    ni, na, ptr, var, coeff, inputs, aux = circuits.mul_chain(6, x0=5)
+    ocs = O.CS(ni, na, ptr, var, coeff)
+    rows = []
+    for k in range(6):
+        row = []
+        for w in range(3):
+            row.append([(O.fr_int(coeff[w][t]), int(var[w][t])) for t in range(ptr[w][k], ptr[w][k + 1])])
+        rows.append(tuple(row))
+    cs = P.R1CS(ni, na, rows)
+    toxic = [101, 102, 103, 104, 105]
+    proof, _ = P.groth16_closed_form(cs, O.np_to_frs(inputs), O.np_to_frs(aux), toxic, 77, 88)
+    prm = O.Params.generate(ocs, toxic)
+    rc, pf = prm.create_proof(ocs, inputs, aux, 77, 88)
+    assert rc == 0 and O.proof_tuple(pf) == proof

@@ -1,0 +1,10 @@
+"""za_b200 — B200-native Groth16 proving backend for za (the bellman-bn128 hot path only).
+
+The product is the CUDA library `libza_b200.so` (C ABI in include/za_b200.h); this package is the thin
+host-side mirror of the reference's prover interface over it (za_b200.groth16).  There is no CPU,
+PyTorch or oracle fallback anywhere in this package.
+"""
+from . import _lib  # noqa: F401
+from ._lib import ZaError  # noqa: F401
+from .groth16 import (Context, Bases, Parameters, Circuit, create_proof, multiexp, multiexp_device, point_sum,  # noqa: F401
+                      proof_to_json, FFT, IFFT, COSET_FFT, ICOSET_FFT)

@@ -1,0 +1,25 @@
+// Internal host entry points shared between the translation units of libza_b200.so.
+#pragma once
+#include "common.cuh"
+
+namespace za {
+
+// ntt.cu
+Fr host_domain_omega(int log_n);
+void fr_convert(Ctx* ctx, Fr* d, size_t n, int dir);
+void ntt_mode(Ctx* ctx, Fr* buf, int log_n, int mode, int batch);
+void h_poly_device(Ctx* ctx, Fr* a, Fr* b, Fr* c, int log_m);
+void h_poly_checkpointed(Ctx* ctx, Fr* a, Fr* b, Fr* c, int log_m, uint8_t* ck);
+
+// msm.cu
+template <class F> uint32_t bases_import(Ctx* ctx, void* d_pts, size_t n);
+template <class F> XYZZ<F> msm_run(Ctx* ctx, const Affine<F>* d_bases, const uint32_t* d_scalars, size_t n, bool has_infinity);
+int msm_window_bits(size_t n);
+
+}  // namespace za
+
+// the opaque context of the C ABI
+struct za_ctx {
+    za::Ctx c;
+    cudaStream_t own = nullptr;
+};

@@ -1,0 +1,190 @@
+// extern "C" surface of libza_b200.so (declared in include/za_b200.h).
+// Every entry point converts C++ exceptions into status codes; nothing crosses the ABI but plain
+// pointers and sizes.
+#include "common.cuh"
+#include "api_internal.cuh"
+#include <string.h>
+
+namespace za {
+
+std::string& last_error() {
+    static thread_local std::string s;
+    return s;
+}
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    last_error() = buf;
+    return code;
+}
+Ctx::~Ctx() {
+    for (auto& kv : domains) delete kv.second;
+    if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
+}  // namespace za
+
+using namespace za;
+
+
+#define ZA_TRY try {
+#define ZA_CATCH                                                                   \
+    }                                                                              \
+    catch (const ZaError& e) { return fail(e.code, "%s", e.what()); }              \
+    catch (const CudaError& e) { return fail(ZA_ERR_CUDA, "%s", e.what()); }       \
+    catch (const std::bad_alloc&) { return fail(ZA_ERR_INVALID, "out of host memory"); } \
+    catch (const std::exception& e) { return fail(ZA_ERR_INVALID, "%s", e.what()); }
+
+extern "C" {
+
+const char* za_last_error(void) { return last_error().c_str(); }
+int za_version(void) { return 1; }
+
+int za_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int za_ctx_create(int device, za_ctx** out) {
+    if (!out) return fail(ZA_ERR_INVALID, "za_ctx_create: out is NULL");
+    *out = nullptr;
+    ZA_TRY
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(ZA_ERR_CUDA, "no CUDA device available (%s); za_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(ZA_ERR_INVALID, "device %d out of range (have %d)", device, n);
+    ZA_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    ZA_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(ZA_ERR_CUDA, "device %d is sm_%d%d; za_b200 is built for sm_100a only", device, prop.major, prop.minor);
+    za_ctx* c = new za_ctx();
+    c->c.device = device;
+    c->c.sm_count = prop.multiProcessorCount;
+    ZA_CUDA(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
+    c->c.stream = c->own;
+    c->c.own_stream = false;  // destroyed below, not by ~Ctx
+    *out = c;
+    return ZA_OK;
+    ZA_CATCH
+}
+
+void za_ctx_destroy(za_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->c.device);
+    cudaStreamSynchronize(ctx->c.stream);
+    if (ctx->own) cudaStreamDestroy(ctx->own);
+    delete ctx;
+}
+
+int za_ctx_set_stream(za_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return fail(ZA_ERR_INVALID, "ctx is NULL");
+    ctx->c.stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own;
+    return ZA_OK;
+}
+
+int za_ctx_synchronize(za_ctx* ctx) {
+    if (!ctx) return fail(ZA_ERR_INVALID, "ctx is NULL");
+    ZA_TRY
+    ZA_CUDA(cudaSetDevice(ctx->c.device));
+    ZA_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    return ZA_OK;
+    ZA_CATCH
+}
+
+uint64_t za_ctx_launch_count(const za_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+// ------------------------------------------------------------------------------------- NTT
+int za_fr_convert_device(za_ctx* ctx, void* d_data, size_t n, int dir) {
+    if (!ctx || !d_data) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    ZA_CUDA(cudaSetDevice(ctx->c.device));
+    fr_convert(&ctx->c, (Fr*)d_data, n, dir);
+    return ZA_OK;
+    ZA_CATCH
+}
+
+int za_ntt_device(za_ctx* ctx, void* d_data, int log_n, int mode, int batch) {
+    if (!ctx || !d_data) return fail(ZA_ERR_INVALID, "NULL argument");
+    if (log_n < 0 || batch < 1 || mode < 0 || mode > 3) return fail(ZA_ERR_INVALID, "bad log_n/mode/batch");
+    ZA_TRY
+    ZA_CUDA(cudaSetDevice(ctx->c.device));
+    ntt_mode(&ctx->c, (Fr*)d_data, log_n, mode, batch);
+    return ZA_OK;
+    ZA_CATCH
+}
+
+static void check_canonical_host(const uint8_t* p, size_t n, const char* what) {
+    for (size_t i = 0; i < n; i++) {
+        uint32_t w[8];
+        memcpy(w, p + 32 * i, 32);
+        if (!fp_is_canonical<FrParams>(w)) {
+            char b[128];
+            snprintf(b, sizeof b, "%s[%zu] is not a canonical Fr element (>= r)", what, i);
+            throw ZaError(ZA_ERR_NOT_CANONICAL, b);
+        }
+    }
+}
+
+int za_ntt(za_ctx* ctx, uint8_t* data, int log_n, int mode) {
+    if (!ctx || !data) return fail(ZA_ERR_INVALID, "NULL argument");
+    if (log_n < 0 || mode < 0 || mode > 3) return fail(ZA_ERR_INVALID, "bad log_n/mode");
+    ZA_TRY
+    if (log_n >= 28) throw ZaError(ZA_ERR_POLY_DEGREE_TOO_LARGE, "domain of 2^28 or more elements");
+    Ctx* c = &ctx->c;
+    ZA_CUDA(cudaSetDevice(c->device));
+    size_t N = (size_t)1 << log_n;
+    check_canonical_host(data, N, "data");
+    DevBuf& buf = c->scratch[1];
+    buf.ensure(N * sizeof(Fr));
+    ZA_CUDA(cudaMemcpyAsync(buf.p, data, N * 32, cudaMemcpyHostToDevice, c->stream));
+    fr_convert(c, buf.as<Fr>(), N, 0);
+    ntt_mode(c, buf.as<Fr>(), log_n, mode, 1);
+    fr_convert(c, buf.as<Fr>(), N, 1);
+    ZA_CUDA(cudaMemcpyAsync(data, buf.p, N * 32, cudaMemcpyDeviceToHost, c->stream));
+    ZA_CUDA(cudaStreamSynchronize(c->stream));
+    return ZA_OK;
+    ZA_CATCH
+}
+
+int za_h_poly_device(za_ctx* ctx, void* d_a, void* d_b, void* d_c, int log_m) {
+    if (!ctx || !d_a || !d_b || !d_c) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    ZA_CUDA(cudaSetDevice(ctx->c.device));
+    h_poly_device(&ctx->c, (Fr*)d_a, (Fr*)d_b, (Fr*)d_c, log_m);
+    return ZA_OK;
+    ZA_CATCH
+}
+
+int za_h_poly(za_ctx* ctx, const uint8_t* a, const uint8_t* b, const uint8_t* c, size_t len, uint8_t* h_out, uint8_t* checkpoints) {
+    if (!ctx || !a || !b || !c || !h_out) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    Ctx* cx = &ctx->c;
+    ZA_CUDA(cudaSetDevice(cx->device));
+    size_t m = 1;
+    int log_m = 0;
+    while (m < len) { m *= 2; log_m++; if (log_m >= 28) throw ZaError(ZA_ERR_POLY_DEGREE_TOO_LARGE, "domain of 2^28 or more elements"); }
+    check_canonical_host(a, len, "a"); check_canonical_host(b, len, "b"); check_canonical_host(c, len, "c");
+    DevBuf& buf = cx->scratch[1];
+    buf.ensure(3 * m * sizeof(Fr));
+    Fr* d = buf.as<Fr>();
+    ZA_CUDA(cudaMemsetAsync(d, 0, 3 * m * sizeof(Fr), cx->stream));
+    const uint8_t* src[3] = {a, b, c};
+    for (int v = 0; v < 3; v++) ZA_CUDA(cudaMemcpyAsync(d + v * m, src[v], len * 32, cudaMemcpyHostToDevice, cx->stream));
+    fr_convert(cx, d, 3 * m, 0);
+    if (checkpoints) h_poly_checkpointed(cx, d, d + m, d + 2 * m, log_m, checkpoints);
+    else h_poly_device(cx, d, d + m, d + 2 * m, log_m);
+    if (m > 1) ZA_CUDA(cudaMemcpyAsync(h_out, d, (m - 1) * 32, cudaMemcpyDeviceToHost, cx->stream));
+    ZA_CUDA(cudaStreamSynchronize(cx->stream));
+    return ZA_OK;
+    ZA_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// Shared host-side plumbing for the za_b200 CUDA library: error reporting and the context object.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <stdexcept>
+#include "../../include/za_b200.h"
+#include "ec.cuh"
+
+namespace za {
+
+// thread-local last-error text, returned by za_last_error()
+std::string& last_error();
+int fail(int code, const char* fmt, ...);
+
+struct CudaError : std::runtime_error {
+    explicit CudaError(const std::string& s) : std::runtime_error(s) {}
+};
+struct ZaError : std::runtime_error {
+    int code;
+    ZaError(int c, const std::string& s) : std::runtime_error(s), code(c) {}
+};
+
+#define ZA_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (expr);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            char b_[512];                                                                               \
+            snprintf(b_, sizeof b_, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+            throw za::CudaError(b_);                                                                    \
+        }                                                                                               \
+    } while (0)
+
+// RAII device buffer (cudaMallocAsync on the context stream would need pool tuning; plain cudaMalloc
+// is fine because every long-lived buffer is cached in the context or the proving key).
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t n) { alloc(n); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t n) {
+        release();
+        if (n == 0) n = 16;
+        ZA_CUDA(cudaMalloc(&p, n));
+        bytes = n;
+    }
+    void ensure(size_t n) { if (n > bytes) alloc(n); }
+    void release() { if (p) { cudaFree(p); p = nullptr; bytes = 0; } }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Per-domain-size tables (bellman's EvaluationDomain fields: omega, omegainv, geninv, minv —
+// here expanded into device tables once and cached).
+struct NttDomain {
+    int log_n = 0;
+    DevBuf tw;          // omega^e, e in [0, N/2]    (N/2 + 1 entries; the last one is -1)
+    DevBuf pow_g;       // g^i                      (coset_fft pre-scale), built lazily
+    DevBuf pow_g_minv;  // m^-1 g^i                 (fused ifft -> coset_fft)
+    DevBuf pow_ginv_minv;  // m^-1 g^-i             (icoset_fft post-scale)
+    DevBuf consts;      // [0] = m^-1, [1] = (g^m - 1)^-1
+    bool have_coset = false;
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;      // stream all work of this context is issued on
+    bool own_stream = false;
+    int sm_count = 0;
+    std::map<int, NttDomain*> domains;  // by log_n
+    // scratch reused across calls
+    DevBuf scratch[8];
+    uint64_t launches = 0;              // kernels launched through this context (bench: gpu_launches)
+    ~Ctx();
+};
+
+NttDomain* get_domain(Ctx* ctx, int log_n, bool need_coset);
+
+}  // namespace za

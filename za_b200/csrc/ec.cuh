@@ -14,6 +14,10 @@
 // Every formula handles the exceptional cases bellman handles
 // (acc = inf, P = inf, P = acc -> double, P = -acc -> inf): duplicate and
 // opposite points do occur in real proving keys.
+//
+// Inlining policy on the device: the G1 mixed addition (the bucket-accumulation hot loop) is inlined;
+// every other group operation, and everything over Fq2, is a real call (`*_call` below) — otherwise
+// a G2 kernel inlines ~100 Montgomery products per loop body and ptxas needs many minutes.
 #pragma once
 #include "ff.cuh"
 
@@ -45,9 +49,13 @@ struct XYZZ {
     }
 };
 
+template <class F> ZA_HD XYZZ<F> xyzz_dbl_affine(const F& x, const F& y);
+template <class F> ZA_HD XYZZ<F> xyzz_dbl(const XYZZ<F>& p);
+
+// ------------------------------------------------------------------ formula bodies
 // 2 * (x, y) -> XYZZ          (mdbl-2008-s-1, a = 0)
 template <class F>
-ZA_HD XYZZ<F> xyzz_dbl_affine(const F& x, const F& y) {
+ZA_HD XYZZ<F> xyzz_dbl_affine_body(const F& x, const F& y) {
     XYZZ<F> r;
     F U = dbl(y);
     F V = sqr(U);
@@ -64,7 +72,7 @@ ZA_HD XYZZ<F> xyzz_dbl_affine(const F& x, const F& y) {
 
 // 2 * acc                      (dbl-2008-s-1, a = 0)
 template <class F>
-ZA_HD XYZZ<F> xyzz_dbl(const XYZZ<F>& p) {
+ZA_HD XYZZ<F> xyzz_dbl_body(const XYZZ<F>& p) {
     if (p.is_inf()) return p;
     XYZZ<F> r;
     F U = dbl(p.Y);
@@ -80,9 +88,9 @@ ZA_HD XYZZ<F> xyzz_dbl(const XYZZ<F>& p) {
     return r;
 }
 
-// acc += (x, sign ? -y : y)    (madd-2008-s)   — the bucket-accumulation step
+// acc += (x, negate ? -y : y)  (madd-2008-s)   — the bucket-accumulation step
 template <class F>
-ZA_HD void xyzz_madd(XYZZ<F>& acc, const F& x, const F& y_in, bool negate) {
+ZA_HD void xyzz_madd_body(XYZZ<F>& acc, const F& x, const F& y_in, bool negate) {
     F y = negate ? -y_in : y_in;
     if (acc.is_inf()) {
         acc.X = x; acc.Y = y; acc.ZZ = F::one(); acc.ZZZ = F::one();
@@ -107,15 +115,9 @@ ZA_HD void xyzz_madd(XYZZ<F>& acc, const F& x, const F& y_in, bool negate) {
     acc.ZZZ = acc.ZZZ * PPP;
 }
 
-template <class F>
-ZA_HD void xyzz_madd(XYZZ<F>& acc, const Affine<F>& p, bool negate = false) {
-    if (p.is_inf()) return;
-    xyzz_madd<F>(acc, p.x, p.y, negate);
-}
-
 // acc += b                     (add-2008-s)
 template <class F>
-ZA_HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& b) {
+ZA_HD void xyzz_add_body(XYZZ<F>& acc, const XYZZ<F>& b) {
     if (b.is_inf()) return;
     if (acc.is_inf()) { acc = b; return; }
     F U1 = acc.X * b.ZZ;
@@ -139,6 +141,61 @@ ZA_HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& b) {
     acc.ZZZ = acc.ZZZ * b.ZZZ * PPP;
 }
 
+// ------------------------------------------------------------------ dispatch
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ void g1_dbl_affine_call(XYZZ<Fq>* r, const Fq* x, const Fq* y) { *r = xyzz_dbl_affine_body<Fq>(*x, *y); }
+static __device__ __noinline__ void g2_dbl_affine_call(XYZZ<Fq2>* r, const Fq2* x, const Fq2* y) { *r = xyzz_dbl_affine_body<Fq2>(*x, *y); }
+static __device__ __noinline__ void g1_dbl_call(XYZZ<Fq>* r, const XYZZ<Fq>* p) { *r = xyzz_dbl_body<Fq>(*p); }
+static __device__ __noinline__ void g2_dbl_call(XYZZ<Fq2>* r, const XYZZ<Fq2>* p) { *r = xyzz_dbl_body<Fq2>(*p); }
+static __device__ __noinline__ void g2_madd_call(XYZZ<Fq2>* acc, const Fq2* x, const Fq2* y, bool negate) { xyzz_madd_body<Fq2>(*acc, *x, *y, negate); }
+static __device__ __noinline__ void g1_add_call(XYZZ<Fq>* acc, const XYZZ<Fq>* b) { xyzz_add_body<Fq>(*acc, *b); }
+static __device__ __noinline__ void g2_add_call(XYZZ<Fq2>* acc, const XYZZ<Fq2>* b) { xyzz_add_body<Fq2>(*acc, *b); }
+#endif
+
+template <class F>
+ZA_HD XYZZ<F> xyzz_dbl_affine(const F& x, const F& y) {
+#if defined(__CUDA_ARCH__)
+    XYZZ<F> r;
+    if constexpr (sizeof(F) == sizeof(Fq2)) g2_dbl_affine_call(&r, &x, &y);
+    else g1_dbl_affine_call(&r, &x, &y);
+    return r;
+#else
+    return xyzz_dbl_affine_body<F>(x, y);
+#endif
+}
+template <class F>
+ZA_HD XYZZ<F> xyzz_dbl(const XYZZ<F>& p) {
+#if defined(__CUDA_ARCH__)
+    XYZZ<F> r;
+    if constexpr (sizeof(F) == sizeof(Fq2)) g2_dbl_call(&r, &p);
+    else g1_dbl_call(&r, &p);
+    return r;
+#else
+    return xyzz_dbl_body<F>(p);
+#endif
+}
+template <class F>
+ZA_HD void xyzz_madd(XYZZ<F>& acc, const F& x, const F& y, bool negate) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(F) == sizeof(Fq2)) { g2_madd_call(&acc, &x, &y, negate); return; }
+#endif
+    xyzz_madd_body<F>(acc, x, y, negate);
+}
+template <class F>
+ZA_HD void xyzz_madd(XYZZ<F>& acc, const Affine<F>& p, bool negate = false) {
+    if (p.is_inf()) return;
+    xyzz_madd<F>(acc, p.x, p.y, negate);
+}
+template <class F>
+ZA_HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& b) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(F) == sizeof(Fq2)) g2_add_call(&acc, &b);
+    else g1_add_call(&acc, &b);
+#else
+    xyzz_add_body<F>(acc, b);
+#endif
+}
+
 template <class F>
 ZA_HD XYZZ<F> xyzz_neg(const XYZZ<F>& p) {
     XYZZ<F> r = p;
@@ -146,34 +203,23 @@ ZA_HD XYZZ<F> xyzz_neg(const XYZZ<F>& p) {
     return r;
 }
 
-// k * p for a small unsigned k (window weights in the bucket reduction)
-template <class F>
-ZA_HD XYZZ<F> xyzz_mul_u32(const XYZZ<F>& p, uint32_t k) {
-    XYZZ<F> r = XYZZ<F>::inf();
-    for (int i = 31; i >= 0; i--) {
-        r = xyzz_dbl<F>(r);
-        if ((k >> i) & 1u) xyzz_add<F>(r, p);
-    }
-    return r;
-}
-
 // scalar given as 8 canonical little-endian 32-bit words; MSB-first double-and-add
 template <class F>
 ZA_HD XYZZ<F> xyzz_mul(const XYZZ<F>& p, const uint32_t* k) {
     XYZZ<F> r = XYZZ<F>::inf();
-    for (int i = 255; i >= 0; i--) {
+    int top = 255;
+    while (top >= 0 && !((k[top >> 5] >> (top & 31)) & 1u)) top--;
+    for (int i = top; i >= 0; i--) {
         r = xyzz_dbl<F>(r);
         if ((k[i >> 5] >> (i & 31)) & 1u) xyzz_add<F>(r, p);
     }
     return r;
 }
 
+// x = X/ZZ, y = Y/ZZZ with one inversion: t = 1/(ZZ*ZZZ), 1/ZZ = t*ZZZ, 1/ZZZ = t*ZZ
 template <class F>
 ZA_HD Affine<F> xyzz_to_affine(const XYZZ<F>& p) {
     if (p.is_inf()) return Affine<F>::inf();
-    // 1/ZZZ once; 1/ZZ = ZZZ^-1 * (ZZZ/ZZ) where ZZZ/ZZ = Z, Z^2 = ZZ  -> use two inversions' worth
-    // of multiplications instead: iZZZ = 1/ZZZ, iZZ = (ZZ * iZZZ)^2 * ZZ ... Z = ZZZ/ZZ is not directly
-    // available, so invert the product and split.
     F t = inv(p.ZZ * p.ZZZ);
     F iZZ = t * p.ZZZ;
     F iZZZ = t * p.ZZ;

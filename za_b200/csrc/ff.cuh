@@ -18,8 +18,14 @@
 #include <stdint.h>
 #include <stddef.h>
 
+// Force inlining only in the device pass: force-inlining the host copies of the curve formulas
+// (proof assembly) makes the host compiler spend minutes on a few giant functions.
 #if defined(__CUDACC__)
+#if defined(__CUDA_ARCH__)
 #define ZA_HD __host__ __device__ __forceinline__
+#else
+#define ZA_HD __host__ __device__ inline
+#endif
 #define ZA_D __device__ __forceinline__
 #else
 #define ZA_HD inline
@@ -275,6 +281,41 @@ ZA_HD void fp_mad_redc(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi)
 
 template <class P>
 ZA_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+#if !defined(__CUDA_ARCH__) && !defined(ZA_FF_EMULATE_PTX)
+    // Host fast path (proof assembly, window combination): 4 x 64-bit CIOS.  Define
+    // ZA_FF_EMULATE_PTX to run the device limb schedule on the host instead (unit tests do).
+    typedef unsigned __int128 u128;
+    uint64_t A[4], B[4], M[4], t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        A[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+        B[i] = (uint64_t)b.v[2 * i] | ((uint64_t)b.v[2 * i + 1] << 32);
+        M[i] = (uint64_t)P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32);
+    }
+    // -p^-1 mod 2^64 from the 32-bit constant by one Newton step: x' = x (2 + p x)  for x = -p^-1
+    uint64_t ninv = (uint64_t)P::inv;
+    ninv = ninv * (2 + M[0] * ninv);
+    for (int i = 0; i < 4; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 4; j++) { c += (u128)A[j] * B[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+        c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * ninv;
+        c = (u128)m * M[0] + t[0]; c >>= 64;
+        for (int j = 1; j < 4; j++) { c += (u128)m * M[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+        c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+    }
+    bool ge = t[4] != 0;
+    if (!ge) {
+        ge = true;
+        for (int i = 3; i >= 0; i--) { if (t[i] > M[i]) break; if (t[i] < M[i]) { ge = false; break; } }
+    }
+    if (ge) {
+        uint64_t borrow = 0;
+        for (int i = 0; i < 4; i++) { u128 d = (u128)t[i] - M[i] - borrow; t[i] = (uint64_t)d; borrow = (uint64_t)(d >> 64) & 1; }
+    }
+    Fp<P> r;
+    for (int i = 0; i < 4; i++) { r.v[2 * i] = (uint32_t)t[i]; r.v[2 * i + 1] = (uint32_t)(t[i] >> 32); }
+    return r;
+#else
     uint32_t ev[8], od[8];
     fp_mad_redc<P, true>(ev, od, a.v, b.v[0]);
     fp_mad_redc<P, false>(od, ev, a.v, b.v[1]);
@@ -290,6 +331,7 @@ ZA_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
     r.v[7] = p_addc(ev[7], 0u);
     fp_final_sub<P>(r.v);
     return r;
+#endif
 }
 
 template <class P>
@@ -375,11 +417,19 @@ ZA_HD Fq2 operator+(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = a.c0 + b.c0; r.c
 ZA_HD Fq2 operator-(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; return r; }
 ZA_HD Fq2 operator-(const Fq2& a) { Fq2 r; r.c0 = -a.c0; r.c1 = -a.c1; return r; }
 ZA_HD Fq2 dbl(const Fq2& a) { Fq2 r; r.c0 = dbl(a.c0); r.c1 = dbl(a.c1); return r; }
+// On the device the Fq product under Fq2 is a real call: G2 kernels would otherwise inline ~40 Montgomery
+// products per group operation (minutes of ptxas time, code far beyond the instruction cache).
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ Fq fq_mul_call(const Fq a, const Fq b) { return fp_mul<FqParams>(a, b); }
+ZA_D Fq fq2_base_mul(const Fq& a, const Fq& b) { return fq_mul_call(a, b); }
+#else
+inline Fq fq2_base_mul(const Fq& a, const Fq& b) { return fp_mul<FqParams>(a, b); }
+#endif
 // Karatsuba: 3 Fq products
 ZA_HD Fq2 operator*(const Fq2& a, const Fq2& b) {
-    Fq aa = a.c0 * b.c0;
-    Fq bb = a.c1 * b.c1;
-    Fq s = (a.c0 + a.c1) * (b.c0 + b.c1);
+    Fq aa = fq2_base_mul(a.c0, b.c0);
+    Fq bb = fq2_base_mul(a.c1, b.c1);
+    Fq s = fq2_base_mul(a.c0 + a.c1, b.c0 + b.c1);
     Fq2 r;
     r.c0 = aa - bb;
     r.c1 = s - aa - bb;
@@ -387,9 +437,9 @@ ZA_HD Fq2 operator*(const Fq2& a, const Fq2& b) {
 }
 // complex squaring: 2 Fq products
 ZA_HD Fq2 sqr(const Fq2& a) {
-    Fq t = a.c0 * a.c1;
+    Fq t = fq2_base_mul(a.c0, a.c1);
     Fq2 r;
-    r.c0 = (a.c0 + a.c1) * (a.c0 - a.c1);
+    r.c0 = fq2_base_mul(a.c0 + a.c1, a.c0 - a.c1);
     r.c1 = dbl(t);
     return r;
 }

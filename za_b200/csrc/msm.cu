@@ -1,0 +1,485 @@
+// Pippenger multi-scalar multiplication over BN254 G1 / G2.
+//
+// Replaces (un-vendored) bellman_ce multiexp.rs `multiexp` / `multiexp_inner`, which create_proof
+// calls eight times per proof (entered from
+// /root/reference/prover/src/groth16/prover.rs:173).  bellman: unsigned c = ceil(ln n) windows,
+// one CPU task per window, Jacobian buckets.  Here:
+//
+//   K3  msm_digits_*      signed-digit recoding of every scalar (W = ceil(255/c) windows,
+//                         2^(c-1) buckets per window, negation is free)
+//   K4  counting sort     histogram (global atomics) -> exclusive scan -> scatter of
+//                         (point index | sign) into bucket order
+//   K5  msm_accumulate    the sorted entry stream is cut into equal chunks, one per thread; a thread
+//                         walks its chunk with XYZZ mixed additions (8M+2S); buckets that straddle
+//                         chunk boundaries leave partial sums that a warp-cooperative fix-up kernel
+//                         folds together — load balance is independent of the scalar distribution
+//                         (witness vectors are dominated by 0 and 1)
+//   K6  msm_bucket_reduce running-sum over segments of buckets + weight fix-up, then a warp
+//                         reduction per window; the W window sums go to the host, which does the
+//                         c doublings per window (a few hundred field operations)
+//
+// All results are exact group elements; equality with the reference is checked after affine
+// normalisation (representation independent).
+#include "common.cuh"
+#include "api_internal.cuh"
+
+namespace za {
+
+// ------------------------------------------------------------------------------ device helpers
+template <class T>
+static __device__ __forceinline__ T ld_vec(const T* p) {
+    static_assert(sizeof(T) % 16 == 0, "16-byte multiple");
+    T r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (unsigned i = 0; i < sizeof(T) / 16; i++) d[i] = s[i];
+    return r;
+}
+template <class T>
+static __device__ __forceinline__ T ldg_vec(const T* p) {
+    T r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (unsigned i = 0; i < sizeof(T) / 16; i++) d[i] = __ldg(s + i);
+    return r;
+}
+template <class T>
+static __device__ __forceinline__ void st_vec(T* p, const T& v) {
+    uint4* d = reinterpret_cast<uint4*>(p);
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+    for (unsigned i = 0; i < sizeof(T) / 16; i++) d[i] = s[i];
+}
+
+// signed digit of window w given the running carry; updates the carry.
+// digit in [-(2^(c-1) - 1), 2^(c-1)]
+static __device__ __forceinline__ int next_digit(const uint32_t* s, int w, int c, uint32_t& carry) {
+    const int bit = w * c;
+    const int word = bit >> 5, sh = bit & 31;
+    uint64_t v = 0;
+    if (word < 8) v = s[word];
+    if (word + 1 < 8) v |= (uint64_t)s[word + 1] << 32;
+    uint32_t raw = (uint32_t)((v >> sh) & ((1u << c) - 1)) + carry;
+    if (raw > (1u << (c - 1))) { carry = 1; return (int)raw - (1 << c); }
+    carry = 0;
+    return (int)raw;
+}
+
+// K3 + K4a: per-bucket entry counts
+__global__ void msm_digits_hist_kernel(const uint32_t* __restrict__ scalars, size_t n, int c, int W, uint32_t B, uint32_t* counts) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    const uint4* p = reinterpret_cast<const uint4*>(scalars + 8 * i);
+    uint4 a = __ldg(p), b = __ldg(p + 1);
+    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+    if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) return;
+    uint32_t carry = 0;
+    for (int w = 0; w < W; w++) {
+        int d = next_digit(s, w, c, carry);
+        if (d != 0) atomicAdd(&counts[(uint32_t)w * B + (uint32_t)(d < 0 ? -d : d) - 1], 1u);
+    }
+}
+
+// K4c: scatter (point index | sign << 31) into bucket order.  Order inside a bucket is arbitrary;
+// the bucket sum is not (group addition is commutative and exact).
+__global__ void msm_digits_scatter_kernel(const uint32_t* __restrict__ scalars, size_t n, int c, int W, uint32_t B, uint32_t* cursors,
+                                          uint32_t* entries) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    const uint4* p = reinterpret_cast<const uint4*>(scalars + 8 * i);
+    uint4 a = __ldg(p), b = __ldg(p + 1);
+    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+    if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) return;
+    uint32_t carry = 0;
+    for (int w = 0; w < W; w++) {
+        int d = next_digit(s, w, c, carry);
+        if (d != 0) {
+            uint32_t pos = atomicAdd(&cursors[(uint32_t)w * B + (uint32_t)(d < 0 ? -d : d) - 1], 1u);
+            entries[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+        }
+    }
+}
+
+// K4b: exclusive scan of `count` values (+ total at [count]); single CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* counts, uint32_t count, uint32_t* offsets, uint32_t* cursors) {
+    __shared__ uint32_t sums[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (count + 1023) / 1024;
+    const uint32_t lo = t * per, hi = (lo + per < count) ? lo + per : count;
+    uint32_t s = 0;
+    for (uint32_t i = lo; i < hi; i++) s += counts[i];
+    sums[t] = s;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+        uint32_t v = t >= d ? sums[t - d] : 0;
+        __syncthreads();
+        sums[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = t ? sums[t - 1] : 0;
+    for (uint32_t i = lo; i < hi; i++) {
+        uint32_t cnt = counts[i];
+        offsets[i] = run;
+        cursors[i] = run;
+        run += cnt;
+    }
+    if (t == 1023) offsets[count] = sums[1023];
+}
+
+// K5: chunked segmented accumulation.  Thread `chunk` owns entries [chunk*Lc, (chunk+1)*Lc).
+template <class F>
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ entries,
+                                                             const uint32_t* __restrict__ offsets, uint32_t nkeys, uint32_t Lc,
+                                                             XYZZ<F>* bucket_sums, XYZZ<F>* part_head, XYZZ<F>* part_tail,
+                                                             uint32_t* tail_owner_key) {
+    const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t E = offsets[nkeys];
+    const uint64_t start64 = (uint64_t)chunk * Lc;
+    if (start64 >= E) return;
+    const uint32_t start = (uint32_t)start64;
+    const uint32_t end = (uint64_t)start + Lc < E ? start + Lc : E;
+    // last key with offsets[key] <= start  (non-empty by construction)
+    uint32_t lo = 0, hi = nkeys;
+    while (lo + 1 < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= start) lo = mid; else hi = mid;
+    }
+    uint32_t key = lo;
+    bool head_open = offsets[key] < start;
+    uint32_t pos = start;
+    while (pos < end) {
+        const uint32_t bend = offsets[key + 1];
+        const uint32_t run_end = bend < end ? bend : end;
+        XYZZ<F> acc = XYZZ<F>::inf();
+        uint32_t e = entries[pos];
+        Affine<F> P = ldg_vec(bases + (e & 0x7fffffffu));
+        for (; pos < run_end; pos++) {
+            const uint32_t e_cur = e;
+            const Affine<F> P_cur = P;
+            if (pos + 1 < end) {                       // prefetch the next point while this one is added
+                e = entries[pos + 1];
+                P = ldg_vec(bases + (e & 0x7fffffffu));
+            }
+            xyzz_madd<F>(acc, P_cur.x, P_cur.y, (e_cur >> 31) != 0);
+        }
+        const bool closes = bend <= end;
+        if (!head_open && closes) st_vec(bucket_sums + key, acc);
+        else if (head_open) st_vec(part_head + chunk, acc);
+        else { st_vec(part_tail + chunk, acc); tail_owner_key[chunk] = key; }
+        head_open = false;
+        if (pos < end) { do { key++; } while (offsets[key + 1] <= pos); }
+    }
+}
+
+template <class F>
+static __device__ __forceinline__ XYZZ<F> warp_reduce_xyzz(XYZZ<F> acc, unsigned lane) {
+    constexpr int WORDS = sizeof(XYZZ<F>) / 4;
+#pragma unroll 1
+    for (int step = 16; step >= 1; step >>= 1) {
+        XYZZ<F> other;
+        uint32_t* o = reinterpret_cast<uint32_t*>(&other);
+        const uint32_t* a = reinterpret_cast<const uint32_t*>(&acc);
+#pragma unroll
+        for (int k = 0; k < WORDS; k++) o[k] = __shfl_down_sync(0xffffffffu, a[k], step);
+        if (lane < (unsigned)step) xyzz_add<F>(acc, other);
+    }
+    return acc;
+}
+
+// K5b: one warp per bucket that straddles chunk boundaries: tail partial of the chunk where the bucket
+// starts + head partials of every following chunk the bucket reaches into.
+template <class F>
+__global__ void __launch_bounds__(128) msm_fixup_kernel(const uint32_t* __restrict__ offsets, uint32_t nkeys, uint32_t Lc, uint32_t nchunks,
+                                                        const XYZZ<F>* part_head, const XYZZ<F>* part_tail, const uint32_t* tail_owner_key,
+                                                        XYZZ<F>* bucket_sums) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31;
+    if (warp >= nchunks) return;
+    const uint32_t key = tail_owner_key[warp];
+    if (key == 0xffffffffu) return;
+    const uint32_t bend = offsets[key + 1];
+    const uint32_t t_end = (bend - 1) / Lc;        // last chunk holding entries of this bucket
+    const uint32_t count = t_end - warp + 1;       // element 0 = tail of `warp`, element k = head of warp + k
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = lane; k < count; k += 32) {
+        XYZZ<F> v = k == 0 ? ld_vec(part_tail + warp) : ld_vec(part_head + warp + k);
+        xyzz_add<F>(acc, v);
+    }
+    acc = warp_reduce_xyzz<F>(acc, lane);
+    if (lane == 0) st_vec(bucket_sums + key, acc);
+}
+
+// K6a: thread per segment of `seg` buckets inside one window: sum_{b in seg} (b+1) * S_b
+template <class F>
+__global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(const XYZZ<F>* __restrict__ bucket_sums, uint32_t B, uint32_t seg,
+                                                                uint32_t segs_per_window, uint32_t total_segs, XYZZ<F>* seg_out) {
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total_segs) return;
+    const uint32_t w = id / segs_per_window, s = id % segs_per_window;
+    const uint32_t lo = s * seg, hi = lo + seg < B ? lo + seg : B;
+    XYZZ<F> running = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+    for (uint32_t b = hi; b-- > lo;) {
+        XYZZ<F> v = ld_vec(bucket_sums + (size_t)w * B + b);
+        xyzz_add<F>(running, v);
+        xyzz_add<F>(acc, running);
+    }
+    if (lo) {
+        // + lo * running, MSB-first from the highest set bit
+        XYZZ<F> m = running;
+        int top = 31 - __clz(lo);
+        for (int i = top - 1; i >= 0; i--) {
+            m = xyzz_dbl<F>(m);
+            if ((lo >> i) & 1u) xyzz_add<F>(m, running);
+        }
+        xyzz_add<F>(acc, m);
+    }
+    st_vec(seg_out + id, acc);
+}
+
+// K6b: warp per group of `per` consecutive points -> one sum
+template <class F>
+__global__ void __launch_bounds__(128) msm_group_reduce_kernel(const XYZZ<F>* __restrict__ in, uint32_t per, uint32_t groups, XYZZ<F>* out) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31;
+    if (warp >= groups) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = lane; k < per; k += 32) {
+        XYZZ<F> v = ld_vec(in + (size_t)warp * per + k);
+        xyzz_add<F>(acc, v);
+    }
+    acc = warp_reduce_xyzz<F>(acc, lane);
+    if (lane == 0) st_vec(out + warp, acc);
+}
+
+// Small inputs (public-input queries have a handful of points): thread per point, double-and-add,
+// then a single-warp tree.  Also an independent on-device check of the bucket pipeline (tests).
+template <class F>
+__global__ void __launch_bounds__(128) msm_naive_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ scalars, uint32_t n,
+                                                        XYZZ<F>* out) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t i = warp * 32 + lane;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (i < n) {
+        uint32_t k[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) k[j] = scalars[8 * (size_t)i + j];
+        Affine<F> P = ldg_vec(bases + i);
+        if (!P.is_inf()) {
+            int top = 255;
+            while (top >= 0 && !((k[top >> 5] >> (top & 31)) & 1u)) top--;
+            for (int b = top; b >= 0; b--) {
+                acc = xyzz_dbl<F>(acc);
+                if ((k[b >> 5] >> (b & 31)) & 1u) xyzz_madd<F>(acc, P.x, P.y, false);
+            }
+        }
+    }
+    acc = warp_reduce_xyzz<F>(acc, lane);
+    if (lane == 0) st_vec(out + warp, acc);
+}
+
+// any base at infinity paired with a non-zero scalar?  (bellman: SynthesisError::UnexpectedIdentity)
+template <class F>
+__global__ void msm_identity_check_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ scalars, size_t n, uint32_t* flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t o = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) o |= scalars[8 * i + j];
+    if (o == 0) return;
+    Affine<F> P = ldg_vec(bases + i);
+    if (P.is_inf()) atomicOr(flag, 1u);
+}
+
+// canonical LE affine (host interchange) -> Montgomery affine; infinity (all zero) stays all zero.
+// flags[0] |= 1 if a coordinate is not canonical, |= 2 if a point is off the curve, |= 4 if any infinity
+template <class F, int NF>
+__global__ void bases_import_kernel(Affine<F>* pts, size_t n, const F b_coeff, uint32_t* flags) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p = ld_vec(pts + i);
+    Fq* c = reinterpret_cast<Fq*>(&p);
+    uint32_t any = 0;
+#pragma unroll
+    for (int k = 0; k < NF; k++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) any |= c[k].v[j];
+    }
+    if (any == 0) { atomicOr(flags, 4u); return; }
+#pragma unroll
+    for (int k = 0; k < NF; k++) {
+        if (!fp_is_canonical<FqParams>(c[k].v)) atomicOr(flags, 1u);
+        c[k] = fp_to_mont<FqParams>(c[k]);
+    }
+    if (!affine_on_curve<F>(p, b_coeff)) atomicOr(flags, 2u);
+    st_vec(pts + i, p);
+}
+
+// Montgomery -> canonical for a handful of XYZZ points
+template <class F, int NF>
+__global__ void xyzz_export_kernel(XYZZ<F>* pts, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XYZZ<F> p = ld_vec(pts + i);
+    Fq* c = reinterpret_cast<Fq*>(&p);
+#pragma unroll
+    for (int k = 0; k < NF; k++) c[k] = fp_from_mont<FqParams>(c[k]);
+    st_vec(pts + i, p);
+}
+
+// ------------------------------------------------------------------------------------------ host
+template <class F> struct GroupInfo;
+template <> struct GroupInfo<Fq> { static constexpr int NF_AFF = 2, NF_XYZZ = 4; };
+template <> struct GroupInfo<Fq2> { static constexpr int NF_AFF = 4, NF_XYZZ = 8; };
+
+Fq host_g1_b() { return fp_from_u64<FqParams>(3); }
+Fq2 host_g2_b() {
+    // 3 / (9 + u)
+    Fq2 xi; xi.c0 = fp_from_u64<FqParams>(9); xi.c1 = fp_from_u64<FqParams>(1);
+    Fq2 three; three.c0 = fp_from_u64<FqParams>(3); three.c1 = Fq::zero();
+    return three * inv(xi);
+}
+
+static inline unsigned nblk(size_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
+
+int msm_window_bits(size_t n) {
+    // minimise n*W*10 + W*2^(c-1)*28 field multiplications, with W = ceil(255/c); c <= 16 keeps the
+    // bucket array (W * 2^(c-1) XYZZ points) and the reduction latency small.
+    int best = 1;
+    double best_cost = 1e300;
+    for (int c = 2; c <= 16; c++) {
+        double W = (255 + c - 1) / c;
+        double cost = (double)n * W * 10.0 + W * (double)(1u << (c - 1)) * 40.0;
+        if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
+}
+
+template <class F>
+static void import_bases(Ctx* ctx, Affine<F>* d_pts, size_t n, uint32_t* d_flags);
+template <>
+void import_bases<Fq>(Ctx* ctx, Affine<Fq>* d_pts, size_t n, uint32_t* d_flags) {
+    bases_import_kernel<Fq, 2><<<nblk(n, 128), 128, 0, ctx->stream>>>(d_pts, n, host_g1_b(), d_flags);
+    ctx->launches++;
+}
+template <>
+void import_bases<Fq2>(Ctx* ctx, Affine<Fq2>* d_pts, size_t n, uint32_t* d_flags) {
+    bases_import_kernel<Fq2, 4><<<nblk(n, 128), 128, 0, ctx->stream>>>(d_pts, n, host_g2_b(), d_flags);
+    ctx->launches++;
+}
+
+// Upload canonical affine points and convert in place.  Returns flags (see bases_import_kernel).
+template <class F>
+uint32_t bases_import(Ctx* ctx, void* d_pts, size_t n) {
+    if (!n) return 0;
+    DevBuf flags(4);
+    ZA_CUDA(cudaMemsetAsync(flags.p, 0, 4, ctx->stream));
+    import_bases<F>(ctx, (Affine<F>*)d_pts, n, flags.as<uint32_t>());
+    ZA_CUDA(cudaGetLastError());
+    uint32_t h = 0;
+    ZA_CUDA(cudaMemcpyAsync(&h, flags.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return h;
+}
+template uint32_t bases_import<Fq>(Ctx*, void*, size_t);
+template uint32_t bases_import<Fq2>(Ctx*, void*, size_t);
+
+// Runs the MSM; returns the result as a host XYZZ point (Montgomery form).
+// d_scalars: n canonical scalars on device.  has_infinity: bases may contain the (0,0) encoding.
+template <class F>
+XYZZ<F> msm_run(Ctx* ctx, const Affine<F>* d_bases, const uint32_t* d_scalars, size_t n, bool has_infinity) {
+    XYZZ<F> result = XYZZ<F>::inf();
+    if (n == 0) return result;
+    if (n >= ((size_t)1 << 27)) throw ZaError(ZA_ERR_INVALID, "multiexp of 2^27 or more points is not supported");
+    cudaStream_t st = ctx->stream;
+    if (has_infinity) {
+        DevBuf flag(4);
+        ZA_CUDA(cudaMemsetAsync(flag.p, 0, 4, st));
+        msm_identity_check_kernel<F><<<nblk(n, 256), 256, 0, st>>>(d_bases, d_scalars, n, flag.as<uint32_t>());
+        ctx->launches++;
+        uint32_t h = 0;
+        ZA_CUDA(cudaMemcpyAsync(&h, flag.p, 4, cudaMemcpyDeviceToHost, st));
+        ZA_CUDA(cudaStreamSynchronize(st));
+        if (h) throw ZaError(ZA_ERR_UNEXPECTED_IDENTITY, "multiexp: a base at infinity has a non-zero exponent");
+    }
+    if (n <= 64) {
+        const uint32_t warps = (uint32_t)((n + 31) / 32);
+        DevBuf& out = ctx->scratch[2];
+        out.ensure(warps * sizeof(XYZZ<F>));
+        msm_naive_kernel<F><<<nblk(warps * 32, 128), 128, 0, st>>>(d_bases, d_scalars, (uint32_t)n, out.as<XYZZ<F>>());
+        ctx->launches++;
+        ZA_CUDA(cudaGetLastError());
+        XYZZ<F> h[2];
+        ZA_CUDA(cudaMemcpyAsync(h, out.p, warps * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
+        ZA_CUDA(cudaStreamSynchronize(st));
+        for (uint32_t i = 0; i < warps; i++) xyzz_add<F>(result, h[i]);
+        return result;
+    }
+    const int c = msm_window_bits(n);
+    const int W = (255 + c - 1) / c;
+    const uint32_t B = 1u << (c - 1);
+    const uint32_t nkeys = (uint32_t)W * B;
+    const uint64_t Emax = (uint64_t)n * W;
+    if (Emax >= 0xffffffffull) throw ZaError(ZA_ERR_INVALID, "multiexp too large for 32-bit entry offsets");
+    // chunk length: ~8 chunks per resident thread slot, between 8 and 2048 entries
+    uint64_t slots = (uint64_t)ctx->sm_count * 512 * 8;
+    uint32_t Lc = (uint32_t)((Emax + slots - 1) / slots);
+    if (Lc < 8) Lc = 8;
+    if (Lc > 2048) Lc = 2048;
+    const uint32_t nchunks = (uint32_t)((Emax + Lc - 1) / Lc);
+
+    DevBuf& counts = ctx->scratch[2];      // counts | offsets | cursors
+    counts.ensure(((size_t)nkeys * 3 + 2) * 4);
+    uint32_t* d_counts = counts.as<uint32_t>();
+    uint32_t* d_offsets = d_counts + nkeys;
+    uint32_t* d_cursors = d_offsets + nkeys + 1;
+    DevBuf& entries = ctx->scratch[3];
+    entries.ensure((size_t)Emax * 4);
+    DevBuf& buckets = ctx->scratch[4];
+    buckets.ensure((size_t)nkeys * sizeof(XYZZ<F>));
+    DevBuf& parts = ctx->scratch[5];       // part_head | part_tail | tail_owner_key
+    parts.ensure((size_t)nchunks * (2 * sizeof(XYZZ<F>) + 4));
+    XYZZ<F>* d_head = parts.as<XYZZ<F>>();
+    XYZZ<F>* d_tail = d_head + nchunks;
+    uint32_t* d_owner = reinterpret_cast<uint32_t*>(d_tail + nchunks);
+    uint32_t seg = 32;
+    if (seg > B) seg = B;
+    const uint32_t segs_per_window = B / seg;
+    const uint32_t total_segs = segs_per_window * (uint32_t)W;
+    DevBuf& segs = ctx->scratch[6];
+    segs.ensure((size_t)(total_segs + W) * sizeof(XYZZ<F>));
+    XYZZ<F>* d_seg = segs.as<XYZZ<F>>();
+    XYZZ<F>* d_win = d_seg + total_segs;
+
+    ZA_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nkeys * 4, st));
+    ZA_CUDA(cudaMemsetAsync(buckets.p, 0, (size_t)nkeys * sizeof(XYZZ<F>), st));
+    ZA_CUDA(cudaMemsetAsync(d_owner, 0xff, (size_t)nchunks * 4, st));
+    msm_digits_hist_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_counts);
+    msm_scan_kernel<<<1, 1024, 0, st>>>(d_counts, nkeys, d_offsets, d_cursors);
+    msm_digits_scatter_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_cursors, entries.as<uint32_t>());
+    msm_accumulate_kernel<F><<<nblk(nchunks, 128), 128, 0, st>>>(d_bases, entries.as<uint32_t>(), d_offsets, nkeys, Lc,
+                                                                 buckets.as<XYZZ<F>>(), d_head, d_tail, d_owner);
+    msm_fixup_kernel<F><<<nblk((size_t)nchunks * 32, 128), 128, 0, st>>>(d_offsets, nkeys, Lc, nchunks, d_head, d_tail, d_owner,
+                                                                         buckets.as<XYZZ<F>>());
+    msm_bucket_reduce_kernel<F><<<nblk(total_segs, 128), 128, 0, st>>>(buckets.as<XYZZ<F>>(), B, seg, segs_per_window, total_segs, d_seg);
+    msm_group_reduce_kernel<F><<<nblk((size_t)W * 32, 128), 128, 0, st>>>(d_seg, segs_per_window, (uint32_t)W, d_win);
+    ctx->launches += 7;
+    ZA_CUDA(cudaGetLastError());
+    std::vector<XYZZ<F>> win(W);
+    ZA_CUDA(cudaMemcpyAsync(win.data(), d_win, (size_t)W * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
+    ZA_CUDA(cudaStreamSynchronize(st));
+    // window combination on the host: result = sum_w 2^(c w) S_w   (bellman: `higher.double()` x c, then add)
+    for (int w = W - 1; w >= 0; w--) {
+        for (int k = 0; k < c; k++) result = xyzz_dbl<F>(result);
+        xyzz_add<F>(result, win[w]);
+    }
+    return result;
+}
+template XYZZ<Fq> msm_run<Fq>(Ctx*, const Affine<Fq>*, const uint32_t*, size_t, bool);
+template XYZZ<Fq2> msm_run<Fq2>(Ctx*, const Affine<Fq2>*, const uint32_t*, size_t, bool);
+
+}  // namespace za

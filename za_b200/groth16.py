@@ -1,0 +1,290 @@
+"""Host-side mirror of the interface the reference's prover crate drives, over the za_b200 C ABI.
+
+Names follow the reference / bellman:
+  Parameters.read            <- bellman Parameters::read  (/root/reference/prover/src/groth16/format.rs:285)
+  create_proof               <- bellman create_proof / create_random_proof (prover.rs:173)
+  multiexp                   <- bellman multiexp (multiexp.rs)
+  Context.fft/ifft/coset_fft/icoset_fft <- EvaluationDomain (domain.rs)
+  proof_to_json              <- JsonProofAndInput (format.rs:80-128)
+Scalars are (n, 32) uint8 arrays of little-endian canonical values, points (n, 64|128) uint8 arrays
+(include/za_b200.h).  Everything runs on the GPU; failures raise ZaError.
+"""
+import ctypes
+
+import numpy as np
+
+from ._lib import check, lib, ZaR1CS, ZaTrace, u8p, u32p
+
+FFT, IFFT, COSET_FFT, ICOSET_FFT = 0, 1, 2, 3
+AUX = 0x80000000
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def _u8(a, width=None):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if width is not None:
+        a = a.reshape(-1, width)
+    return a
+
+
+class Context:
+    """One per GPU (za_ctx): owns the stream, the cached EvaluationDomain tables and scratch memory."""
+
+    def __init__(self, device=0):
+        h = ctypes.c_void_p()
+        check(lib().za_ctx_create(device, ctypes.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().za_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        check(lib().za_ctx_set_stream(self.h, ctypes.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        check(lib().za_ctx_synchronize(self.h))
+
+    def launch_count(self):
+        return int(lib().za_ctx_launch_count(self.h))
+
+    # ---- EvaluationDomain -------------------------------------------------------------------
+    def ntt(self, data, mode):
+        """data: (2^k, 32) canonical scalars on the host -> transformed copy."""
+        d = _u8(data, 32).copy()
+        n = d.shape[0]
+        log_n = n.bit_length() - 1
+        if n != 1 << log_n:
+            raise ValueError("length must be a power of two")
+        check(lib().za_ntt(self.h, _p(d), log_n, mode))
+        return d
+
+    def fft(self, data):
+        return self.ntt(data, FFT)
+
+    def ifft(self, data):
+        return self.ntt(data, IFFT)
+
+    def coset_fft(self, data):
+        return self.ntt(data, COSET_FFT)
+
+    def icoset_fft(self, data):
+        return self.ntt(data, ICOSET_FFT)
+
+    def ntt_device(self, dptr, log_n, mode, batch=1):
+        check(lib().za_ntt_device(self.h, ctypes.c_void_p(dptr), log_n, mode, batch))
+
+    def fr_convert_device(self, dptr, n, to_canonical):
+        check(lib().za_fr_convert_device(self.h, ctypes.c_void_p(dptr), n, 1 if to_canonical else 0))
+
+    def h_poly(self, a, b, c, checkpoints=False):
+        """create_proof's H block.  Returns h ((m-1, 32)) and, if asked, the 8 checkpoint vectors."""
+        a, b, c = _u8(a, 32), _u8(b, 32), _u8(c, 32)
+        n = a.shape[0]
+        m = 1
+        while m < n:
+            m *= 2
+        out = np.zeros((max(m - 1, 1), 32), np.uint8)
+        ck = np.zeros((8, m, 32), np.uint8) if checkpoints else None
+        check(lib().za_h_poly(self.h, _p(a), _p(b), _p(c), n, _p(out), _p(ck)))
+        out = out[:m - 1]
+        return (out, ck) if checkpoints else out
+
+    def h_poly_device(self, da, db, dc, log_m):
+        check(lib().za_h_poly_device(self.h, ctypes.c_void_p(da), ctypes.c_void_p(db), ctypes.c_void_p(dc), log_m))
+
+
+class Bases:
+    """Device-resident G1 (group=1) or G2 (group=2) affine bases."""
+
+    def __init__(self, ctx, group, points):
+        self.ctx, self.group = ctx, group
+        pts = _u8(points, 64 if group == 1 else 128)
+        h = ctypes.c_void_p()
+        check(lib().za_bases_upload(ctx.h, group, _p(pts), pts.shape[0], ctypes.byref(h)))
+        self.h = h
+
+    def __len__(self):
+        return int(lib().za_bases_len(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().za_bases_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def multiexp(ctx, bases, scalars, density=None, offset=0):
+    """bellman multiexp: sum scalars[i] * bases[offset + k(i)].  Returns the affine point bytes."""
+    s = _u8(scalars, 32)
+    d = None if density is None else _u8(density)
+    out = np.zeros(64 if bases.group == 1 else 128, np.uint8)
+    check(lib().za_multiexp(ctx.h, bases.h, offset, _p(s), s.shape[0], _p(d), _p(out)))
+    return out.tobytes()
+
+
+def multiexp_device(ctx, bases, d_scalars, n, offset=0, partial=False):
+    """Scalars already resident on the GPU (raw device pointer).  partial=True returns the XYZZ partial sum."""
+    size = (64 if bases.group == 1 else 128) * (2 if partial else 1)
+    out = np.zeros(size, np.uint8)
+    fn = lib().za_multiexp_partial_device if partial else lib().za_multiexp_device
+    check(fn(ctx.h, bases.h, offset, ctypes.c_void_p(d_scalars), n, _p(out)))
+    return out.tobytes()
+
+
+def point_sum(group, partials):
+    """Add XYZZ partial sums (multi-GPU combine) and normalise to affine."""
+    buf = np.frombuffer(b"".join(partials), np.uint8)
+    out = np.zeros(64 if group == 1 else 128, np.uint8)
+    check(lib().za_point_sum(group, _p(buf), len(partials), _p(out)))
+    return out.tobytes()
+
+
+class Parameters:
+    """bellman Parameters<Bn256> resident on the GPU."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+
+    @classmethod
+    def read(cls, ctx, data, checked=True):
+        buf = np.frombuffer(bytes(data), np.uint8)
+        h = ctypes.c_void_p()
+        check(lib().za_pk_load(ctx.h, _p(buf), buf.shape[0], 1 if checked else 0, ctypes.byref(h)))
+        return cls(ctx, h)
+
+    def counts(self):
+        c = (ctypes.c_uint32 * 6)()
+        check(lib().za_pk_counts(self.h, c))
+        return dict(zip(("ic", "h", "l", "a", "b_g1", "b_g2"), list(c)))
+
+    def vk(self):
+        n_ic = self.counts()["ic"]
+        buf = np.zeros(64 * 3 + 128 * 3 + 64 * n_ic, np.uint8)
+        check(lib().za_pk_vk(self.h, _p(buf), buf.shape[0]))
+        b = buf.tobytes()
+        return dict(alpha_g1=b[0:64], beta_g1=b[64:128], beta_g2=b[128:256], gamma_g2=b[256:384], delta_g1=b[384:448],
+                    delta_g2=b[448:576], ic=[b[576 + 64 * i:640 + 64 * i] for i in range(n_ic)])
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().za_pk_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Circuit:
+    """The enforce(A, B, C) rows CircomCircuit::synthesize (prover.rs:45-103) hands to bellman, on the GPU.
+
+    ptr/var/coeff: per matrix (A, B, C) CSR arrays; var has bit 31 set for aux variables.
+    """
+
+    def __init__(self, ctx, num_inputs, num_aux, ptr, var, coeff):
+        self.ctx = ctx
+        self.num_inputs, self.num_aux = num_inputs, num_aux
+        self._ptr = [np.ascontiguousarray(p, dtype=np.uint32) for p in ptr]
+        self._var = [np.ascontiguousarray(v, dtype=np.uint32) for v in var]
+        self._coeff = [_u8(c, 32) for c in coeff]
+        self.num_constraints = len(self._ptr[0]) - 1
+        s = ZaR1CS()
+        s.num_inputs, s.num_aux, s.num_constraints = num_inputs, num_aux, self.num_constraints
+        for w in range(3):
+            s.ptr[w] = self._ptr[w].ctypes.data_as(u32p)
+            s.var[w] = self._var[w].ctypes.data_as(u32p)
+            s.coeff[w] = self._coeff[w].ctypes.data_as(u8p)
+        h = ctypes.c_void_p()
+        check(lib().za_circuit_upload(ctx.h, ctypes.byref(s), ctypes.byref(h)))
+        self.h = h
+
+    @classmethod
+    def from_rows(cls, ctx, num_inputs, num_aux, rows):
+        """rows: [(A_terms, B_terms, C_terms)], terms [(coeff_int, var)]"""
+        ptr, var, coeff = [], [], []
+        for w in range(3):
+            p, v, c = [0], [], []
+            for row in rows:
+                for co, va in row[w]:
+                    v.append(va)
+                    c.append(int(co).to_bytes(32, "little"))
+                p.append(len(v))
+            ptr.append(np.array(p, np.uint32))
+            var.append(np.array(v, np.uint32))
+            coeff.append(np.frombuffer(b"".join(c), np.uint8).reshape(-1, 32) if c else np.zeros((0, 32), np.uint8))
+        return cls(ctx, num_inputs, num_aux, ptr, var, coeff)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().za_circuit_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _domain_size(n):
+    m = 1
+    while m < n:
+        m *= 2
+    return m
+
+
+def create_proof(ctx, params, circuit, inputs, aux, r, s, trace=False):
+    """bellman create_proof(circuit, params, r, s).  inputs[0] must be 1.  Returns 256 proof bytes
+    (a || b || c) and, with trace=True, the intermediates named in za_trace."""
+    inputs, aux = _u8(inputs, 32), _u8(aux, 32)
+    if inputs.shape[0] != circuit.num_inputs or aux.shape[0] != circuit.num_aux:
+        raise ValueError("witness size does not match the circuit")
+    rb = np.frombuffer(int(r).to_bytes(32, "little"), np.uint8)
+    sb = np.frombuffer(int(s).to_bytes(32, "little"), np.uint8)
+    proof = np.zeros(256, np.uint8)
+    tr, bufs = None, {}
+    n = circuit.num_constraints + circuit.num_inputs
+    m = _domain_size(n)
+    if trace:
+        bufs = dict(a_eval=np.zeros((n, 32), np.uint8), b_eval=np.zeros((n, 32), np.uint8), c_eval=np.zeros((n, 32), np.uint8),
+                    h_coeffs=np.zeros((max(m - 1, 1), 32), np.uint8), msm_g1=np.zeros((7, 64), np.uint8),
+                    msm_g2=np.zeros((2, 128), np.uint8), a_aux_density=np.zeros(max(circuit.num_aux, 1), np.uint8),
+                    b_input_density=np.zeros(circuit.num_inputs, np.uint8), b_aux_density=np.zeros(max(circuit.num_aux, 1), np.uint8))
+        tr = ZaTrace(**{k: v.ctypes.data_as(u8p) for k, v in bufs.items()})
+    check(lib().za_create_proof(ctx.h, params.h, circuit.h, _p(inputs), _p(aux), _p(rb), _p(sb), _p(proof),
+                                ctypes.byref(tr) if tr is not None else None))
+    if trace:
+        bufs["h_coeffs"] = bufs["h_coeffs"][:m - 1]
+        bufs["a_aux_density"] = bufs["a_aux_density"][:circuit.num_aux]
+        bufs["b_aux_density"] = bufs["b_aux_density"][:circuit.num_aux]
+        return proof.tobytes(), bufs
+    return proof.tobytes()
+
+
+def proof_to_json(proof, public_inputs):
+    """JsonProofAndInput (format.rs:80-128).  public_inputs: ints (decimal strings in the JSON)."""
+    p = np.frombuffer(bytes(proof), np.uint8)
+    pi = np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in public_inputs), np.uint8) if public_inputs else None
+    size = 1024 + 80 * len(public_inputs)
+    buf = ctypes.create_string_buffer(size)
+    check(lib().za_proof_to_json(_p(p), _p(pi), len(public_inputs), buf, size))
+    return buf.value.decode()
