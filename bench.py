@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric on B200 (BASELINE.json):
+  "Groth16 prove ms @2^20 constraints; G1 MSM Mpts/s; Fr NTT GElem/s".
+
+One step = one create_proof over the synthetic 2^20-domain multiplication-chain circuit (SURVEY §8d
+config 4).  `value` = device-timed ms per proof with the witness resident in HBM; `e2e` = the same
+through the public host-buffer call (za_create_proof: witness H2D and proof D2H inside the timed
+region).  Sub-metrics: 2^24-point G1 MSM and 2^24-point Fr NTT (config 5), each with its roofline.
+N > 1 (one process per GPU under torchrun): every query of every multiexp is cut by point range across
+ranks, rank 0 runs the H-polynomial NTTs and scatters the h scalars over NCCL, partial sums are
+gathered and combined on the host — total work is fixed, so scaling is "strong".
+
+`--impl reference`: the CPU restatement of bellman's algorithm (oracle/, multi-threaded) on the same
+workload; it is also what `cpu_baseline` reports.  The oracle is never on the GPU arm's timed path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Groth16 prove ms @2^20 constraints; G1 MSM Mpts/s; Fr NTT GElem/s"
+IMAD_PER_MODMUL = 264          # 8x32-bit-limb Montgomery product, IMAD-class instructions
+MODMUL_PER_MADD_G1 = 10        # XYZZ mixed addition, 8M + 2S
+MODMUL_PER_MADD_G2 = 30        # same over Fq2 (Karatsuba: 3 Fq products per Fq2 product)
+R_FIXED = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF1234567890AB
+S_FIXED = 0x0FEDCBA9876543210FEDCBA9876543210FEDCBA9876543210FEDCBA98765
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_prove_workload(log_m):
+    """The synthetic circuit and proving-key sizes, shared by both arms."""
+    from za_b200 import synthetic
+    nc = (1 << log_m) - 2
+    t = time.time()
+    cs = synthetic.mul_chain(nc, x0=0x5A410004)
+    counts = synthetic.pk_counts_for_mul_chain(nc)
+    return nc, cs, counts, time.time() - t
+
+
+def run_reference(args):
+    """The CPU restatement of bellman's create_proof on this host's cores (oracle/), same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from tests import oracle as O
+    cores = os.cpu_count() or 1
+    total_steps = args.steps + args.warmup
+    log_m = args.log_m if total_steps <= 6 else min(args.log_m, 18)        # bounded sample
+    nc, cs, counts, _ = cpu_prove_workload(log_m)
+    ni, na, ptr, var, coeff, inputs, aux = cs
+    ocs = O.CS(ni, na, ptr, var, coeff)
+    prm = O.Params.synthetic(counts["ic"], counts["h"], counts["l"], counts["a"], counts["b_g1"], counts["b_g2"], threads=cores)
+    times = []
+    for i in range(total_steps):
+        t = time.perf_counter()
+        rc, proof = prm.create_proof(ocs, inputs, aux, R_FIXED, S_FIXED, threads=cores)
+        dt = (time.perf_counter() - t) * 1e3
+        assert rc == 0
+        if i >= args.warmup:
+            times.append(dt)
+    ms = sum(times) / len(times)
+    scale = float(1 << (args.log_m - log_m))
+    value = ms * scale
+    sample = f"create_proof, mul-chain circuit, domain 2^{log_m}, {cores} threads" + \
+             (f"; linearly extrapolated x{int(scale)} to 2^{args.log_m}" if scale != 1 else "")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": value, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64-limb Montgomery (CPU)", "data": "synthetic",
+            "config": {"workload": f"synthetic mul-chain R1CS, domain 2^{args.log_m}: 7 NTT + 4 G1 MSM + 1 G2 MSM + 3 input MSMs",
+                       "log_m": args.log_m, "sample_log_m": log_m},
+            "cpu_baseline": {"value": value, "unit": "ms", "cores": cores, "kind": "port", "sample": sample,
+                             "note": "bellman-algorithm restatement (oracle/), not bellman itself"},
+            "e2e": {"value": value, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_gpu(args):
+    import torch
+    import za_b200
+    from za_b200 import synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = za_b200.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    log_m = args.log_m
+    nc, cs, counts, _ = cpu_prove_workload(log_m)
+    ni, na, ptr, var, coeff, inputs, aux = cs
+    circ = za_b200.Circuit(ctx, ni, na, ptr, var, coeff)
+    pk = za_b200.Parameters.synthetic(ctx, counts["ic"], counts["h"], counts["l"], counts["a"], counts["b_g1"], counts["b_g2"])
+    m = 1 << log_m
+    wit_host = torch.from_numpy(np.concatenate([inputs, aux])).pin_memory()
+    inputs_pin = torch.from_numpy(inputs.copy()).pin_memory()
+    aux_pin = torch.from_numpy(aux.copy()).pin_memory()
+    wit_dev = wit_host.to(dev, non_blocking=True)
+    h_dev = torch.zeros((m, 32), dtype=torch.uint8, device=dev)
+    partial_dev = torch.zeros(za_b200.PARTIALS_BYTES, dtype=torch.uint8, device=dev)
+    gathered = [torch.zeros_like(partial_dev) for _ in range(world)] if world > 1 else None
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def prove_device_step():
+        """One proof, witness resident on every GPU."""
+        if world == 1:
+            return za_b200.create_proof_device(ctx, pk, circ, wit_dev.data_ptr(), R_FIXED, S_FIXED)
+        if rank == 0:
+            za_b200.prove_h_device(ctx, circ, wit_dev.data_ptr(), h_dev.data_ptr())
+        # the h scalars are produced on rank 0; each rank needs its [lo, hi) slice: scatter over NCCL / NVLink
+        lo_hi = [za_b200.share(m - 1, k, world) for k in range(world)]
+        mine = h_dev[lo_hi[rank][0]:lo_hi[rank][1]]
+        if rank == 0:
+            reqs = [dist.isend(h_dev[lo:hi], dst=k) for k, (lo, hi) in enumerate(lo_hi) if k != 0 and hi > lo]
+            for q in reqs:
+                q.wait()
+        elif mine.shape[0]:
+            dist.recv(mine, src=0)
+        part = za_b200.prove_msm_partials(ctx, pk, circ, wit_dev.data_ptr(), h_dev.data_ptr(), rank, world)
+        partial_dev.copy_(torch.from_numpy(part), non_blocking=False)
+        dist.all_gather(gathered, partial_dev)
+        if rank == 0:
+            allp = torch.stack(gathered).cpu().numpy()
+            return za_b200.prove_assemble(pk, allp, R_FIXED, S_FIXED)
+        return None
+
+    def prove_e2e_step():
+        """Through the host-buffer API: witness H2D (pinned) and proof D2H inside."""
+        if world == 1:
+            return za_b200.create_proof(ctx, pk, circ, inputs_pin.numpy(), aux_pin.numpy(), R_FIXED, S_FIXED)
+        wit_dev.copy_(wit_host, non_blocking=True)
+        return prove_device_step()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    W = max(args.warmup, 3)
+    K = args.steps
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    # ---- headline: prove ms, witness resident
+    ctx.profile(True)
+    ctx.profile_read()
+    l0 = ctx.launch_count()
+    prove_ms, proof = timed(prove_device_step, K, W)
+    launches = (ctx.launch_count() - l0) // (K + W) * K
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    steps_profiled = K + W
+    # ---- e2e: host buffers
+    e2e_ms, proof_e2e = timed(prove_e2e_step, K, W)
+    if rank == 0:
+        assert proof == proof_e2e, "device-resident and host-buffer proofs differ"
+    clocks = sampler.summary() if sampler else None
+
+    line = None
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        imad_peak = za_b200.imad_peak(ctx)
+        acc1, acc2, nttp = prof["msm_accumulate_g1"], prof["msm_accumulate_g2"], prof["ntt"]
+        # dominant kernel of the step: the G1/G2 bucket-accumulation kernels (integer-pipe bound)
+        dom = acc1 if acc1["ms"] >= acc2["ms"] else acc2
+        dom_name = "msm_accumulate_kernel<Fq>" if dom is acc1 else "msm_accumulate_kernel<Fq2>"
+        per_madd = MODMUL_PER_MADD_G1 if dom is acc1 else MODMUL_PER_MADD_G2
+        imads = dom["work"] * per_madd * IMAD_PER_MODMUL
+        achieved = imads / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else 0.0
+        roofline = {"bound": "imad", "kernel": dom_name, "achieved": achieved, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
+                    "frac": achieved / (imad_peak / 1e12) if imad_peak else None, "traffic": None,
+                    "peak_source": "measured in this run (za_imad_peak: dependency-free mad.lo.u32 on all SMs)",
+                    "algorithmic": f"{int(dom['work'] / max(dom['spans'], 1))} mixed additions x {per_madd} modmul x {IMAD_PER_MODMUL} IMAD per launch",
+                    "launch_ms": dom["ms"] / max(dom["spans"], 1), "share_of_step": dom["ms"] / steps_profiled / prove_ms,
+                    "note": "tensor cores not applicable (multiprecision integer); HBM needs 96 B/point, two orders below compute"}
+        ntt_bytes = 64.0 * nttp["work"]
+        ntt_gbs = ntt_bytes / (nttp["ms"] * 1e-3) / 1e9 if nttp["ms"] > 0 else 0.0
+        roofline_ntt = {"bound": "hbm", "kernel": "ntt_pass_kernel (one transform = 3 passes at 2^20)", "achieved": ntt_gbs, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": ntt_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic": "64 B per element per transform (one 32 B read + one 32 B write)",
+                        "imad_frac": (IMAD_PER_MODMUL * (nttp["work"] / 2) * log_m / (nttp["ms"] * 1e-3)) / imad_peak if nttp["ms"] > 0 else None}
+        breakdown = {k: round(v["ms"] / steps_profiled, 4) for k, v in prof.items() if v["ms"] > 0}
+        h2d = int(wit_host.numel())
+        line = {"metric": METRIC, "value": prove_ms, "unit": "ms", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": prove_ms,
+                "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {"workload": f"synthetic mul-chain R1CS, {nc} constraints (domain 2^{log_m}), {na} aux: "
+                                       "7 NTT + 4 G1 MSM + 1 G2 MSM + 3 input MSMs per proof; synthetic proving key "
+                                       "(bases = known multiples of the generators), r and s fixed",
+                           "log_m": log_m, "parallelism": f"msm point-range x{world}" if world > 1 else "single GPU",
+                           "l2": "inputs larger than L2: proving key 470 MB + witness 32 MB per step"},
+                "roofline": roofline, "roofline_ntt": roofline_ntt, "kernel_ms_per_step": breakdown,
+                "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 256 + 16 * 128 * 5 + 16 * 256},
+                "gpu_launches": int(launches), "clocks": clocks, "imad_peak_timads": imad_peak / 1e12}
+
+    # ---- sub-metrics (rank-local, N = 1 only): 2^log_msm-point G1 MSM and 2^log_ntt Fr NTT, inputs resident
+    if world == 1:
+        sub = {}
+        n_msm = 1 << args.log_msm
+        bases = za_b200.Bases.generate(ctx, 1, n_msm, 1)
+        sc = torch.from_numpy(synthetic.random_scalars(n_msm, 0x5A410005)).to(dev)
+        torch.cuda.synchronize()
+        ctx.profile(True)
+        ctx.profile_read()
+        msm_ms, _ = timed(lambda: za_b200.multiexp_device(ctx, bases, sc.data_ptr(), n_msm), max(2, min(K, 5)), 3)
+        p2 = ctx.profile_read()
+        ctx.profile(False)
+        a = p2["msm_accumulate_g1"]
+        sub["g1_msm"] = {"log_n": args.log_msm, "ms": msm_ms, "mpts_s": n_msm / msm_ms / 1e3, "scalars": "uniform 253-bit",
+                         "accumulate_ms": a["ms"] / max(a["spans"], 1), "sort_ms": p2["msm_sort"]["ms"] / max(a["spans"], 1),
+                         "reduce_ms": p2["msm_reduce"]["ms"] / max(a["spans"], 1),
+                         "imad_frac": (a["work"] * MODMUL_PER_MADD_G1 * IMAD_PER_MODMUL / (a["ms"] * 1e-3)) / za_b200.imad_peak(ctx) if a["ms"] else None}
+        scw = torch.from_numpy(synthetic.witness_like_scalars(n_msm, 0x5A410006)).to(dev)
+        msm_w_ms, _ = timed(lambda: za_b200.multiexp_device(ctx, bases, scw.data_ptr(), n_msm), 2, 3)
+        sub["g1_msm_witness_like"] = {"log_n": args.log_msm, "ms": msm_w_ms, "mpts_s": n_msm / msm_w_ms / 1e3, "scalars": "40% 0, 30% 1, 30% uniform"}
+        del bases, sc, scw
+        n_ntt = 1 << args.log_ntt
+        v = torch.from_numpy(synthetic.random_scalars(n_ntt, 0x5A410007)).to(dev)
+        torch.cuda.synchronize()
+        ntt_ms, _ = timed(lambda: ctx.ntt_device(v.data_ptr(), args.log_ntt, za_b200.FFT), max(2, min(K, 5)), 3)
+        hbm_peak, _ = peaks()
+        sub["fr_ntt"] = {"log_n": args.log_ntt, "ms": ntt_ms, "gelem_s": n_ntt / ntt_ms / 1e6, "hbm_frac": 64.0 * n_ntt / (ntt_ms * 1e-3) / 1e9 / hbm_peak,
+                         "order": "natural in, natural out, forward"}
+        del v
+        if line is not None:
+            line["submetrics"] = sub
+
+    # ---- CPU baseline beside it (rank 0, N = 1): bounded sample of the same workload; also the full-size checker
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from tests import oracle as O
+        cores = os.cpu_count() or 1
+        log_s = min(log_m, args.cpu_log_m)
+        nc_s, cs_s, counts_s, _ = cpu_prove_workload(log_s)
+        ocs = O.CS(cs_s[0], cs_s[1], cs_s[2], cs_s[3], cs_s[4])
+        prm = O.Params.synthetic(counts_s["ic"], counts_s["h"], counts_s["l"], counts_s["a"], counts_s["b_g1"], counts_s["b_g2"], threads=cores)
+        t = time.perf_counter()
+        rc, cpu_proof = prm.create_proof(ocs, cs_s[5], cs_s[6], R_FIXED, S_FIXED, threads=cores)
+        cpu_ms = (time.perf_counter() - t) * 1e3
+        assert rc == 0
+        if log_s == log_m:
+            parity = cpu_proof == proof
+        else:
+            c2 = za_b200.Circuit(ctx, cs_s[0], cs_s[1], cs_s[2], cs_s[3], cs_s[4])
+            pk2 = za_b200.Parameters.synthetic(ctx, counts_s["ic"], counts_s["h"], counts_s["l"], counts_s["a"], counts_s["b_g1"], counts_s["b_g2"])
+            parity = cpu_proof == za_b200.create_proof(ctx, pk2, c2, cs_s[5], cs_s[6], R_FIXED, S_FIXED)
+        scale = float(1 << (log_m - log_s))
+        line["cpu_baseline"] = {"value": cpu_ms * scale, "unit": "ms", "cores": cores, "kind": "port",
+                                "sample": f"one create_proof, domain 2^{log_s}, {cores} threads" +
+                                          (f", extrapolated x{int(scale)}" if scale != 1 else ""),
+                                "note": "bellman-algorithm restatement (oracle/), not bellman itself",
+                                "proof_matches_gpu": bool(parity)}
+        if not parity:
+            print("PARITY FAILURE: CPU oracle proof differs from the GPU proof", file=sys.stderr)
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="za_b200", choices=["za_b200", "reference"])
+    ap.add_argument("--log-m", dest="log_m", type=int, default=20, help="log2 of the evaluation domain of the prove workload")
+    ap.add_argument("--log-msm", dest="log_msm", type=int, default=24)
+    ap.add_argument("--log-ntt", dest="log_ntt", type=int, default=24)
+    ap.add_argument("--cpu-log-m", dest="cpu_log_m", type=int, default=20, help="domain of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -83,6 +83,14 @@ int za_ctx_synchronize(za_ctx *ctx);
 /* Kernels launched through this context so far (bench.py reports the delta as gpu_launches). */
 uint64_t za_ctx_launch_count(const za_ctx *ctx);
 
+/* Per-kernel-class device timing (CUDA events on the context's stream), used by bench.py for the roofline
+ * numbers.  za_ctx_profile_read synchronises, fills out[24] = ms[8] | work[8] | spans[8] and resets.
+ * Classes: 0 msm_accumulate G1 (work = mixed additions), 1 msm_accumulate G2, 2 NTT transform (work = elements),
+ * 3 MSM digit sort (work = scalars), 4 MSM bucket reduction (work = buckets), 5 constraint evaluation (work = rows),
+ * 6 H pointwise (work = elements), 7 unused. */
+int za_ctx_profile(za_ctx *ctx, int on);
+int za_ctx_profile_read(za_ctx *ctx, double *out);
+
 /* ---- EvaluationDomain --------------------------------------------------------------------
  * Replaces bellman_ce domain.rs EvaluationDomain::{fft, ifft, coset_fft, icoset_fft} as used by
  * create_proof (entered at prover.rs:173).  Natural order in and out, like bellman's.
@@ -147,6 +155,39 @@ void za_circuit_free(za_circuit *c);
  * aux: num_aux.  proof_out: 256 bytes. */
 int za_create_proof(za_ctx *ctx, const za_pk *pk, const za_circuit *circuit, const uint8_t *inputs, const uint8_t *aux,
                     const uint8_t *r, const uint8_t *s, uint8_t *proof_out, za_trace *trace);
+/* Same with the witness [inputs | aux] (canonical, (num_inputs+num_aux)*32 bytes) already in device memory. */
+int za_create_proof_device(za_ctx *ctx, const za_pk *pk, const za_circuit *circuit, const void *d_witness,
+                           const uint8_t *r, const uint8_t *s, uint8_t *proof_out);
+/* info[7] = num_inputs, num_aux, num_constraints, |a_aux_density|, |b_input_density|, |b_aux_density|, log2(m) */
+int za_circuit_info(const za_circuit *circuit, uint32_t *info);
+
+/* ---- create_proof in stages, for one process per GPU ----------------------------------
+ * Stage 1, one GPU: witness -> a, b, c -> H coefficients.  d_h: m * 32 bytes of device memory; on
+ *   return its first m-1 entries are the canonical h scalars.
+ * Stage 2, every GPU (each holds the proving key): the eight multiexps restricted to this rank's
+ *   contiguous point range of every query; d_h needs to be valid on [lo, hi) = share of m-1 only.
+ *   partials_out: ZA_PARTIALS_BYTES (6 G1 + 2 G2 XYZZ sums, canonical coordinates).
+ * Stage 3, host: add the `world` partial records and assemble the proof (a few group operations). */
+#define ZA_PARTIALS_BYTES 1280
+int za_prove_h_device(za_ctx *ctx, const za_circuit *circuit, const void *d_witness, void *d_h);
+int za_prove_msm_partials(za_ctx *ctx, const za_pk *pk, const za_circuit *circuit, const void *d_witness,
+                          const void *d_h, int rank, int world, uint8_t *partials_out);
+int za_prove_assemble(const za_pk *pk, const uint8_t *partials, int world, const uint8_t *r, const uint8_t *s,
+                      uint8_t *proof_out);
+
+/* ---- synthetic inputs and measurement utilities ---------------------------------------
+ * bases[i] = (first_multiple + i) * G: distinct points with known discrete logarithms, so a full-size
+ * multiexp is checkable with one scalar multiplication.  Generated on the GPU. */
+int za_bases_generate(za_ctx *ctx, int group, size_t n, uint64_t first_multiple, za_bases **out);
+int za_bases_download(za_ctx *ctx, const za_bases *bases, size_t offset, size_t n, uint8_t *out);
+/* A proving key of the given query sizes (counts[6] = |ic|, |h|, |l|, |a|, |b_g1|, |b_g2|) whose bases are
+ * known multiples of the generators: query q entry i = ((q+1) * 2^32 + i + 1) * G with q = 0..3 for
+ * h, l, a, b (b_g1 and b_g2 share multipliers); alpha, beta, gamma, delta = 3, 5, 7, 11; ic[i] = 13 + i.
+ * Not a valid CRS — the work per proof is identical and every proof element has a closed form. */
+int za_pk_synthetic(za_ctx *ctx, const uint32_t *counts, za_pk **out);
+/* Measured 32-bit integer multiply-add throughput of the device (dependency-free mad.lo.u32 on all SMs). */
+int za_imad_peak(za_ctx *ctx, double *imads_per_second);
+
 /* JsonProofAndInput (format.rs:80-128): compact JSON, "0x"+64 hex coordinates, decimal public inputs.
  * public_inputs: n canonical scalars. Returns ZA_ERR_BUFFER_TOO_SMALL if len >= size (binding/c lib.rs:23). */
 int za_proof_to_json(const uint8_t *proof, const uint8_t *public_inputs, size_t n_public, char *buf, size_t size);

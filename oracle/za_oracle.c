@@ -551,6 +551,79 @@ fail:
     ora_params_free(p); return NULL;
 }
 
+/* Synthetic Parameters (bench + full-size property tests; mirrors the definition in include/za_b200.h
+ * za_pk_synthetic — written independently): query q entry i = ((q+1) * 2^32 + i + 1) * G,
+ * alpha, beta, gamma, delta = 3, 5, 7, 11, ic[i] = 13 + i.  Not a valid CRS. */
+typedef struct { g1_affine *out1; g2_affine *out2; uint64_t first; } chain_t;
+static void chain_g1_fn(void *p, size_t lo, size_t hi, int tid) {
+    (void)tid; chain_t *c = p; if (lo >= hi) return;
+    uint8_t gen[64], tmp[64], k[32] = {0}; ora_g1_generator(gen);
+    uint64_t f = c->first + lo; memcpy(k, &f, 8);
+    ora_g1_mul(gen, k, tmp);                                   /* (first+lo) * G */
+    g1_affine g = g1_load(gen), cur_a = g1_load(tmp); g1_jac acc = g1_from_affine(&cur_a);
+    g1_jac *buf = malloc(sizeof(g1_jac) * MULT_BATCH); fe *pre = malloc(sizeof(fe) * MULT_BATCH);
+    for (size_t s = lo; s < hi; s += MULT_BATCH) {
+        size_t m = hi - s < MULT_BATCH ? hi - s : MULT_BATCH;
+        for (size_t i = 0; i < m; i++) { buf[i] = acc; g1_add_mixed(&acc, &g); }
+        fe run = fe_one(&FQ);
+        for (size_t i = 0; i < m; i++) { pre[i] = run; run = fe_mul(&FQ, &run, &buf[i].z); }
+        run = fe_inv(&FQ, &run);
+        for (size_t i = m; i-- > 0;) {
+            fe zi = fe_mul(&FQ, &run, &pre[i]); run = fe_mul(&FQ, &run, &buf[i].z);
+            fe zi2 = fe_sqr(&FQ, &zi), zi3 = fe_mul(&FQ, &zi2, &zi);
+            g1_affine a; a.x = fe_mul(&FQ, &buf[i].x, &zi2); a.y = fe_mul(&FQ, &buf[i].y, &zi3); a.inf = 0;
+            c->out1[s + i] = a;
+        }
+    }
+    free(buf); free(pre);
+}
+static void chain_g2_fn(void *p, size_t lo, size_t hi, int tid) {
+    (void)tid; chain_t *c = p; if (lo >= hi) return;
+    uint8_t gen[128], tmp[128], k[32] = {0}; ora_g2_generator(gen);
+    uint64_t f = c->first + lo; memcpy(k, &f, 8);
+    ora_g2_mul(gen, k, tmp);
+    g2_affine g = g2_load(gen), cur_a = g2_load(tmp); g2_jac acc = g2_from_affine(&cur_a);
+    g2_jac *buf = malloc(sizeof(g2_jac) * MULT_BATCH); fe2 *pre = malloc(sizeof(fe2) * MULT_BATCH);
+    for (size_t s = lo; s < hi; s += MULT_BATCH) {
+        size_t m = hi - s < MULT_BATCH ? hi - s : MULT_BATCH;
+        for (size_t i = 0; i < m; i++) { buf[i] = acc; g2_add_mixed(&acc, &g); }
+        fe2 run = fe2_one();
+        for (size_t i = 0; i < m; i++) { pre[i] = run; run = fe2_mul(&run, &buf[i].z); }
+        run = fe2_inv(&run);
+        for (size_t i = m; i-- > 0;) {
+            fe2 zi = fe2_mul(&run, &pre[i]); run = fe2_mul(&run, &buf[i].z);
+            fe2 zi2 = fe2_sqr(&zi), zi3 = fe2_mul(&zi2, &zi);
+            g2_affine a; a.x = fe2_mul(&buf[i].x, &zi2); a.y = fe2_mul(&buf[i].y, &zi3); a.inf = 0;
+            c->out2[s + i] = a;
+        }
+    }
+    free(buf); free(pre);
+}
+static g1_affine g1_small_multiple(uint64_t k) {
+    uint8_t gen[64], tmp[64], kb[32] = {0}; ora_g1_generator(gen); memcpy(kb, &k, 8); ora_g1_mul(gen, kb, tmp); return g1_load(tmp);
+}
+static g2_affine g2_small_multiple(uint64_t k) {
+    uint8_t gen[128], tmp[128], kb[32] = {0}; ora_g2_generator(gen); memcpy(kb, &k, 8); ora_g2_mul(gen, kb, tmp); return g2_load(tmp);
+}
+void *ora_params_synthetic(const uint32_t *counts, int threads) {
+    params_t *p = calloc(1, sizeof(params_t));
+    p->alpha_g1 = g1_small_multiple(3); p->beta_g1 = g1_small_multiple(5); p->delta_g1 = g1_small_multiple(11);
+    p->beta_g2 = g2_small_multiple(5); p->gamma_g2 = g2_small_multiple(7); p->delta_g2 = g2_small_multiple(11);
+    p->n_ic = counts[0]; p->ic = malloc(sizeof(g1_affine) * ((size_t)counts[0] + 1));
+    for (uint32_t i = 0; i < counts[0]; i++) p->ic[i] = g1_small_multiple(13 + i);
+    p->n_h = counts[1]; p->n_l = counts[2]; p->n_a = counts[3]; p->n_bg1 = counts[4]; p->n_bg2 = counts[5];
+    p->h = malloc(sizeof(g1_affine) * ((size_t)p->n_h + 1)); p->l = malloc(sizeof(g1_affine) * ((size_t)p->n_l + 1));
+    p->a = malloc(sizeof(g1_affine) * ((size_t)p->n_a + 1)); p->b_g1 = malloc(sizeof(g1_affine) * ((size_t)p->n_bg1 + 1));
+    p->b_g2 = malloc(sizeof(g2_affine) * ((size_t)p->n_bg2 + 1));
+    chain_t c; c.out2 = NULL;
+    c.out1 = p->h; c.first = ((uint64_t)1 << 32) + 1; worker_scope(threads, p->n_h, chain_g1_fn, &c);
+    c.out1 = p->l; c.first = ((uint64_t)2 << 32) + 1; worker_scope(threads, p->n_l, chain_g1_fn, &c);
+    c.out1 = p->a; c.first = ((uint64_t)3 << 32) + 1; worker_scope(threads, p->n_a, chain_g1_fn, &c);
+    c.out1 = p->b_g1; c.first = ((uint64_t)4 << 32) + 1; worker_scope(threads, p->n_bg1, chain_g1_fn, &c);
+    c.out1 = NULL; c.out2 = p->b_g2; c.first = ((uint64_t)4 << 32) + 1; worker_scope(threads, p->n_bg2, chain_g2_fn, &c);
+    return p;
+}
+
 /* ------------------------------------------------- ProvingAssignment::eval
  * bellman groth16/prover.rs `eval`: acc += coeff * value in insertion order, coeff == 1 skips the
  * multiply, density.inc(i) for every term regardless of coefficient or value. */

@@ -82,6 +82,8 @@ size_t ora_params_size(const void *params);
 int ora_params_write(const void *params, uint8_t *buf);
 void *ora_params_read(const uint8_t *buf, size_t len, int checked, int *err);
 void ora_params_free(void *params);
+/* counts[6] = ic,h,l,a,b_g1,b_g2: bases are known multiples of the generators (not a valid CRS) */
+void *ora_params_synthetic(const uint32_t *counts, int threads);
 void ora_params_counts(const void *params, uint32_t *counts /* ic,h,l,a,b_g1,b_g2 */);
 int ora_create_proof(const void *params, const ora_r1cs *cs, const uint8_t *inputs, const uint8_t *aux,
                      const uint8_t *r, const uint8_t *s, uint8_t *proof, ora_trace *trace, int threads);

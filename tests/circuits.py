@@ -51,31 +51,12 @@ def mul_chain(num_constraints, x0=3, extra_linear=True):
 
 
 def mul_chain_fast(num_constraints, x0=3):
-    """Same shape as mul_chain(extra_linear=False) but vectorised for 2^16..2^20 rows.
-    The squaring chain itself is sequential python-int work (~1 us per step)."""
-    nc = num_constraints
-    vals = np.zeros((nc + 1, 32), np.uint8)
-    v = x0 % R_MOD
-    for k in range(nc + 1):
-        vals[k] = np.frombuffer(v.to_bytes(32, "little"), np.uint8)
-        v = v * v % R_MOD
-    one = np.zeros((1, 32), np.uint8); one[0, 0] = 1
-    ptr = np.arange(nc + 1, dtype=np.uint32)
-    va = (np.arange(nc, dtype=np.uint32) | np.uint32(AUX))
-    vc = (np.arange(1, nc + 1, dtype=np.uint32) | np.uint32(AUX))
-    vc[nc - 1] = 1
-    ones = np.repeat(one, nc, axis=0)
-    inputs = np.stack([one[0], vals[nc]])
-    return (2, nc, [ptr, ptr.copy(), ptr.copy()], [va, va.copy(), vc], [ones, ones.copy(), ones.copy()], inputs, vals[:nc].copy())
+    """The config-2/4 circuit (za_b200.synthetic.mul_chain)."""
+    from za_b200.synthetic import mul_chain as mc
+    return mc(num_constraints, x0)
 
 
 def witness_like(n, seed):
     """Config 5a second distribution: 40 % zeros, 30 % ones, 30 % uniform."""
-    from tests.oracle import random_frs
-    rng = np.random.default_rng(seed)
-    s = random_frs(n, seed + 1)
-    u = rng.random(n)
-    s[u < 0.4] = 0
-    one = np.zeros(32, np.uint8); one[0] = 1
-    s[(u >= 0.4) & (u < 0.7)] = one
-    return s
+    from za_b200.synthetic import witness_like_scalars
+    return witness_like_scalars(n, seed)

@@ -45,6 +45,8 @@ def lib():
         L = ctypes.CDLL(build())
         L.ora_generate_parameters.restype = ctypes.c_void_p
         L.ora_params_read.restype = ctypes.c_void_p
+        L.ora_params_synthetic.restype = ctypes.c_void_p
+        L.ora_params_synthetic.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.ora_params_size.restype = ctypes.c_size_t
         L.ora_params_size.argtypes = [ctypes.c_void_p]
         L.ora_params_write.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
@@ -235,6 +237,11 @@ class Params:
         if not h:
             raise RuntimeError(f"ora_params_read failed: {err.value}")
         return cls(h)
+
+    @classmethod
+    def synthetic(cls, ic, h, l, a, b_g1, b_g2, threads=1):
+        c = (ctypes.c_uint32 * 6)(ic, h, l, a, b_g1, b_g2)
+        return cls(lib().ora_params_synthetic(c, threads))
 
     def write(self):
         n = lib().ora_params_size(self.h)

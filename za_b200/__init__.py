@@ -6,5 +6,6 @@ PyTorch or oracle fallback anywhere in this package.
 """
 from . import _lib  # noqa: F401
 from ._lib import ZaError  # noqa: F401
-from .groth16 import (Context, Bases, Parameters, Circuit, create_proof, multiexp, multiexp_device, point_sum,  # noqa: F401
-                      proof_to_json, FFT, IFFT, COSET_FFT, ICOSET_FFT)
+from .groth16 import (Context, Bases, Parameters, Circuit, create_proof, create_proof_device, multiexp,  # noqa: F401
+                      multiexp_device, point_sum, prove_h_device, prove_msm_partials, prove_assemble, share,
+                      imad_peak, proof_to_json, PARTIALS_BYTES, FFT, IFFT, COSET_FFT, ICOSET_FFT)

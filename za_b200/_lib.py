@@ -50,6 +50,8 @@ SYMBOLS = {
     "za_ctx_set_stream": (ci, [vp, vp]),
     "za_ctx_synchronize": (ci, [vp]),
     "za_ctx_launch_count": (ctypes.c_uint64, [vp]),
+    "za_ctx_profile": (ci, [vp, ci]),
+    "za_ctx_profile_read": (ci, [vp, vp]),
     "za_ntt": (ci, [vp, vp, ci, ci]),
     "za_ntt_device": (ci, [vp, vp, ci, ci, ci]),
     "za_fr_convert_device": (ci, [vp, vp, sz, ci]),
@@ -69,6 +71,15 @@ SYMBOLS = {
     "za_circuit_upload": (ci, [vp, vp, ctypes.POINTER(vp)]),
     "za_circuit_free": (None, [vp]),
     "za_create_proof": (ci, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "za_create_proof_device": (ci, [vp, vp, vp, vp, vp, vp, vp]),
+    "za_circuit_info": (ci, [vp, vp]),
+    "za_prove_h_device": (ci, [vp, vp, vp, vp]),
+    "za_prove_msm_partials": (ci, [vp, vp, vp, vp, vp, ci, ci, vp]),
+    "za_prove_assemble": (ci, [vp, vp, ci, vp, vp, vp]),
+    "za_bases_generate": (ci, [vp, ci, sz, ctypes.c_uint64, ctypes.POINTER(vp)]),
+    "za_bases_download": (ci, [vp, vp, sz, sz, vp]),
+    "za_pk_synthetic": (ci, [vp, vp, ctypes.POINTER(vp)]),
+    "za_imad_peak": (ci, [vp, ctypes.POINTER(ctypes.c_double)]),
     "za_proof_to_json": (ci, [vp, vp, sz, ctypes.c_char_p, sz]),
 }
 

@@ -101,6 +101,33 @@ int za_ctx_synchronize(za_ctx* ctx) {
 
 uint64_t za_ctx_launch_count(const za_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
 
+int za_ctx_profile(za_ctx* ctx, int on) {
+    if (!ctx) return fail(ZA_ERR_INVALID, "ctx is NULL");
+    ctx->c.profile = on != 0;
+    return ZA_OK;
+}
+
+int za_ctx_profile_read(za_ctx* ctx, double* out) {
+    if (!ctx || !out) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    Ctx* c = &ctx->c;
+    ZA_CUDA(cudaSetDevice(c->device));
+    ZA_CUDA(cudaStreamSynchronize(c->stream));
+    double ms[PROF_NCAT] = {0};
+    for (ProfSpan& sp : c->spans) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) ms[sp.cat] += t;
+        cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+    }
+    c->spans.clear();
+    for (int i = 0; i < PROF_NCAT; i++) {
+        out[i] = ms[i]; out[PROF_NCAT + i] = c->prof_work[i]; out[2 * PROF_NCAT + i] = (double)c->prof_count[i];
+        c->prof_work[i] = 0; c->prof_count[i] = 0;
+    }
+    return ZA_OK;
+    ZA_CATCH
+}
+
 // ------------------------------------------------------------------------------------- NTT
 int za_fr_convert_device(za_ctx* ctx, void* d_data, size_t n, int dir) {
     if (!ctx || !d_data) return fail(ZA_ERR_INVALID, "NULL argument");

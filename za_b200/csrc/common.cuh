@@ -73,6 +73,9 @@ struct NttDomain {
     bool have_coset = false;
 };
 
+enum { PROF_ACC_G1 = 0, PROF_ACC_G2 = 1, PROF_NTT = 2, PROF_MSM_SORT = 3, PROF_MSM_REDUCE = 4, PROF_R1CS = 5, PROF_POINTWISE = 6, PROF_OTHER = 7, PROF_NCAT = 8 };
+struct ProfSpan { cudaEvent_t a, b; int cat; };
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;      // stream all work of this context is issued on
@@ -82,9 +85,30 @@ struct Ctx {
     // scratch reused across calls
     DevBuf scratch[8];
     uint64_t launches = 0;              // kernels launched through this context (bench: gpu_launches)
+    // optional per-kernel-class timing with CUDA events on `stream` (bench.py roofline numbers)
+    bool profile = false;
+    std::vector<ProfSpan> spans;
+    double prof_work[PROF_NCAT] = {0};  // algorithmic work units per class (mixed additions, elements, ...)
+    uint64_t prof_count[PROF_NCAT] = {0};
     ~Ctx();
 };
 
 NttDomain* get_domain(Ctx* ctx, int log_n, bool need_coset);
+
+// RAII: brackets the kernels issued in its scope with two events when profiling is on
+struct ProfScope {
+    Ctx* c; int cat; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(Ctx* ctx, int category, double work = 0) : c(ctx), cat(category) {
+        if (!c->profile) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+        c->prof_work[cat] += work; c->prof_count[cat]++;
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, c->stream);
+        c->spans.push_back(ProfSpan{a, b, cat});
+    }
+};
 
 }  // namespace za

@@ -331,6 +331,70 @@ __global__ void xyzz_export_kernel(XYZZ<F>* pts, uint32_t n) {
     st_vec(pts + i, p);
 }
 
+// ---- synthetic bases: out[i] = (first + i) * G, distinct points with known
+// discrete logarithms so that a full-size MSM can be checked with one scalar multiplication.
+template <class F>
+__global__ void __launch_bounds__(128) bases_gen_chain_kernel(XYZZ<F>* out, size_t n, uint64_t first, const Affine<F> G, int chunk) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t start = t * (size_t)chunk;
+    if (start >= n) return;
+    uint64_t k = first + start;
+    XYZZ<F> P = XYZZ<F>::inf();
+    for (int b = 63 - __clzll((long long)k); b >= 0; b--) {
+        P = xyzz_dbl<F>(P);
+        if ((k >> b) & 1ull) xyzz_madd<F>(P, G.x, G.y, false);
+    }
+    size_t end = start + chunk < n ? start + chunk : n;
+    for (size_t i = start; i < end; i++) {
+        st_vec(out + i, P);
+        xyzz_madd<F>(P, G.x, G.y, false);
+    }
+}
+#define GEN_CHUNK 32
+template <class F>
+__global__ void __launch_bounds__(128) bases_gen_normalise_kernel(const XYZZ<F>* in, Affine<F>* out, size_t n) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t start = t * (size_t)GEN_CHUNK;
+    if (start >= n) return;
+    const int cnt = (int)(start + GEN_CHUNK < n ? GEN_CHUNK : n - start);
+    F pre[GEN_CHUNK];                     // running products of ZZ*ZZZ (Montgomery's simultaneous inversion)
+    F run = F::one();
+    for (int j = 0; j < cnt; j++) {
+        XYZZ<F> p = ld_vec(in + start + j);
+        pre[j] = run;
+        run = run * (p.ZZ * p.ZZZ);
+    }
+    F iv = inv(run);
+    for (int j = cnt - 1; j >= 0; j--) {
+        XYZZ<F> p = ld_vec(in + start + j);
+        F tj = iv * pre[j];               // 1 / (ZZ_j ZZZ_j)
+        iv = iv * (p.ZZ * p.ZZZ);
+        Affine<F> a;
+        a.x = p.X * (tj * p.ZZZ);
+        a.y = p.Y * (tj * p.ZZ);
+        st_vec(out + start + j, a);
+    }
+}
+
+// Integer-pipe peak probe: dependency-free mad.lo.u32 chains, 8 independent accumulators per thread.
+__global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, uint32_t a, uint32_t b, int iters) {
+    uint32_t x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x0) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x1) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x2) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x3) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x4) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x5) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x6) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x7) : "r"(a), "r"(b));
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+}
+
 // ------------------------------------------------------------------------------------------ host
 template <class F> struct GroupInfo;
 template <> struct GroupInfo<Fq> { static constexpr int NF_AFF = 2, NF_XYZZ = 4; };
@@ -458,20 +522,33 @@ XYZZ<F> msm_run(Ctx* ctx, const Affine<F>* d_bases, const uint32_t* d_scalars, s
     ZA_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nkeys * 4, st));
     ZA_CUDA(cudaMemsetAsync(buckets.p, 0, (size_t)nkeys * sizeof(XYZZ<F>), st));
     ZA_CUDA(cudaMemsetAsync(d_owner, 0xff, (size_t)nchunks * 4, st));
-    msm_digits_hist_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_counts);
-    msm_scan_kernel<<<1, 1024, 0, st>>>(d_counts, nkeys, d_offsets, d_cursors);
-    msm_digits_scatter_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_cursors, entries.as<uint32_t>());
-    msm_accumulate_kernel<F><<<nblk(nchunks, 128), 128, 0, st>>>(d_bases, entries.as<uint32_t>(), d_offsets, nkeys, Lc,
-                                                                 buckets.as<XYZZ<F>>(), d_head, d_tail, d_owner);
-    msm_fixup_kernel<F><<<nblk((size_t)nchunks * 32, 128), 128, 0, st>>>(d_offsets, nkeys, Lc, nchunks, d_head, d_tail, d_owner,
-                                                                         buckets.as<XYZZ<F>>());
-    msm_bucket_reduce_kernel<F><<<nblk(total_segs, 128), 128, 0, st>>>(buckets.as<XYZZ<F>>(), B, seg, segs_per_window, total_segs, d_seg);
-    msm_group_reduce_kernel<F><<<nblk((size_t)W * 32, 128), 128, 0, st>>>(d_seg, segs_per_window, (uint32_t)W, d_win);
+    {
+        ProfScope prof(ctx, PROF_MSM_SORT, (double)n);
+        msm_digits_hist_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_counts);
+        msm_scan_kernel<<<1, 1024, 0, st>>>(d_counts, nkeys, d_offsets, d_cursors);
+        msm_digits_scatter_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_cursors, entries.as<uint32_t>());
+    }
+    const int acc_cat = sizeof(F) == sizeof(Fq) ? PROF_ACC_G1 : PROF_ACC_G2;
+    {
+        ProfScope prof(ctx, acc_cat, 0);
+        msm_accumulate_kernel<F><<<nblk(nchunks, 128), 128, 0, st>>>(d_bases, entries.as<uint32_t>(), d_offsets, nkeys, Lc,
+                                                                     buckets.as<XYZZ<F>>(), d_head, d_tail, d_owner);
+    }
+    {
+        ProfScope prof(ctx, PROF_MSM_REDUCE, (double)nkeys);
+        msm_fixup_kernel<F><<<nblk((size_t)nchunks * 32, 128), 128, 0, st>>>(d_offsets, nkeys, Lc, nchunks, d_head, d_tail, d_owner,
+                                                                             buckets.as<XYZZ<F>>());
+        msm_bucket_reduce_kernel<F><<<nblk(total_segs, 128), 128, 0, st>>>(buckets.as<XYZZ<F>>(), B, seg, segs_per_window, total_segs, d_seg);
+        msm_group_reduce_kernel<F><<<nblk((size_t)W * 32, 128), 128, 0, st>>>(d_seg, segs_per_window, (uint32_t)W, d_win);
+    }
     ctx->launches += 7;
     ZA_CUDA(cudaGetLastError());
     std::vector<XYZZ<F>> win(W);
     ZA_CUDA(cudaMemcpyAsync(win.data(), d_win, (size_t)W * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
+    uint32_t E_host = 0;
+    if (ctx->profile) ZA_CUDA(cudaMemcpyAsync(&E_host, d_offsets + nkeys, 4, cudaMemcpyDeviceToHost, st));
     ZA_CUDA(cudaStreamSynchronize(st));
+    if (ctx->profile) ctx->prof_work[acc_cat] += (double)E_host;   // mixed additions actually performed
     // window combination on the host: result = sum_w 2^(c w) S_w   (bellman: `higher.double()` x c, then add)
     for (int w = W - 1; w >= 0; w--) {
         for (int k = 0; k < c; k++) result = xyzz_dbl<F>(result);
@@ -481,5 +558,43 @@ XYZZ<F> msm_run(Ctx* ctx, const Affine<F>* d_bases, const uint32_t* d_scalars, s
 }
 template XYZZ<Fq> msm_run<Fq>(Ctx*, const Affine<Fq>*, const uint32_t*, size_t, bool);
 template XYZZ<Fq2> msm_run<Fq2>(Ctx*, const Affine<Fq2>*, const uint32_t*, size_t, bool);
+
+template <class F>
+void bases_generate(Ctx* ctx, Affine<F>* d_out, size_t n, uint64_t first, const Affine<F>& G) {
+    if (!n) return;
+    DevBuf tmp(n * sizeof(XYZZ<F>));
+    size_t threads = (n + GEN_CHUNK - 1) / GEN_CHUNK;
+    bases_gen_chain_kernel<F><<<nblk(threads, 128), 128, 0, ctx->stream>>>(tmp.as<XYZZ<F>>(), n, first, G, GEN_CHUNK);
+    bases_gen_normalise_kernel<F><<<nblk(threads, 128), 128, 0, ctx->stream>>>(tmp.as<XYZZ<F>>(), d_out, n);
+    ctx->launches += 2;
+    ZA_CUDA(cudaGetLastError());
+    ZA_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+template void bases_generate<Fq>(Ctx*, Affine<Fq>*, size_t, uint64_t, const Affine<Fq>&);
+template void bases_generate<Fq2>(Ctx*, Affine<Fq2>*, size_t, uint64_t, const Affine<Fq2>&);
+
+// measured 32-bit multiply-add throughput of the whole chip, in IMAD/s
+double imad_peak(Ctx* ctx) {
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 2000;
+    DevBuf out((size_t)blocks * threads * 4);
+    cudaEvent_t e0, e1;
+    ZA_CUDA(cudaEventCreate(&e0));
+    ZA_CUDA(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        ZA_CUDA(cudaEventRecord(e0, ctx->stream));
+        imad_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(out.as<uint32_t>(), 0x9e3779b1u, 0x7f4a7c15u, iters);
+        ZA_CUDA(cudaEventRecord(e1, ctx->stream));
+        ZA_CUDA(cudaEventSynchronize(e1));
+        ctx->launches++;
+        float ms = 0;
+        ZA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double rate = (double)blocks * threads * iters * 128.0 / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return best;
+}
 
 }  // namespace za

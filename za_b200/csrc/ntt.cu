@@ -300,6 +300,7 @@ static std::vector<int> plan_passes(int n) {
 void ntt_run(Ctx* ctx, Fr* buf, Fr* scratch, int n, int batch, bool inverse, const Fr* tw, const Fr* pre, const Fr* post,
              const Fr* post_const) {
     const size_t N = (size_t)1 << n;
+    ProfScope prof(ctx, PROF_NTT, (double)batch * (double)N);
     static bool attr_set = false;
     if (!attr_set) {
         ZA_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_L) * 32));
@@ -394,9 +395,12 @@ void h_poly_device(Ctx* ctx, Fr* a, Fr* b, Fr* c, int log_m) {
         ntt_run(ctx, vecs[v], scratch.as<Fr>(), log_m, 1, true, tw, nullptr, d->pow_g_minv.as<Fr>(), nullptr);
         ntt_run(ctx, vecs[v], scratch.as<Fr>(), log_m, 1, false, tw, nullptr, nullptr, nullptr);
     }
-    h_pointwise_kernel<<<nblk(m, 256), 256, 0, ctx->stream>>>(a, b, c, d->consts.as<Fr>() + 1, m);
-    ctx->launches++;
-    ZA_CUDA(cudaGetLastError());
+    {
+        ProfScope prof(ctx, PROF_POINTWISE, (double)m);
+        h_pointwise_kernel<<<nblk(m, 256), 256, 0, ctx->stream>>>(a, b, c, d->consts.as<Fr>() + 1, m);
+        ctx->launches++;
+        ZA_CUDA(cudaGetLastError());
+    }
     ntt_run(ctx, a, scratch.as<Fr>(), log_m, 1, true, tw, nullptr, d->pow_ginv_minv.as<Fr>(), nullptr);
     fr_convert(ctx, a, m, 1);
 }

@@ -337,7 +337,10 @@ static std::unique_ptr<Circuit> circuit_upload(Ctx* ctx, const za_r1cs* cs) {
     return c;
 }
 
-// ------------------------------------------------------------------ create_proof
+// ------------------------------------------------------------------ create_proof, in three stages
+// Stage 1 (one GPU): witness -> a, b, c -> H coefficients.        SURVEY §3.2 steps 2-4
+// Stage 2 (every GPU): the eight multiexps over this rank's point range.   steps 4-5, SURVEY §8e
+// Stage 3 (host): add the per-rank partial sums and assemble A, B, C.       steps 6-8
 static const uint32_t* gather(Ctx* ctx, const uint8_t* d_src, const DevBuf& idx, uint32_t total, DevBuf& dst) {
     dst.ensure((size_t)total * 32);
     if (total) {
@@ -348,37 +351,39 @@ static const uint32_t* gather(Ctx* ctx, const uint8_t* d_src, const DevBuf& idx,
     return dst.as<uint32_t>();
 }
 
-static void create_proof(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* inputs, const uint8_t* aux, const uint8_t* r_le,
-                         const uint8_t* s_le, uint8_t* proof_out, za_trace* tr) {
-    cudaStream_t st = ctx->stream;
-    const uint32_t ni = c->ni, na = c->na, nc = c->nc;
-    check_scalars_canonical(inputs, ni, "inputs"); check_scalars_canonical(aux, na, "aux");
-    check_scalars_canonical(r_le, 1, "r"); check_scalars_canonical(s_le, 1, "s");
-    const size_t len = (size_t)nc + ni;          // rows incl. the input-consistency rows (step 3)
+static size_t domain_size(const Circuit* c, int* log_m_out) {
+    const size_t len = (size_t)c->nc + c->ni;      // rows incl. the input-consistency rows (step 3)
     size_t m = 1; int log_m = 0;
     while (m < len) { m *= 2; log_m++; if (log_m >= 28) throw ZaError(ZA_ERR_POLY_DEGREE_TOO_LARGE, "create_proof: domain of 2^28 or more elements"); }
+    if (log_m_out) *log_m_out = log_m;
+    return m;
+}
 
-    // witness on device: canonical copy (multiexp exponents) and Montgomery copy (row evaluation)
-    DevBuf wit_canon(((size_t)ni + na) * 32), wit_mont(((size_t)ni + na) * 32);
-    ZA_CUDA(cudaMemcpyAsync(wit_canon.p, inputs, (size_t)ni * 32, cudaMemcpyHostToDevice, st));
-    if (na) ZA_CUDA(cudaMemcpyAsync((uint8_t*)wit_canon.p + (size_t)ni * 32, aux, (size_t)na * 32, cudaMemcpyHostToDevice, st));
-    ZA_CUDA(cudaMemcpyAsync(wit_mont.p, wit_canon.p, ((size_t)ni + na) * 32, cudaMemcpyDeviceToDevice, st));
-    fr_convert(ctx, wit_mont.as<Fr>(), (size_t)ni + na, 0);
-
+// d_wit: [inputs | aux] canonical on device.  d_h: m scalars; on return the first m-1 are the canonical h coefficients.
+static void prove_h(Ctx* ctx, const Circuit* c, const uint8_t* d_wit, Fr* d_h, za_trace* tr) {
+    cudaStream_t st = ctx->stream;
+    const uint32_t ni = c->ni, na = c->na, nc = c->nc;
+    int log_m; const size_t m = domain_size(c, &log_m);
+    const size_t len = (size_t)nc + ni;
+    DevBuf& wit_mont = ctx->scratch[7];
+    wit_mont.ensure(((size_t)ni + na) * 32 + 2 * m * sizeof(Fr));
+    Fr* d_w = wit_mont.as<Fr>();
+    Fr* d_b = d_w + ni + na; Fr* d_c = d_b + m; Fr* d_a = d_h;
+    ZA_CUDA(cudaMemcpyAsync(d_w, d_wit, ((size_t)ni + na) * 32, cudaMemcpyDeviceToDevice, st));
+    fr_convert(ctx, d_w, (size_t)ni + na, 0);
     // steps 2-3: a, b, c = <row, witness>; then rows a = input_i, b = c = 0
-    DevBuf abc(3 * m * sizeof(Fr));
-    Fr* d_a = abc.as<Fr>(); Fr* d_b = d_a + m; Fr* d_c = d_b + m;
-    ZA_CUDA(cudaMemsetAsync(abc.p, 0, 3 * m * sizeof(Fr), st));
+    ZA_CUDA(cudaMemsetAsync(d_a, 0, m * sizeof(Fr), st));
+    ZA_CUDA(cudaMemsetAsync(d_b, 0, 2 * m * sizeof(Fr), st));
     Fr* outs[3] = {d_a, d_b, d_c};
     if (nc) {
+        ProfScope prof(ctx, PROF_R1CS, 3.0 * nc);
         for (int w = 0; w < 3; w++) {
-            r1cs_eval_kernel<<<nblk(nc, 128), 128, 0, st>>>(c->ptr[w].as<uint32_t>(), c->col[w].as<uint32_t>(), c->coeff[w].as<Fr>(),
-                                                          wit_mont.as<Fr>(), nc, outs[w]);
+            r1cs_eval_kernel<<<nblk(nc, 128), 128, 0, st>>>(c->ptr[w].as<uint32_t>(), c->col[w].as<uint32_t>(), c->coeff[w].as<Fr>(), d_w, nc, outs[w]);
             ctx->launches++;
         }
         ZA_CUDA(cudaGetLastError());
     }
-    ZA_CUDA(cudaMemcpyAsync(d_a + nc, wit_mont.p, (size_t)ni * 32, cudaMemcpyDeviceToDevice, st));
+    ZA_CUDA(cudaMemcpyAsync(d_a + nc, d_w, (size_t)ni * 32, cudaMemcpyDeviceToDevice, st));
     if (tr && (tr->a_eval || tr->b_eval || tr->c_eval)) {
         DevBuf tmp(len * 32);
         uint8_t* dst[3] = {tr->a_eval, tr->b_eval, tr->c_eval};
@@ -395,45 +400,81 @@ static void create_proof(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t
         if (tr->b_input_density) memcpy(tr->b_input_density, c->b_in_density.data(), ni);
         if (tr->b_aux_density && na) memcpy(tr->b_aux_density, c->b_aux_density.data(), na);
     }
-
-    // step 4: H polynomial; result canonical in d_a[0 .. m-1)
+    // step 4
     h_poly_device(ctx, d_a, d_b, d_c, log_m);
     if (tr && tr->h_coeffs && m > 1) {
         ZA_CUDA(cudaMemcpyAsync(tr->h_coeffs, d_a, (m - 1) * 32, cudaMemcpyDeviceToHost, st));
         ZA_CUDA(cudaStreamSynchronize(st));
     }
+}
 
-    // steps 4-5: the eight multiexps
-    const uint8_t* d_in = (const uint8_t*)wit_canon.p;
-    const uint8_t* d_aux = d_in + (size_t)ni * 32;
-    G1XYZZ H = multiexp_dev<Fq>(ctx, pk->h.get(), 0, (const uint32_t*)d_a, m - 1);
-    G1XYZZ Lq = multiexp_dev<Fq>(ctx, pk->l.get(), 0, (const uint32_t*)d_aux, na);
-    G1XYZZ A_in = multiexp_dev<Fq>(ctx, pk->a.get(), 0, (const uint32_t*)d_in, ni);
-    DevBuf g1buf, g2buf;
-    const uint32_t* sc = gather(ctx, d_aux, c->a_aux_idx, c->a_aux_total, g1buf);
-    G1XYZZ A_aux = multiexp_dev<Fq>(ctx, pk->a.get(), ni, sc, c->a_aux_total);
-    const uint32_t* sc_bin = gather(ctx, d_in, c->b_in_idx, c->b_in_total, g2buf);
-    G1XYZZ B1_in = multiexp_dev<Fq>(ctx, pk->b_g1.get(), 0, sc_bin, c->b_in_total);
-    G2XYZZ B2_in = multiexp_dev<Fq2>(ctx, pk->b_g2.get(), 0, sc_bin, c->b_in_total);
-    const uint32_t* sc_baux = gather(ctx, d_aux, c->b_aux_idx, c->b_aux_total, g1buf);
-    G1XYZZ B1_aux = multiexp_dev<Fq>(ctx, pk->b_g1.get(), c->b_in_total, sc_baux, c->b_aux_total);
-    G2XYZZ B2_aux = multiexp_dev<Fq2>(ctx, pk->b_g2.get(), c->b_in_total, sc_baux, c->b_aux_total);
-    if (tr && tr->msm_g1) {
-        const G1XYZZ* v[6] = {&H, &Lq, &A_in, &A_aux, &B1_in, &B1_aux};
-        for (int i = 0; i < 6; i++) g1_to_le(xyzz_to_affine<Fq>(*v[i]), tr->msm_g1 + 64 * i);
-    }
-    if (tr && tr->msm_g2) {
-        g2_to_le(xyzz_to_affine<Fq2>(B2_in), tr->msm_g2);
-        g2_to_le(xyzz_to_affine<Fq2>(B2_aux), tr->msm_g2 + 128);
-    }
+struct Partials {
+    G1XYZZ g1[6];   // h, l, a_inputs, a_aux, b1_inputs, b1_aux
+    G2XYZZ g2[2];   // b2_inputs, b2_aux
+};
+static const size_t PARTIALS_BYTES = 6 * 128 + 2 * 256;
+static void partials_to_le(const Partials& p, uint8_t* out) {
+    for (int i = 0; i < 6; i++) xyzz_to_le(p.g1[i], out + 128 * i);
+    for (int i = 0; i < 2; i++) xyzz_to_le(p.g2[i], out + 768 + 256 * i);
+}
+static void partials_add_le(Partials& acc, const uint8_t* in) {
+    for (int i = 0; i < 6; i++) xyzz_add<Fq>(acc.g1[i], g1_xyzz_from_le(in + 128 * i));
+    for (int i = 0; i < 2; i++) xyzz_add<Fq2>(acc.g2[i], g2_xyzz_from_le(in + 768 + 256 * i));
+}
+static Partials partials_zero() {
+    Partials p;
+    for (int i = 0; i < 6; i++) p.g1[i] = G1XYZZ::inf();
+    for (int i = 0; i < 2; i++) p.g2[i] = G2XYZZ::inf();
+    return p;
+}
 
-    // steps 6-8: assembly on the host (a handful of group operations)
+// contiguous share of `cnt` items for `rank` of `world`
+static inline void share(size_t cnt, int rank, int world, size_t& lo, size_t& hi) {
+    lo = (size_t)(((unsigned __int128)cnt * (unsigned)rank) / (unsigned)world);
+    hi = (size_t)(((unsigned __int128)cnt * (unsigned)(rank + 1)) / (unsigned)world);
+}
+
+// ParameterSource for &Parameters: get_h -> (h,0); get_l -> (l,0); get_a -> ((a,0),(a,num_inputs));
+// get_b_g1/g2 -> ((b,0),(b,b_input_density_total)).  Each large query is cut by point range across ranks;
+// the input-sized queries run on rank 0.
+static void prove_msms(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* d_wit, const Fr* d_h, int rank, int world, Partials& out) {
+    const uint32_t ni = c->ni, na = c->na;
+    const size_t m = domain_size(c, nullptr);
+    out = partials_zero();
+    const uint8_t* d_in = d_wit;
+    const uint8_t* d_aux = d_wit + (size_t)ni * 32;
+    size_t lo, hi;
+    // the whole-query length checks bellman's cursors would trip over (unexpected EOF)
+    if (pk->h->n < m - 1 || pk->l->n < na || pk->a->n < (size_t)ni + c->a_aux_total || pk->b_g1->n < (size_t)c->b_in_total + c->b_aux_total ||
+        pk->b_g2->n < (size_t)c->b_in_total + c->b_aux_total)
+        throw ZaError(ZA_ERR_IO, "create_proof: a proving-key query is shorter than the circuit needs (bellman: unexpected EOF)");
+    share(m - 1, rank, world, lo, hi);
+    out.g1[0] = multiexp_dev<Fq>(ctx, pk->h.get(), lo, (const uint32_t*)(d_h + lo), hi - lo);
+    share(na, rank, world, lo, hi);
+    out.g1[1] = multiexp_dev<Fq>(ctx, pk->l.get(), lo, (const uint32_t*)(d_aux + lo * 32), hi - lo);
+    DevBuf& gbuf = ctx->scratch[1];
+    if (rank == 0) {
+        out.g1[2] = multiexp_dev<Fq>(ctx, pk->a.get(), 0, (const uint32_t*)d_in, ni);
+        const uint32_t* sc_bin = gather(ctx, d_in, c->b_in_idx, c->b_in_total, gbuf);
+        out.g1[4] = multiexp_dev<Fq>(ctx, pk->b_g1.get(), 0, sc_bin, c->b_in_total);
+        out.g2[0] = multiexp_dev<Fq2>(ctx, pk->b_g2.get(), 0, sc_bin, c->b_in_total);
+    }
+    const uint32_t* sc = gather(ctx, d_aux, c->a_aux_idx, c->a_aux_total, gbuf);
+    share(c->a_aux_total, rank, world, lo, hi);
+    out.g1[3] = multiexp_dev<Fq>(ctx, pk->a.get(), ni + lo, sc + lo * 8, hi - lo);
+    sc = gather(ctx, d_aux, c->b_aux_idx, c->b_aux_total, gbuf);
+    share(c->b_aux_total, rank, world, lo, hi);
+    out.g1[5] = multiexp_dev<Fq>(ctx, pk->b_g1.get(), c->b_in_total + lo, sc + lo * 8, hi - lo);
+    out.g2[1] = multiexp_dev<Fq2>(ctx, pk->b_g2.get(), c->b_in_total + lo, sc + lo * 8, hi - lo);
+}
+
+static void prove_assemble(const Pk* pk, const Partials& P, const uint8_t* r_le, const uint8_t* s_le, uint8_t* proof_out) {
     if (pk->delta_g1.is_inf() || pk->delta_g2.is_inf()) throw ZaError(ZA_ERR_UNEXPECTED_IDENTITY, "create_proof: delta is the point at infinity");
+    check_scalars_canonical(r_le, 1, "r"); check_scalars_canonical(s_le, 1, "s");
     uint32_t r[8], s[8];
     memcpy(r, r_le, 32); memcpy(s, s_le, 32);
     Fr rf, sf; memcpy(rf.v, r, 32); memcpy(sf.v, s, 32);
-    Fr rs_m = fp_to_mont<FrParams>(rf) * fp_to_mont<FrParams>(sf);
-    Fr rs_c = fp_from_mont<FrParams>(rs_m);
+    Fr rs_c = fp_from_mont<FrParams>(fp_to_mont<FrParams>(rf) * fp_to_mont<FrParams>(sf));
     G1XYZZ d1 = G1XYZZ::from_affine(pk->delta_g1), al = G1XYZZ::from_affine(pk->alpha_g1), be1 = G1XYZZ::from_affine(pk->beta_g1);
     G2XYZZ d2 = G2XYZZ::from_affine(pk->delta_g2);
     G1XYZZ g_a = xyzz_mul<Fq>(d1, r); xyzz_madd<Fq>(g_a, pk->alpha_g1);
@@ -441,18 +482,69 @@ static void create_proof(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t
     G1XYZZ g_c = xyzz_mul<Fq>(d1, rs_c.v);
     xyzz_add<Fq>(g_c, xyzz_mul<Fq>(al, s));
     xyzz_add<Fq>(g_c, xyzz_mul<Fq>(be1, r));
-    G1XYZZ a_ans = A_in; xyzz_add<Fq>(a_ans, A_aux);
+    G1XYZZ a_ans = P.g1[2]; xyzz_add<Fq>(a_ans, P.g1[3]);
     xyzz_add<Fq>(g_a, a_ans);
     xyzz_add<Fq>(g_c, xyzz_mul<Fq>(a_ans, s));
-    G1XYZZ b1_ans = B1_in; xyzz_add<Fq>(b1_ans, B1_aux);
-    G2XYZZ b2_ans = B2_in; xyzz_add<Fq2>(b2_ans, B2_aux);
+    G1XYZZ b1_ans = P.g1[4]; xyzz_add<Fq>(b1_ans, P.g1[5]);
+    G2XYZZ b2_ans = P.g2[0]; xyzz_add<Fq2>(b2_ans, P.g2[1]);
     xyzz_add<Fq2>(g_b, b2_ans);
     xyzz_add<Fq>(g_c, xyzz_mul<Fq>(b1_ans, r));
-    xyzz_add<Fq>(g_c, H);
-    xyzz_add<Fq>(g_c, Lq);
+    xyzz_add<Fq>(g_c, P.g1[0]);
+    xyzz_add<Fq>(g_c, P.g1[1]);
     g1_to_le(xyzz_to_affine<Fq>(g_a), proof_out);
     g2_to_le(xyzz_to_affine<Fq2>(g_b), proof_out + 64);
     g1_to_le(xyzz_to_affine<Fq>(g_c), proof_out + 192);
+}
+
+// whole proof on one GPU, witness already on the device
+static void create_proof_device(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* d_wit, const uint8_t* r_le, const uint8_t* s_le,
+                                uint8_t* proof_out, za_trace* tr) {
+    const size_t m = domain_size(c, nullptr);
+    DevBuf h(m * sizeof(Fr));
+    prove_h(ctx, c, d_wit, h.as<Fr>(), tr);
+    Partials P;
+    prove_msms(ctx, pk, c, d_wit, h.as<Fr>(), 0, 1, P);
+    if (tr && tr->msm_g1) for (int i = 0; i < 6; i++) g1_to_le(xyzz_to_affine<Fq>(P.g1[i]), tr->msm_g1 + 64 * i);
+    if (tr && tr->msm_g2) for (int i = 0; i < 2; i++) g2_to_le(xyzz_to_affine<Fq2>(P.g2[i]), tr->msm_g2 + 128 * i);
+    prove_assemble(pk, P, r_le, s_le, proof_out);
+}
+
+static void create_proof(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* inputs, const uint8_t* aux, const uint8_t* r_le,
+                         const uint8_t* s_le, uint8_t* proof_out, za_trace* tr) {
+    cudaStream_t st = ctx->stream;
+    const uint32_t ni = c->ni, na = c->na;
+    check_scalars_canonical(inputs, ni, "inputs"); check_scalars_canonical(aux, na, "aux");
+    DevBuf wit(((size_t)ni + na) * 32);
+    ZA_CUDA(cudaMemcpyAsync(wit.p, inputs, (size_t)ni * 32, cudaMemcpyHostToDevice, st));
+    if (na) ZA_CUDA(cudaMemcpyAsync((uint8_t*)wit.p + (size_t)ni * 32, aux, (size_t)na * 32, cudaMemcpyHostToDevice, st));
+    create_proof_device(ctx, pk, c, (const uint8_t*)wit.p, r_le, s_le, proof_out, tr);
+}
+
+// synthetic proving key: every base is a known multiple of the generator (bench + full-size property tests)
+static Affine<Fq> host_g1_gen() { Affine<Fq> g; g.x = fp_from_u64<FqParams>(1); g.y = fp_from_u64<FqParams>(2); return g; }
+static Affine<Fq2> host_g2_gen() {
+    // /root/reference/prover/src/groth16/ethereum.rs:28-31
+    static const uint32_t X0[8] = {0xd992f6edu, 0x46debd5cu, 0xf75edaddu, 0x674322d4u, 0x5e5c4479u, 0x426a0066u, 0x121f1e76u, 0x1800deefu};
+    static const uint32_t X1[8] = {0xaef312c2u, 0x97e485b7u, 0x35a9e712u, 0xf1aa4933u, 0x31fb5d25u, 0x7260bfb7u, 0x920d483au, 0x198e9393u};
+    static const uint32_t Y0[8] = {0x66fa7daau, 0x4ce6cc01u, 0x0c43d37bu, 0xe3d1e769u, 0x8dcb408fu, 0x4aab7180u, 0xdb8c6debu, 0x12c85ea5u};
+    static const uint32_t Y1[8] = {0xd122975bu, 0x55acdadcu, 0x70b38ef3u, 0xbc4b3133u, 0x690c3395u, 0xec9e99adu, 0x585ff075u, 0x090689d0u};
+    Affine<Fq2> g; Fq t;
+    memcpy(t.v, X0, 32); g.x.c0 = fp_to_mont<FqParams>(t); memcpy(t.v, X1, 32); g.x.c1 = fp_to_mont<FqParams>(t);
+    memcpy(t.v, Y0, 32); g.y.c0 = fp_to_mont<FqParams>(t); memcpy(t.v, Y1, 32); g.y.c1 = fp_to_mont<FqParams>(t);
+    return g;
+}
+static std::unique_ptr<Bases> bases_generated(Ctx* ctx, int group, size_t n, uint64_t first) {
+    std::unique_ptr<Bases> b(new Bases());
+    b->ctx = ctx; b->group = group; b->n = n; b->has_infinity = false;
+    if (first == 0 || first + n >= ((uint64_t)1 << 62)) throw ZaError(ZA_ERR_INVALID, "bases_generate: multiplier range must be in [1, 2^62)");
+    if (group == 1) { b->pts.alloc(n * sizeof(G1Affine)); bases_generate<Fq>(ctx, b->pts.as<G1Affine>(), n, first, host_g1_gen()); }
+    else { b->pts.alloc(n * sizeof(G2Affine)); bases_generate<Fq2>(ctx, b->pts.as<G2Affine>(), n, first, host_g2_gen()); }
+    return b;
+}
+template <class F>
+static Affine<F> host_multiple(const Affine<F>& g, uint64_t k) {
+    uint32_t w[8] = {(uint32_t)k, (uint32_t)(k >> 32), 0, 0, 0, 0, 0, 0};
+    return xyzz_to_affine<F>(xyzz_mul<F>(XYZZ<F>::from_affine(g), w));
 }
 
 }  // namespace za
@@ -603,6 +695,130 @@ int za_circuit_upload(za_ctx* ctx, const za_r1cs* cs, za_circuit** out) {
     ZA_CATCH
 }
 void za_circuit_free(za_circuit* c) { delete c; }
+
+int za_bases_generate(za_ctx* ctx, int group, size_t n, uint64_t first_multiple, za_bases** out) {
+    if (!ctx || !out) return fail(ZA_ERR_INVALID, "NULL argument");
+    if (group != 1 && group != 2) return fail(ZA_ERR_INVALID, "group must be 1 (G1) or 2 (G2)");
+    *out = nullptr;
+    ZA_TRY
+    ZA_CUDA(cudaSetDevice(ctx->c.device));
+    za_bases* h = new za_bases();
+    try { h->b = bases_generated(&ctx->c, group, n, first_multiple); }
+    catch (...) { delete h; throw; }
+    *out = h;
+    return ZA_OK;
+    ZA_CATCH
+}
+
+int za_bases_download(za_ctx* ctx, const za_bases* bases, size_t offset, size_t n, uint8_t* out) {
+    if (!ctx || !bases || !out) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    const Bases* b = bases->b.get();
+    if (offset > b->n || n > b->n - offset) return fail(ZA_ERR_INVALID, "range outside the bases array");
+    ZA_CUDA(cudaSetDevice(ctx->c.device));
+    if (b->group == 1) {
+        std::vector<G1Affine> h(n ? n : 1);
+        ZA_CUDA(cudaMemcpy(h.data(), b->pts.as<G1Affine>() + offset, n * sizeof(G1Affine), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++) g1_to_le(h[i], out + 64 * i);
+    } else {
+        std::vector<G2Affine> h(n ? n : 1);
+        ZA_CUDA(cudaMemcpy(h.data(), b->pts.as<G2Affine>() + offset, n * sizeof(G2Affine), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++) g2_to_le(h[i], out + 128 * i);
+    }
+    return ZA_OK;
+    ZA_CATCH
+}
+
+int za_pk_synthetic(za_ctx* ctx, const uint32_t* counts, za_pk** out) {
+    if (!ctx || !counts || !out) return fail(ZA_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    ZA_TRY
+    Ctx* c = &ctx->c;
+    ZA_CUDA(cudaSetDevice(c->device));
+    za_pk* h = new za_pk();
+    try {
+        h->p.reset(new Pk());
+        Pk* pk = h->p.get();
+        pk->ctx = c;
+        Affine<Fq> g1 = host_g1_gen(); Affine<Fq2> g2 = host_g2_gen();
+        pk->alpha_g1 = host_multiple<Fq>(g1, 3); pk->beta_g1 = host_multiple<Fq>(g1, 5); pk->delta_g1 = host_multiple<Fq>(g1, 11);
+        pk->beta_g2 = host_multiple<Fq2>(g2, 5); pk->gamma_g2 = host_multiple<Fq2>(g2, 7); pk->delta_g2 = host_multiple<Fq2>(g2, 11);
+        pk->ic.resize(counts[0]);
+        for (uint32_t i = 0; i < counts[0]; i++) pk->ic[i] = host_multiple<Fq>(g1, 13 + i);
+        // query q, entry i is the multiple  (q+1) * 2^32 + i + 1  of the generator
+        pk->h = bases_generated(c, 1, counts[1], ((uint64_t)1 << 32) + 1);
+        pk->l = bases_generated(c, 1, counts[2], ((uint64_t)2 << 32) + 1);
+        pk->a = bases_generated(c, 1, counts[3], ((uint64_t)3 << 32) + 1);
+        pk->b_g1 = bases_generated(c, 1, counts[4], ((uint64_t)4 << 32) + 1);
+        pk->b_g2 = bases_generated(c, 2, counts[5], ((uint64_t)4 << 32) + 1);
+    } catch (...) { delete h; throw; }
+    *out = h;
+    return ZA_OK;
+    ZA_CATCH
+}
+
+int za_circuit_info(const za_circuit* circuit, uint32_t* info) {
+    if (!circuit || !info) return fail(ZA_ERR_INVALID, "NULL argument");
+    const Circuit* c = circuit->c.get();
+    info[0] = c->ni; info[1] = c->na; info[2] = c->nc; info[3] = c->a_aux_total; info[4] = c->b_in_total; info[5] = c->b_aux_total;
+    int log_m = 0;
+    ZA_TRY
+    domain_size(c, &log_m);
+    info[6] = (uint32_t)log_m;
+    return ZA_OK;
+    ZA_CATCH
+}
+
+int za_imad_peak(za_ctx* ctx, double* imads_per_second) {
+    if (!ctx || !imads_per_second) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    ZA_CUDA(cudaSetDevice(ctx->c.device));
+    *imads_per_second = imad_peak(&ctx->c);
+    return ZA_OK;
+    ZA_CATCH
+}
+
+int za_prove_h_device(za_ctx* ctx, const za_circuit* circuit, const void* d_witness, void* d_h) {
+    if (!ctx || !circuit || !d_witness || !d_h) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    ZA_CUDA(cudaSetDevice(ctx->c.device));
+    prove_h(&ctx->c, circuit->c.get(), (const uint8_t*)d_witness, (Fr*)d_h, nullptr);
+    return ZA_OK;
+    ZA_CATCH
+}
+
+int za_prove_msm_partials(za_ctx* ctx, const za_pk* pk, const za_circuit* circuit, const void* d_witness, const void* d_h, int rank, int world,
+                          uint8_t* partials_out) {
+    if (!ctx || !pk || !circuit || !d_witness || !d_h || !partials_out) return fail(ZA_ERR_INVALID, "NULL argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(ZA_ERR_INVALID, "bad rank/world");
+    ZA_TRY
+    ZA_CUDA(cudaSetDevice(ctx->c.device));
+    Partials P;
+    prove_msms(&ctx->c, pk->p.get(), circuit->c.get(), (const uint8_t*)d_witness, (const Fr*)d_h, rank, world, P);
+    partials_to_le(P, partials_out);
+    return ZA_OK;
+    ZA_CATCH
+}
+
+int za_prove_assemble(const za_pk* pk, const uint8_t* partials, int world, const uint8_t* r, const uint8_t* s, uint8_t* proof_out) {
+    if (!pk || !partials || !r || !s || !proof_out || world < 1) return fail(ZA_ERR_INVALID, "bad argument");
+    ZA_TRY
+    Partials P = partials_zero();
+    for (int k = 0; k < world; k++) partials_add_le(P, partials + (size_t)k * PARTIALS_BYTES);
+    prove_assemble(pk->p.get(), P, r, s, proof_out);
+    return ZA_OK;
+    ZA_CATCH
+}
+
+int za_create_proof_device(za_ctx* ctx, const za_pk* pk, const za_circuit* circuit, const void* d_witness, const uint8_t* r, const uint8_t* s,
+                           uint8_t* proof_out) {
+    if (!ctx || !pk || !circuit || !d_witness || !r || !s || !proof_out) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    ZA_CUDA(cudaSetDevice(ctx->c.device));
+    create_proof_device(&ctx->c, pk->p.get(), circuit->c.get(), (const uint8_t*)d_witness, r, s, proof_out, nullptr);
+    return ZA_OK;
+    ZA_CATCH
+}
 
 int za_create_proof(za_ctx* ctx, const za_pk* pk, const za_circuit* circuit, const uint8_t* inputs, const uint8_t* aux, const uint8_t* r,
                     const uint8_t* s, uint8_t* proof_out, za_trace* trace) {

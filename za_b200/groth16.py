@@ -59,6 +59,17 @@ class Context:
     def launch_count(self):
         return int(lib().za_ctx_launch_count(self.h))
 
+    PROFILE_CLASSES = ("msm_accumulate_g1", "msm_accumulate_g2", "ntt", "msm_sort", "msm_reduce", "r1cs_eval", "h_pointwise", "other")
+
+    def profile(self, on=True):
+        check(lib().za_ctx_profile(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """{class: dict(ms=, work=, spans=)} accumulated since the last read (device time, CUDA events)."""
+        out = (ctypes.c_double * 24)()
+        check(lib().za_ctx_profile_read(self.h, out))
+        return {n: dict(ms=out[i], work=out[8 + i], spans=int(out[16 + i])) for i, n in enumerate(self.PROFILE_CLASSES)}
+
     # ---- EvaluationDomain -------------------------------------------------------------------
     def ntt(self, data, mode):
         """data: (2^k, 32) canonical scalars on the host -> transformed copy."""
@@ -115,6 +126,22 @@ class Bases:
         check(lib().za_bases_upload(ctx.h, group, _p(pts), pts.shape[0], ctypes.byref(h)))
         self.h = h
 
+    @classmethod
+    def generate(cls, ctx, group, n, first_multiple=1):
+        """bases[i] = (first_multiple + i) * G, generated on the GPU (synthetic inputs)."""
+        self = cls.__new__(cls)
+        self.ctx, self.group = ctx, group
+        h = ctypes.c_void_p()
+        check(lib().za_bases_generate(ctx.h, group, n, first_multiple, ctypes.byref(h)))
+        self.h = h
+        return self
+
+    def download(self, offset=0, n=None):
+        n = len(self) - offset if n is None else n
+        out = np.zeros((n, 64 if self.group == 1 else 128), np.uint8)
+        check(lib().za_bases_download(self.ctx.h, self.h, offset, n, _p(out)))
+        return out
+
     def __len__(self):
         return int(lib().za_bases_len(self.h))
 
@@ -169,6 +196,15 @@ class Parameters:
         check(lib().za_pk_load(ctx.h, _p(buf), buf.shape[0], 1 if checked else 0, ctypes.byref(h)))
         return cls(ctx, h)
 
+    @classmethod
+    def synthetic(cls, ctx, ic, h, l, a, b_g1, b_g2):
+        """Proving key of the given query sizes whose bases are known multiples of the generators
+        (include/za_b200.h: za_pk_synthetic).  Not a valid CRS; same work per proof."""
+        c = (ctypes.c_uint32 * 6)(ic, h, l, a, b_g1, b_g2)
+        hd = ctypes.c_void_p()
+        check(lib().za_pk_synthetic(ctx.h, c, ctypes.byref(hd)))
+        return cls(ctx, hd)
+
     def counts(self):
         c = (ctypes.c_uint32 * 6)()
         check(lib().za_pk_counts(self.h, c))
@@ -216,6 +252,11 @@ class Circuit:
         h = ctypes.c_void_p()
         check(lib().za_circuit_upload(ctx.h, ctypes.byref(s), ctypes.byref(h)))
         self.h = h
+
+    def info(self):
+        c = (ctypes.c_uint32 * 7)()
+        check(lib().za_circuit_info(self.h, c))
+        return dict(zip(("num_inputs", "num_aux", "num_constraints", "a_aux_total", "b_input_total", "b_aux_total", "log_m"), list(c)))
 
     @classmethod
     def from_rows(cls, ctx, num_inputs, num_aux, rows):
@@ -278,6 +319,52 @@ def create_proof(ctx, params, circuit, inputs, aux, r, s, trace=False):
         bufs["b_aux_density"] = bufs["b_aux_density"][:circuit.num_aux]
         return proof.tobytes(), bufs
     return proof.tobytes()
+
+
+PARTIALS_BYTES = 1280
+
+
+def _scalar(x):
+    return np.frombuffer(int(x).to_bytes(32, "little"), np.uint8)
+
+
+def create_proof_device(ctx, params, circuit, d_witness, r, s):
+    """create_proof with the witness [inputs | aux] (canonical) already resident on the GPU."""
+    proof = np.zeros(256, np.uint8)
+    check(lib().za_create_proof_device(ctx.h, params.h, circuit.h, ctypes.c_void_p(d_witness), _p(_scalar(r)), _p(_scalar(s)), _p(proof)))
+    return proof.tobytes()
+
+
+def prove_h_device(ctx, circuit, d_witness, d_h):
+    """Stage 1 (one GPU): witness -> H coefficients into d_h (m * 32 bytes of device memory)."""
+    check(lib().za_prove_h_device(ctx.h, circuit.h, ctypes.c_void_p(d_witness), ctypes.c_void_p(d_h)))
+
+
+def prove_msm_partials(ctx, params, circuit, d_witness, d_h, rank, world):
+    """Stage 2 (every GPU): the eight multiexps over this rank's point range -> PARTIALS_BYTES record."""
+    out = np.zeros(PARTIALS_BYTES, np.uint8)
+    check(lib().za_prove_msm_partials(ctx.h, params.h, circuit.h, ctypes.c_void_p(d_witness), ctypes.c_void_p(d_h), rank, world, _p(out)))
+    return out
+
+
+def prove_assemble(params, partials, r, s):
+    """Stage 3 (host): add the per-rank partial records and assemble the proof."""
+    partials = np.ascontiguousarray(partials, dtype=np.uint8).reshape(-1, PARTIALS_BYTES)
+    proof = np.zeros(256, np.uint8)
+    check(lib().za_prove_assemble(params.h, _p(partials), partials.shape[0], _p(_scalar(r)), _p(_scalar(s)), _p(proof)))
+    return proof.tobytes()
+
+
+def share(count, rank, world):
+    """The contiguous [lo, hi) share of `count` items that rank owns (same rule as the library)."""
+    return count * rank // world, count * (rank + 1) // world
+
+
+def imad_peak(ctx):
+    """Measured integer multiply-add throughput of the device, IMAD/s."""
+    v = ctypes.c_double(0)
+    check(lib().za_imad_peak(ctx.h, ctypes.byref(v)))
+    return v.value
 
 
 def proof_to_json(proof, public_inputs):
