@@ -140,7 +140,8 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     ctx = za_b200.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)      # one explicit stream for the library, torch copies and NCCL
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     log_m = args.log_m

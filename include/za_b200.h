@@ -77,8 +77,10 @@ int za_version(void);
 int za_device_count(void);
 int za_ctx_create(int device, za_ctx **out);
 void za_ctx_destroy(za_ctx *ctx);
-/* Issue all work of this context on `cuda_stream` (a cudaStream_t; NULL restores the context's own). */
+/* Issue all work of this context on `cuda_stream` (a cudaStream_t; NULL is the CUDA default stream).
+ * A new context starts on its own non-blocking stream; za_ctx_use_own_stream goes back to it. */
 int za_ctx_set_stream(za_ctx *ctx, void *cuda_stream);
+int za_ctx_use_own_stream(za_ctx *ctx);
 int za_ctx_synchronize(za_ctx *ctx);
 /* Kernels launched through this context so far (bench.py reports the delta as gpu_launches). */
 uint64_t za_ctx_launch_count(const za_ctx *ctx);

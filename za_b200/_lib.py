@@ -48,6 +48,7 @@ SYMBOLS = {
     "za_ctx_create": (ci, [ci, ctypes.POINTER(vp)]),
     "za_ctx_destroy": (None, [vp]),
     "za_ctx_set_stream": (ci, [vp, vp]),
+    "za_ctx_use_own_stream": (ci, [vp]),
     "za_ctx_synchronize": (ci, [vp]),
     "za_ctx_launch_count": (ctypes.c_uint64, [vp]),
     "za_ctx_profile": (ci, [vp, ci]),

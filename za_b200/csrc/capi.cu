@@ -86,7 +86,13 @@ void za_ctx_destroy(za_ctx* ctx) {
 
 int za_ctx_set_stream(za_ctx* ctx, void* cuda_stream) {
     if (!ctx) return fail(ZA_ERR_INVALID, "ctx is NULL");
-    ctx->c.stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own;
+    ctx->c.stream = (cudaStream_t)cuda_stream;      // NULL is the CUDA default stream
+    return ZA_OK;
+}
+
+int za_ctx_use_own_stream(za_ctx* ctx) {
+    if (!ctx) return fail(ZA_ERR_INVALID, "ctx is NULL");
+    ctx->c.stream = ctx->own;
     return ZA_OK;
 }
 

@@ -83,7 +83,7 @@ struct Ctx {
     int sm_count = 0;
     std::map<int, NttDomain*> domains;  // by log_n
     // scratch reused across calls
-    DevBuf scratch[8];
+    DevBuf scratch[16];
     uint64_t launches = 0;              // kernels launched through this context (bench: gpu_launches)
     // optional per-kernel-class timing with CUDA events on `stream` (bench.py roofline numbers)
     bool profile = false;

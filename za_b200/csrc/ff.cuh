@@ -40,6 +40,12 @@ namespace za {
 
 ZA_D uint32_t p_mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 ZA_D uint32_t p_mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+// full 32x32 -> 64 product as one instruction (IMAD.WIDE.U32); the halves then enter add.cc chains
+ZA_D void p_mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+    uint64_t p;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a), "r"(b));
+    asm("mov.b64 {%0,%1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p));
+}
 ZA_D uint32_t p_add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 ZA_D uint32_t p_addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 ZA_D uint32_t p_addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
@@ -64,6 +70,7 @@ inline HostCC& host_cc() { static thread_local HostCC s; return s; }
 
 inline uint32_t p_mul_lo(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b); }
 inline uint32_t p_mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline void p_mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { uint64_t p = (uint64_t)a * b; lo = (uint32_t)p; hi = (uint32_t)(p >> 32); }
 inline uint32_t emu_add(uint64_t a, uint64_t b, uint64_t cin, bool set_cc) {
     uint64_t s = a + b + cin;
     if (set_cc) host_cc().cf = (uint32_t)(s >> 32);
@@ -229,35 +236,39 @@ ZA_HD Fp<P> fp_dbl(const Fp<P>& a) { return fp_add<P>(a, a); }
 
 // One CIOS round: (E,O) += a*bi ; (E,O) += m*q ; implicit >>32 by role swap.
 // Value represented: sum E[j] 2^(32j) + sum O[j] 2^(32(j+1)).
+// The a*bi products do not depend on the running reduction, so they are issued as eight independent
+// IMAD.WIDE (p_mul_wide) and folded in with add.cc chains; the m*q products do depend on it and go
+// through mad.lo.cc/madc.hi.cc pairs, which ptxas fuses into IMAD.WIDE.U32.X (multiply-add with
+// carry in and out).  ~136 integer-pipe multiply instructions per field product.
 template <class P, bool FIRST>
 ZA_HD void fp_mad_redc(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi) {
+    uint32_t pl[8], ph[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) p_mul_wide(pl[j], ph[j], a[j], bi);
     if (FIRST) {
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
-            O[j] = p_mul_lo(a[j + 1], bi);
-            O[j + 1] = p_mul_hi(a[j + 1], bi);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-            E[j] = p_mul_lo(a[j], bi);
-            E[j + 1] = p_mul_hi(a[j], bi);
+            O[j] = pl[j + 1];
+            O[j + 1] = ph[j + 1];
+            E[j] = pl[j];
+            E[j + 1] = ph[j];
         }
     } else {
         // O still holds the previous round's low word (now weight 2^0) in O[1].
         E[0] = p_add_cc(E[0], O[1]);
 #pragma unroll
         for (int j = 0; j < 6; j += 2) {
-            O[j] = p_madc_lo_cc(a[j + 1], bi, O[j + 2]);
-            O[j + 1] = p_madc_hi_cc(a[j + 1], bi, O[j + 3]);
+            O[j] = p_addc_cc(pl[j + 1], O[j + 2]);
+            O[j + 1] = p_addc_cc(ph[j + 1], O[j + 3]);
         }
-        O[6] = p_madc_lo_cc(a[7], bi, 0u);
-        O[7] = p_madc_hi(a[7], bi, 0u);
-        E[0] = p_mad_lo_cc(a[0], bi, E[0]);
-        E[1] = p_madc_hi_cc(a[0], bi, E[1]);
+        O[6] = p_addc_cc(pl[7], 0u);
+        O[7] = p_addc(ph[7], 0u);
+        E[0] = p_add_cc(E[0], pl[0]);
+        E[1] = p_addc_cc(E[1], ph[0]);
 #pragma unroll
         for (int j = 2; j < 8; j += 2) {
-            E[j] = p_madc_lo_cc(a[j], bi, E[j]);
-            E[j + 1] = p_madc_hi_cc(a[j], bi, E[j + 1]);
+            E[j] = p_addc_cc(E[j], pl[j]);
+            E[j + 1] = p_addc_cc(E[j + 1], ph[j]);
         }
         O[7] = p_addc(O[7], 0u);
     }

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* counts, 
 
 // K5: chunked segmented accumulation.  Thread `chunk` owns entries [chunk*Lc, (chunk+1)*Lc).
 template <class F>
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ entries,
+__global__ void __launch_bounds__(128, (sizeof(F) == sizeof(Fq) ? 4 : 2)) msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ entries,
                                                              const uint32_t* __restrict__ offsets, uint32_t nkeys, uint32_t Lc,
                                                              XYZZ<F>* bucket_sums, XYZZ<F>* part_head, XYZZ<F>* part_tail,
                                                              uint32_t* tail_owner_key) {
@@ -150,29 +150,59 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine<F>* __
     }
     uint32_t key = lo;
     bool head_open = offsets[key] < start;
-    uint32_t pos = start;
-    while (pos < end) {
-        const uint32_t bend = offsets[key + 1];
-        const uint32_t run_end = bend < end ? bend : end;
-        XYZZ<F> acc = XYZZ<F>::inf();
-        uint32_t e = entries[pos];
-        Affine<F> P = ldg_vec(bases + (e & 0x7fffffffu));
-        for (; pos < run_end; pos++) {
-            const uint32_t e_cur = e;
-            const Affine<F> P_cur = P;
-            if (pos + 1 < end) {                       // prefetch the next point while this one is added
-                e = entries[pos + 1];
-                P = ldg_vec(bases + (e & 0x7fffffffu));
-            }
-            xyzz_madd<F>(acc, P_cur.x, P_cur.y, (e_cur >> 31) != 0);
+    uint32_t bend = offsets[key + 1];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    uint32_t e = entries[start];
+    Affine<F> P = ldg_vec(bases + (e & 0x7fffffffu));
+    // One flat loop: every lane performs one mixed addition per iteration (convergent); the bucket
+    // bookkeeping at run boundaries is the only divergent part and is a few instructions plus one store.
+    for (uint32_t pos = start; pos < end; pos++) {
+        const uint32_t e_cur = e;
+        const Affine<F> P_cur = P;
+        if (pos + 1 < end) {                       // prefetch the next point while this one is added
+            e = entries[pos + 1];
+            P = ldg_vec(bases + (e & 0x7fffffffu));
         }
-        const bool closes = bend <= end;
-        if (!head_open && closes) st_vec(bucket_sums + key, acc);
-        else if (head_open) st_vec(part_head + chunk, acc);
-        else { st_vec(part_tail + chunk, acc); tail_owner_key[chunk] = key; }
-        head_open = false;
-        if (pos < end) { do { key++; } while (offsets[key + 1] <= pos); }
+        xyzz_madd<F>(acc, P_cur.x, P_cur.y, (e_cur >> 31) != 0);
+        const uint32_t nxt = pos + 1;
+        if (nxt == bend || nxt == end) {
+            const bool closes = nxt == bend;
+            if (!head_open && closes) st_vec(bucket_sums + key, acc);
+            else if (head_open) st_vec(part_head + chunk, acc);
+            else { st_vec(part_tail + chunk, acc); tail_owner_key[chunk] = key; }
+            head_open = false;
+            acc = XYZZ<F>::inf();
+            if (nxt < end) {
+                do { key++; } while (offsets[key + 1] <= nxt);
+                bend = offsets[key + 1];
+            }
+        }
     }
+}
+
+// K5b: buckets that straddle chunk boundaries.  Element 0 of a chain is the tail partial of the chunk where
+// the bucket starts, element k the head partial of chunk + k.  Short chains (the common case) are folded
+// by one thread; long chains (one bucket holding a large share of all entries — witness vectors full of
+// ones) are queued and folded warp-cooperatively by msm_fixup_long_kernel.
+#define FIXUP_SHORT 6
+template <class F>
+__global__ void __launch_bounds__(128) msm_fixup_kernel(const uint32_t* __restrict__ offsets, uint32_t nkeys, uint32_t Lc, uint32_t nchunks,
+                                                        const XYZZ<F>* part_head, const XYZZ<F>* part_tail, const uint32_t* tail_owner_key,
+                                                        XYZZ<F>* bucket_sums, uint32_t* long_list, uint32_t* long_count) {
+    const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chunk >= nchunks) return;
+    const uint32_t key = tail_owner_key[chunk];
+    if (key == 0xffffffffu) return;
+    const uint32_t bend = offsets[key + 1];
+    const uint32_t t_end = (bend - 1) / Lc;        // last chunk holding entries of this bucket
+    const uint32_t count = t_end - chunk + 1;
+    if (count > FIXUP_SHORT) { long_list[atomicAdd(long_count, 1u)] = chunk; return; }
+    XYZZ<F> acc = ld_vec(part_tail + chunk);
+    for (uint32_t k = 1; k < count; k++) {
+        XYZZ<F> v = ld_vec(part_head + chunk + k);
+        xyzz_add<F>(acc, v);
+    }
+    st_vec(bucket_sums + key, acc);
 }
 
 template <class F>
@@ -190,54 +220,54 @@ static __device__ __forceinline__ XYZZ<F> warp_reduce_xyzz(XYZZ<F> acc, unsigned
     return acc;
 }
 
-// K5b: one warp per bucket that straddles chunk boundaries: tail partial of the chunk where the bucket
-// starts + head partials of every following chunk the bucket reaches into.
 template <class F>
-__global__ void __launch_bounds__(128) msm_fixup_kernel(const uint32_t* __restrict__ offsets, uint32_t nkeys, uint32_t Lc, uint32_t nchunks,
-                                                        const XYZZ<F>* part_head, const XYZZ<F>* part_tail, const uint32_t* tail_owner_key,
-                                                        XYZZ<F>* bucket_sums) {
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__global__ void __launch_bounds__(128) msm_fixup_long_kernel(const uint32_t* __restrict__ offsets, uint32_t Lc, const XYZZ<F>* part_head,
+                                                             const XYZZ<F>* part_tail, const uint32_t* tail_owner_key, XYZZ<F>* bucket_sums,
+                                                             const uint32_t* long_list, const uint32_t* long_count) {
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     const unsigned lane = threadIdx.x & 31;
-    if (warp >= nchunks) return;
-    const uint32_t key = tail_owner_key[warp];
-    if (key == 0xffffffffu) return;
-    const uint32_t bend = offsets[key + 1];
-    const uint32_t t_end = (bend - 1) / Lc;        // last chunk holding entries of this bucket
-    const uint32_t count = t_end - warp + 1;       // element 0 = tail of `warp`, element k = head of warp + k
-    XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t k = lane; k < count; k += 32) {
-        XYZZ<F> v = k == 0 ? ld_vec(part_tail + warp) : ld_vec(part_head + warp + k);
-        xyzz_add<F>(acc, v);
+    const uint32_t total = *long_count;
+    for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += nwarps) {
+        const uint32_t chunk = long_list[item];
+        const uint32_t key = tail_owner_key[chunk];
+        const uint32_t bend = offsets[key + 1];
+        const uint32_t count = (bend - 1) / Lc - chunk + 1;
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t k = lane; k < count; k += 32) {
+            XYZZ<F> v = k == 0 ? ld_vec(part_tail + chunk) : ld_vec(part_head + chunk + k);
+            xyzz_add<F>(acc, v);
+        }
+        acc = warp_reduce_xyzz<F>(acc, lane);
+        if (lane == 0) st_vec(bucket_sums + key, acc);
     }
-    acc = warp_reduce_xyzz<F>(acc, lane);
-    if (lane == 0) st_vec(bucket_sums + key, acc);
 }
 
-// K6a: thread per segment of `seg` buckets inside one window: sum_{b in seg} (b+1) * S_b
+// K6a: one level of the weighted bucket reduction.  For window w and segment j of s items X_i:
+//   T_j = sum X_i,  acc_j = sum (i - lo_j) X_i   (running sums, 2(s-1) additions, no scalar multiplication)
+// sum_i i X_i = sum_j acc_j + s * sum_j j T_j, so the T_j are the items of the next level; acc_j, scaled by
+// s^level (scale_dbl doublings), goes into a per-window pool that is summed at the end:
+//   sum_b (b+1) S_b = sum(pool) + T_final.
 template <class F>
-__global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(const XYZZ<F>* __restrict__ bucket_sums, uint32_t B, uint32_t seg,
-                                                                uint32_t segs_per_window, uint32_t total_segs, XYZZ<F>* seg_out) {
+__global__ void __launch_bounds__(128) msm_weighted_level_kernel(const XYZZ<F>* __restrict__ in, uint32_t n_in, uint32_t s, uint32_t n_out,
+                                                                 uint32_t total, int scale_dbl, XYZZ<F>* t_out, XYZZ<F>* pool,
+                                                                 uint32_t pool_stride, uint32_t pool_off) {
     const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= total_segs) return;
-    const uint32_t w = id / segs_per_window, s = id % segs_per_window;
-    const uint32_t lo = s * seg, hi = lo + seg < B ? lo + seg : B;
+    if (id >= total) return;
+    const uint32_t w = id / n_out, j = id % n_out;
+    const XYZZ<F>* base = in + (size_t)w * n_in + (size_t)j * s;
     XYZZ<F> running = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
-    for (uint32_t b = hi; b-- > lo;) {
-        XYZZ<F> v = ld_vec(bucket_sums + (size_t)w * B + b);
+    for (uint32_t i = s; i-- > 1;) {
+        XYZZ<F> v = ld_vec(base + i);
         xyzz_add<F>(running, v);
         xyzz_add<F>(acc, running);
     }
-    if (lo) {
-        // + lo * running, MSB-first from the highest set bit
-        XYZZ<F> m = running;
-        int top = 31 - __clz(lo);
-        for (int i = top - 1; i >= 0; i--) {
-            m = xyzz_dbl<F>(m);
-            if ((lo >> i) & 1u) xyzz_add<F>(m, running);
-        }
-        xyzz_add<F>(acc, m);
+    {
+        XYZZ<F> v = ld_vec(base);
+        xyzz_add<F>(running, v);
     }
-    st_vec(seg_out + id, acc);
+    for (int k = 0; k < scale_dbl; k++) acc = xyzz_dbl<F>(acc);
+    st_vec(t_out + (size_t)w * n_out + j, running);
+    st_vec(pool + (size_t)w * pool_stride + pool_off + j, acc);
 }
 
 // K6b: warp per group of `per` consecutive points -> one sum
@@ -461,7 +491,8 @@ XYZZ<F> msm_run(Ctx* ctx, const Affine<F>* d_bases, const uint32_t* d_scalars, s
     if (n >= ((size_t)1 << 27)) throw ZaError(ZA_ERR_INVALID, "multiexp of 2^27 or more points is not supported");
     cudaStream_t st = ctx->stream;
     if (has_infinity) {
-        DevBuf flag(4);
+        DevBuf& flag = ctx->scratch[11];
+        flag.ensure(256);
         ZA_CUDA(cudaMemsetAsync(flag.p, 0, 4, st));
         msm_identity_check_kernel<F><<<nblk(n, 256), 256, 0, st>>>(d_bases, d_scalars, n, flag.as<uint32_t>());
         ctx->launches++;
@@ -489,18 +520,20 @@ XYZZ<F> msm_run(Ctx* ctx, const Affine<F>* d_bases, const uint32_t* d_scalars, s
     const uint32_t nkeys = (uint32_t)W * B;
     const uint64_t Emax = (uint64_t)n * W;
     if (Emax >= 0xffffffffull) throw ZaError(ZA_ERR_INVALID, "multiexp too large for 32-bit entry offsets");
-    // chunk length: ~8 chunks per resident thread slot, between 8 and 2048 entries
-    uint64_t slots = (uint64_t)ctx->sm_count * 512 * 8;
+    // chunk length: ~4 chunks per resident thread slot, between 16 and 2048 entries
+    uint64_t slots = (uint64_t)ctx->sm_count * 512 * 4;
     uint32_t Lc = (uint32_t)((Emax + slots - 1) / slots);
-    if (Lc < 8) Lc = 8;
+    if (Lc < 16) Lc = 16;
     if (Lc > 2048) Lc = 2048;
     const uint32_t nchunks = (uint32_t)((Emax + Lc - 1) / Lc);
 
-    DevBuf& counts = ctx->scratch[2];      // counts | offsets | cursors
-    counts.ensure(((size_t)nkeys * 3 + 2) * 4);
+    DevBuf& counts = ctx->scratch[2];      // counts | offsets | cursors | long_count | long_list
+    counts.ensure(((size_t)nkeys * 3 + 4 + nchunks) * 4);
     uint32_t* d_counts = counts.as<uint32_t>();
     uint32_t* d_offsets = d_counts + nkeys;
     uint32_t* d_cursors = d_offsets + nkeys + 1;
+    uint32_t* d_long_count = d_cursors + nkeys;
+    uint32_t* d_long_list = d_long_count + 1;
     DevBuf& entries = ctx->scratch[3];
     entries.ensure((size_t)Emax * 4);
     DevBuf& buckets = ctx->scratch[4];
@@ -510,38 +543,74 @@ XYZZ<F> msm_run(Ctx* ctx, const Affine<F>* d_bases, const uint32_t* d_scalars, s
     XYZZ<F>* d_head = parts.as<XYZZ<F>>();
     XYZZ<F>* d_tail = d_head + nchunks;
     uint32_t* d_owner = reinterpret_cast<uint32_t*>(d_tail + nchunks);
-    uint32_t seg = 32;
-    if (seg > B) seg = B;
-    const uint32_t segs_per_window = B / seg;
-    const uint32_t total_segs = segs_per_window * (uint32_t)W;
-    DevBuf& segs = ctx->scratch[6];
-    segs.ensure((size_t)(total_segs + W) * sizeof(XYZZ<F>));
-    XYZZ<F>* d_seg = segs.as<XYZZ<F>>();
-    XYZZ<F>* d_win = d_seg + total_segs;
+    // weighted bucket reduction: levels of segment size 16 (B is a power of two)
+    const uint32_t SEG = 16;
+    struct Level { uint32_t n_in, s, n_out, pool_off; };
+    std::vector<Level> levels;
+    uint32_t pool_len = 0;
+    for (uint32_t nin = B; nin > 1;) {
+        uint32_t sgm = nin < SEG ? nin : SEG;
+        Level lv{nin, sgm, nin / sgm, pool_len};
+        pool_len += lv.n_out;
+        levels.push_back(lv);
+        nin = lv.n_out;
+    }
+    const uint32_t pool_used = pool_len + 1;                         // + the final plain sum T
+    const uint32_t pool_stride = (pool_used + 63) / 64 * 64;         // padded with points at infinity
+    const uint32_t pool_groups = pool_stride / 64;
+    DevBuf& segs = ctx->scratch[6];        // pool | level buffers (ping-pong) | group sums | window sums
+    const size_t lvl_elems = (size_t)W * (B / (B < SEG ? B : SEG) + 1);
+    segs.ensure(((size_t)W * pool_stride + 2 * lvl_elems + (size_t)W * pool_groups + W) * sizeof(XYZZ<F>));
+    XYZZ<F>* d_pool = segs.as<XYZZ<F>>();
+    XYZZ<F>* d_lvl[2] = {d_pool + (size_t)W * pool_stride, d_pool + (size_t)W * pool_stride + lvl_elems};
+    XYZZ<F>* d_grp = d_lvl[1] + lvl_elems;
+    XYZZ<F>* d_win = d_grp + (size_t)W * pool_groups;
 
     ZA_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nkeys * 4, st));
+    ZA_CUDA(cudaMemsetAsync(d_long_count, 0, 4, st));
     ZA_CUDA(cudaMemsetAsync(buckets.p, 0, (size_t)nkeys * sizeof(XYZZ<F>), st));
     ZA_CUDA(cudaMemsetAsync(d_owner, 0xff, (size_t)nchunks * 4, st));
+    ZA_CUDA(cudaMemsetAsync(d_pool, 0, (size_t)W * pool_stride * sizeof(XYZZ<F>), st));
     {
         ProfScope prof(ctx, PROF_MSM_SORT, (double)n);
         msm_digits_hist_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_counts);
         msm_scan_kernel<<<1, 1024, 0, st>>>(d_counts, nkeys, d_offsets, d_cursors);
         msm_digits_scatter_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_cursors, entries.as<uint32_t>());
+        ctx->launches += 3;
     }
     const int acc_cat = sizeof(F) == sizeof(Fq) ? PROF_ACC_G1 : PROF_ACC_G2;
     {
         ProfScope prof(ctx, acc_cat, 0);
         msm_accumulate_kernel<F><<<nblk(nchunks, 128), 128, 0, st>>>(d_bases, entries.as<uint32_t>(), d_offsets, nkeys, Lc,
                                                                      buckets.as<XYZZ<F>>(), d_head, d_tail, d_owner);
+        ctx->launches++;
     }
     {
         ProfScope prof(ctx, PROF_MSM_REDUCE, (double)nkeys);
-        msm_fixup_kernel<F><<<nblk((size_t)nchunks * 32, 128), 128, 0, st>>>(d_offsets, nkeys, Lc, nchunks, d_head, d_tail, d_owner,
-                                                                             buckets.as<XYZZ<F>>());
-        msm_bucket_reduce_kernel<F><<<nblk(total_segs, 128), 128, 0, st>>>(buckets.as<XYZZ<F>>(), B, seg, segs_per_window, total_segs, d_seg);
-        msm_group_reduce_kernel<F><<<nblk((size_t)W * 32, 128), 128, 0, st>>>(d_seg, segs_per_window, (uint32_t)W, d_win);
+        msm_fixup_kernel<F><<<nblk(nchunks, 128), 128, 0, st>>>(d_offsets, nkeys, Lc, nchunks, d_head, d_tail, d_owner, buckets.as<XYZZ<F>>(),
+                                                                d_long_list, d_long_count);
+        msm_fixup_long_kernel<F><<<ctx->sm_count * 2, 128, 0, st>>>(d_offsets, Lc, d_head, d_tail, d_owner, buckets.as<XYZZ<F>>(), d_long_list,
+                                                                    d_long_count);
+        ctx->launches += 2;
+        const XYZZ<F>* src = buckets.as<XYZZ<F>>();
+        int li = 0;
+        for (const Level& lv : levels) {
+            XYZZ<F>* dst = d_lvl[li & 1];
+            // acc of level l carries weight SEG^l: every earlier level had the full segment size SEG = 2^4
+            const uint32_t total = (uint32_t)W * lv.n_out;
+            msm_weighted_level_kernel<F><<<nblk(total, 128), 128, 0, st>>>(src, lv.n_in, lv.s, lv.n_out, total, 4 * li, dst, d_pool, pool_stride,
+                                                                           lv.pool_off);
+            ctx->launches++;
+            src = dst;
+            li++;
+        }
+        // the final T (one per window) is the plain sum of all buckets: pool slot pool_len
+        ZA_CUDA(cudaMemcpy2DAsync(d_pool + pool_len, (size_t)pool_stride * sizeof(XYZZ<F>), src, sizeof(XYZZ<F>), sizeof(XYZZ<F>), W,
+                                  cudaMemcpyDeviceToDevice, st));
+        msm_group_reduce_kernel<F><<<nblk((size_t)W * pool_groups * 32, 128), 128, 0, st>>>(d_pool, 64, (uint32_t)W * pool_groups, d_grp);
+        msm_group_reduce_kernel<F><<<nblk((size_t)W * 32, 128), 128, 0, st>>>(d_grp, pool_groups, (uint32_t)W, d_win);
+        ctx->launches += 2;
     }
-    ctx->launches += 7;
     ZA_CUDA(cudaGetLastError());
     std::vector<XYZZ<F>> win(W);
     ZA_CUDA(cudaMemcpyAsync(win.data(), d_win, (size_t)W * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));

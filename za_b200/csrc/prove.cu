@@ -500,7 +500,8 @@ static void prove_assemble(const Pk* pk, const Partials& P, const uint8_t* r_le,
 static void create_proof_device(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* d_wit, const uint8_t* r_le, const uint8_t* s_le,
                                 uint8_t* proof_out, za_trace* tr) {
     const size_t m = domain_size(c, nullptr);
-    DevBuf h(m * sizeof(Fr));
+    DevBuf& h = ctx->scratch[9];
+    h.ensure(m * sizeof(Fr));
     prove_h(ctx, c, d_wit, h.as<Fr>(), tr);
     Partials P;
     prove_msms(ctx, pk, c, d_wit, h.as<Fr>(), 0, 1, P);
@@ -514,7 +515,8 @@ static void create_proof(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t
     cudaStream_t st = ctx->stream;
     const uint32_t ni = c->ni, na = c->na;
     check_scalars_canonical(inputs, ni, "inputs"); check_scalars_canonical(aux, na, "aux");
-    DevBuf wit(((size_t)ni + na) * 32);
+    DevBuf& wit = ctx->scratch[10];
+    wit.ensure(((size_t)ni + na) * 32);
     ZA_CUDA(cudaMemcpyAsync(wit.p, inputs, (size_t)ni * 32, cudaMemcpyHostToDevice, st));
     if (na) ZA_CUDA(cudaMemcpyAsync((uint8_t*)wit.p + (size_t)ni * 32, aux, (size_t)na * 32, cudaMemcpyHostToDevice, st));
     create_proof_device(ctx, pk, c, (const uint8_t*)wit.p, r_le, s_le, proof_out, tr);
@@ -611,7 +613,7 @@ int za_multiexp(za_ctx* ctx, const za_bases* bases, size_t offset, const uint8_t
         for (size_t i = 0; i < n_exp; i++) if (density[i]) { memcpy(compact.data() + 32 * k, scalars + 32 * i, 32); k++; }
         src = compact.data(); n = cnt;
     }
-    DevBuf& d = c->scratch[7];
+    DevBuf& d = c->scratch[8];
     d.ensure(n * 32);
     if (n) ZA_CUDA(cudaMemcpyAsync(d.p, src, n * 32, cudaMemcpyHostToDevice, c->stream));
     return multiexp_common(ctx, bases, offset, d.as<uint32_t>(), n, out, false);
