@@ -22,6 +22,12 @@ int fail(int code, const char* fmt, ...) {
 }
 Ctx::~Ctx() {
     for (auto& kv : domains) delete kv.second;
+    for (MsmSlot& sl : slots) {
+        if (sl.host_win) cudaFreeHost(sl.host_win);
+        if (sl.acc_done) cudaEventDestroy(sl.acc_done);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (side) cudaStreamDestroy(side);
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -69,6 +75,7 @@ int za_ctx_create(int device, za_ctx** out) {
     c->c.device = device;
     c->c.sm_count = prop.multiProcessorCount;
     ZA_CUDA(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
+    ZA_CUDA(cudaStreamCreateWithFlags(&c->c.side, cudaStreamNonBlocking));
     c->c.stream = c->own;
     c->c.own_stream = false;  // destroyed below, not by ~Ctx
     *out = c;
@@ -80,6 +87,7 @@ void za_ctx_destroy(za_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->c.device);
     cudaStreamSynchronize(ctx->c.stream);
+    if (ctx->c.side) cudaStreamSynchronize(ctx->c.side);
     if (ctx->own) cudaStreamDestroy(ctx->own);
     delete ctx;
 }

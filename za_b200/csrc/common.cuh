@@ -73,6 +73,24 @@ struct NttDomain {
     bool have_coset = false;
 };
 
+// Per-multiexp working set, so that several multiexps can be in flight (sort + accumulate on the main
+// stream, bucket reduction on the side stream) and their window sums collected at the end.
+struct MsmSlot {
+    DevBuf counts, entries, buckets, parts, segs;
+    void* host_win = nullptr;            // pinned: window sums (+ entry count when profiling)
+    size_t host_win_bytes = 0;
+    cudaEvent_t acc_done = nullptr, done = nullptr;
+    bool busy = false;                   // enqueued, not yet finished
+    bool done_valid = false;             // `done` has been recorded at least once
+    uint32_t sort_users = 0;             // slots that reuse this slot's digit sort since its last enqueue
+    int kind = 0;                        // 0 empty, 1 naive (small), 2 bucket method
+    int c = 0, W = 0, warps = 0, acc_cat = 0;
+    uint32_t nkeys = 0, Lc = 0, nchunks = 0;
+    size_t n = 0;
+    uint32_t* d_offsets = nullptr;       // sort result (may be shared by a later multiexp over the same scalars)
+    uint32_t* d_entries = nullptr;
+};
+
 enum { PROF_ACC_G1 = 0, PROF_ACC_G2 = 1, PROF_NTT = 2, PROF_MSM_SORT = 3, PROF_MSM_REDUCE = 4, PROF_R1CS = 5, PROF_POINTWISE = 6, PROF_OTHER = 7, PROF_NCAT = 8 };
 struct ProfSpan { cudaEvent_t a, b; int cat; };
 
@@ -84,6 +102,8 @@ struct Ctx {
     std::map<int, NttDomain*> domains;  // by log_n
     // scratch reused across calls
     DevBuf scratch[16];
+    MsmSlot slots[8];
+    cudaStream_t side = nullptr;        // bucket reductions overlap the next multiexp's accumulation here
     uint64_t launches = 0;              // kernels launched through this context (bench: gpu_launches)
     // optional per-kernel-class timing with CUDA events on `stream` (bench.py roofline numbers)
     bool profile = false;
@@ -98,15 +118,17 @@ NttDomain* get_domain(Ctx* ctx, int log_n, bool need_coset);
 // RAII: brackets the kernels issued in its scope with two events when profiling is on
 struct ProfScope {
     Ctx* c; int cat; cudaEvent_t a = nullptr, b = nullptr;
-    ProfScope(Ctx* ctx, int category, double work = 0) : c(ctx), cat(category) {
+    cudaStream_t st;
+    ProfScope(Ctx* ctx, int category, double work = 0, cudaStream_t on = nullptr, bool use_on = false) : c(ctx), cat(category) {
+        st = use_on ? on : c->stream;
         if (!c->profile) return;
         cudaEventCreate(&a); cudaEventCreate(&b);
-        cudaEventRecord(a, c->stream);
+        cudaEventRecord(a, st);
         c->prof_work[cat] += work; c->prof_count[cat]++;
     }
     ~ProfScope() {
         if (!a) return;
-        cudaEventRecord(b, c->stream);
+        cudaEventRecord(b, st);
         c->spans.push_back(ProfSpan{a, b, cat});
     }
 };

@@ -22,6 +22,7 @@
 // normalisation (representation independent).
 #include "common.cuh"
 #include "api_internal.cuh"
+#include <string.h>
 
 namespace za {
 
@@ -104,30 +105,65 @@ __global__ void msm_digits_scatter_kernel(const uint32_t* __restrict__ scalars, 
     }
 }
 
-// K4b: exclusive scan of `count` values (+ total at [count]); single CTA of 1024 threads.
-__global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* counts, uint32_t count, uint32_t* offsets, uint32_t* cursors) {
-    __shared__ uint32_t sums[1024];
-    const uint32_t t = threadIdx.x;
-    const uint32_t per = (count + 1023) / 1024;
-    const uint32_t lo = t * per, hi = (lo + per < count) ? lo + per : count;
-    uint32_t s = 0;
-    for (uint32_t i = lo; i < hi; i++) s += counts[i];
-    sums[t] = s;
+// K4b: exclusive scan of the per-bucket counts in three small kernels (4096 counters per CTA):
+// per-CTA totals -> scan of the totals -> per-CTA rescan with the CTA's base offset.
+#define SCAN_PER_CTA 4096
+static __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* smem /*32*/, uint32_t& total) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (unsigned)d) x += y; }
+    if (lane == 31) smem[warp] = x;
     __syncthreads();
-    for (uint32_t d = 1; d < 1024; d <<= 1) {
-        uint32_t v = t >= d ? sums[t - d] : 0;
-        __syncthreads();
-        sums[t] += v;
-        __syncthreads();
+    if (warp == 0) {
+        uint32_t w = smem[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, w, d); if (lane >= (unsigned)d) w += y; }
+        smem[lane] = w;
     }
-    uint32_t run = t ? sums[t - 1] : 0;
-    for (uint32_t i = lo; i < hi; i++) {
-        uint32_t cnt = counts[i];
-        offsets[i] = run;
-        cursors[i] = run;
-        run += cnt;
+    __syncthreads();
+    total = smem[31];
+    uint32_t base = warp ? smem[warp - 1] : 0;
+    __syncthreads();
+    return base + x - v;
+}
+__global__ void __launch_bounds__(1024) msm_scan_totals_kernel(const uint32_t* counts, uint32_t count, uint32_t* cta_totals) {
+    __shared__ uint32_t sm[32];
+    const uint32_t base = blockIdx.x * SCAN_PER_CTA + threadIdx.x * 4;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (base + k < count) s += counts[base + k];
+    uint32_t total;
+    block_excl_scan_1024(s, sm, total);
+    if (threadIdx.x == 0) cta_totals[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) msm_scan_ctas_kernel(uint32_t* cta_totals, uint32_t nctas, uint32_t* grand_total) {
+    __shared__ uint32_t sm[32];
+    uint32_t run = 0;
+    for (uint32_t b0 = 0; b0 < nctas; b0 += 1024) {
+        uint32_t i = b0 + threadIdx.x;
+        uint32_t v = i < nctas ? cta_totals[i] : 0;
+        uint32_t total;
+        uint32_t ex = block_excl_scan_1024(v, sm, total);
+        if (i < nctas) cta_totals[i] = run + ex;
+        run += total;
     }
-    if (t == 1023) offsets[count] = sums[1023];
+    if (threadIdx.x == 0) *grand_total = run;
+}
+__global__ void __launch_bounds__(1024) msm_scan_apply_kernel(const uint32_t* counts, uint32_t count, const uint32_t* cta_offsets, uint32_t* offsets,
+                                                              uint32_t* cursors) {
+    __shared__ uint32_t sm[32];
+    const uint32_t base = blockIdx.x * SCAN_PER_CTA + threadIdx.x * 4;
+    uint32_t v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = base + k < count ? counts[base + k] : 0; s += v[k]; }
+    uint32_t total;
+    uint32_t run = cta_offsets[blockIdx.x] + block_excl_scan_1024(s, sm, total);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k < count) { offsets[base + k] = run; cursors[base + k] = run; }
+        run += v[k];
+    }
 }
 
 // K5: chunked segmented accumulation.  Thread `chunk` owns entries [chunk*Lc, (chunk+1)*Lc).
@@ -482,14 +518,33 @@ uint32_t bases_import(Ctx* ctx, void* d_pts, size_t n) {
 template uint32_t bases_import<Fq>(Ctx*, void*, size_t);
 template uint32_t bases_import<Fq2>(Ctx*, void*, size_t);
 
-// Runs the MSM; returns the result as a host XYZZ point (Montgomery form).
-// d_scalars: n canonical scalars on device.  has_infinity: bases may contain the (0,0) encoding.
+// Enqueue one multiexp into `slot` (0..7).  Sort + accumulate go to the context's stream, the bucket reduction
+// and the read-back of the W window sums to the side stream, so the next multiexp's accumulation overlaps it.
+// share_sort >= 0: reuse the digit sort of that slot (same scalar vector, e.g. the G1 and G2 B queries).
+// msm_finish waits for the slot and does the window combination on the host.
 template <class F>
-XYZZ<F> msm_run(Ctx* ctx, const Affine<F>* d_bases, const uint32_t* d_scalars, size_t n, bool has_infinity) {
-    XYZZ<F> result = XYZZ<F>::inf();
-    if (n == 0) return result;
+void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t* d_scalars, size_t n, bool has_infinity, int share_sort) {
+    MsmSlot& sl = ctx->slots[slot_id];
+    cudaStream_t st = ctx->stream, side = ctx->side;
+    if (sl.busy) throw ZaError(ZA_ERR_INVALID, "msm slot enqueued twice without msm_finish");
+    sl.kind = 0; sl.n = n;
+    if (n == 0) { sl.busy = true; return; }
+    // this slot's buffers (and its sort, if another slot borrowed it) may still be read by side-stream work
+    if (sl.done_valid) ZA_CUDA(cudaStreamWaitEvent(st, sl.done, 0));
+    for (int j = 0; j < 8; j++)
+        if ((sl.sort_users >> j) & 1u) { if (ctx->slots[j].done_valid) ZA_CUDA(cudaStreamWaitEvent(st, ctx->slots[j].done, 0)); }
+    sl.sort_users = 0;
     if (n >= ((size_t)1 << 27)) throw ZaError(ZA_ERR_INVALID, "multiexp of 2^27 or more points is not supported");
-    cudaStream_t st = ctx->stream;
+    if (!sl.done) {
+        ZA_CUDA(cudaEventCreateWithFlags(&sl.acc_done, cudaEventDisableTiming));
+        ZA_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
+    const size_t want_host = 64 + 128 * sizeof(XYZZ<Fq2>);     // header (entry count) + up to 128 windows
+    if (sl.host_win_bytes < want_host) {
+        if (sl.host_win) cudaFreeHost(sl.host_win);
+        ZA_CUDA(cudaHostAlloc(&sl.host_win, want_host, cudaHostAllocDefault));
+        sl.host_win_bytes = want_host;
+    }
     if (has_infinity) {
         DevBuf& flag = ctx->scratch[11];
         flag.ensure(256);
@@ -502,17 +557,17 @@ XYZZ<F> msm_run(Ctx* ctx, const Affine<F>* d_bases, const uint32_t* d_scalars, s
         if (h) throw ZaError(ZA_ERR_UNEXPECTED_IDENTITY, "multiexp: a base at infinity has a non-zero exponent");
     }
     if (n <= 64) {
-        const uint32_t warps = (uint32_t)((n + 31) / 32);
-        DevBuf& out = ctx->scratch[2];
-        out.ensure(warps * sizeof(XYZZ<F>));
-        msm_naive_kernel<F><<<nblk(warps * 32, 128), 128, 0, st>>>(d_bases, d_scalars, (uint32_t)n, out.as<XYZZ<F>>());
+        sl.kind = 1;
+        sl.warps = (int)((n + 31) / 32);
+        sl.segs.ensure(2 * sizeof(XYZZ<F>));
+        msm_naive_kernel<F><<<nblk((size_t)sl.warps * 32, 128), 128, 0, st>>>(d_bases, d_scalars, (uint32_t)n, sl.segs.as<XYZZ<F>>());
         ctx->launches++;
         ZA_CUDA(cudaGetLastError());
-        XYZZ<F> h[2];
-        ZA_CUDA(cudaMemcpyAsync(h, out.p, warps * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
-        ZA_CUDA(cudaStreamSynchronize(st));
-        for (uint32_t i = 0; i < warps; i++) xyzz_add<F>(result, h[i]);
-        return result;
+        ZA_CUDA(cudaMemcpyAsync((uint8_t*)sl.host_win + 64, sl.segs.p, (size_t)sl.warps * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
+        ZA_CUDA(cudaEventRecord(sl.done, st));
+        sl.done_valid = true;
+        sl.busy = true;
+        return;
     }
     const int c = msm_window_bits(n);
     const int W = (255 + c - 1) / c;
@@ -521,28 +576,40 @@ XYZZ<F> msm_run(Ctx* ctx, const Affine<F>* d_bases, const uint32_t* d_scalars, s
     const uint64_t Emax = (uint64_t)n * W;
     if (Emax >= 0xffffffffull) throw ZaError(ZA_ERR_INVALID, "multiexp too large for 32-bit entry offsets");
     // chunk length: ~4 chunks per resident thread slot, between 16 and 2048 entries
-    uint64_t slots = (uint64_t)ctx->sm_count * 512 * 4;
-    uint32_t Lc = (uint32_t)((Emax + slots - 1) / slots);
+    uint64_t tslots = (uint64_t)ctx->sm_count * 512 * 4;
+    uint32_t Lc = (uint32_t)((Emax + tslots - 1) / tslots);
     if (Lc < 16) Lc = 16;
     if (Lc > 2048) Lc = 2048;
     const uint32_t nchunks = (uint32_t)((Emax + Lc - 1) / Lc);
+    sl.kind = 2; sl.c = c; sl.W = W; sl.nkeys = nkeys; sl.Lc = Lc; sl.nchunks = nchunks;
+    sl.acc_cat = sizeof(F) == sizeof(Fq) ? PROF_ACC_G1 : PROF_ACC_G2;
 
-    DevBuf& counts = ctx->scratch[2];      // counts | offsets | cursors | long_count | long_list
-    counts.ensure(((size_t)nkeys * 3 + 4 + nchunks) * 4);
-    uint32_t* d_counts = counts.as<uint32_t>();
-    uint32_t* d_offsets = d_counts + nkeys;
-    uint32_t* d_cursors = d_offsets + nkeys + 1;
-    uint32_t* d_long_count = d_cursors + nkeys;
-    uint32_t* d_long_list = d_long_count + 1;
-    DevBuf& entries = ctx->scratch[3];
-    entries.ensure((size_t)Emax * 4);
-    DevBuf& buckets = ctx->scratch[4];
-    buckets.ensure((size_t)nkeys * sizeof(XYZZ<F>));
-    DevBuf& parts = ctx->scratch[5];       // part_head | part_tail | tail_owner_key
-    parts.ensure((size_t)nchunks * (2 * sizeof(XYZZ<F>) + 4));
-    XYZZ<F>* d_head = parts.as<XYZZ<F>>();
+    const uint32_t nctas = (nkeys + SCAN_PER_CTA - 1) / SCAN_PER_CTA;
+    uint32_t *d_counts = nullptr, *d_offsets, *d_cursors = nullptr, *d_cta = nullptr;
+    uint32_t* d_entries;
+    if (share_sort >= 0) {
+        const MsmSlot& src = ctx->slots[share_sort];
+        if (src.kind != 2 || src.n != n || src.c != c) throw ZaError(ZA_ERR_INVALID, "msm sort sharing needs an identical scalar vector");
+        d_offsets = src.d_offsets;
+        d_entries = src.d_entries;
+        ctx->slots[share_sort].sort_users |= 1u << slot_id;
+    } else {
+        sl.counts.ensure(((size_t)nkeys * 3 + 4 + nctas) * 4);   // counts | offsets (+total) | cursors | cta totals
+        d_counts = sl.counts.as<uint32_t>();
+        d_offsets = d_counts + nkeys;
+        d_cursors = d_offsets + nkeys + 1;
+        d_cta = d_cursors + nkeys;
+        sl.entries.ensure((size_t)Emax * 4);
+        d_entries = sl.entries.as<uint32_t>();
+    }
+    sl.d_offsets = d_offsets; sl.d_entries = d_entries;
+    sl.buckets.ensure((size_t)nkeys * sizeof(XYZZ<F>));
+    sl.parts.ensure((size_t)nchunks * (2 * sizeof(XYZZ<F>) + 8) + 16);   // part_head | part_tail | owner | long_list | long_count
+    XYZZ<F>* d_head = sl.parts.as<XYZZ<F>>();
     XYZZ<F>* d_tail = d_head + nchunks;
     uint32_t* d_owner = reinterpret_cast<uint32_t*>(d_tail + nchunks);
+    uint32_t* d_long_list = d_owner + nchunks;
+    uint32_t* d_long_count = d_long_list + nchunks;
     // weighted bucket reduction: levels of segment size 16 (B is a power of two)
     const uint32_t SEG = 16;
     struct Level { uint32_t n_in, s, n_out, pool_off; };
@@ -558,72 +625,103 @@ XYZZ<F> msm_run(Ctx* ctx, const Affine<F>* d_bases, const uint32_t* d_scalars, s
     const uint32_t pool_used = pool_len + 1;                         // + the final plain sum T
     const uint32_t pool_stride = (pool_used + 63) / 64 * 64;         // padded with points at infinity
     const uint32_t pool_groups = pool_stride / 64;
-    DevBuf& segs = ctx->scratch[6];        // pool | level buffers (ping-pong) | group sums | window sums
     const size_t lvl_elems = (size_t)W * (B / (B < SEG ? B : SEG) + 1);
-    segs.ensure(((size_t)W * pool_stride + 2 * lvl_elems + (size_t)W * pool_groups + W) * sizeof(XYZZ<F>));
-    XYZZ<F>* d_pool = segs.as<XYZZ<F>>();
+    sl.segs.ensure(((size_t)W * pool_stride + 2 * lvl_elems + (size_t)W * pool_groups + W) * sizeof(XYZZ<F>));
+    XYZZ<F>* d_pool = sl.segs.as<XYZZ<F>>();
     XYZZ<F>* d_lvl[2] = {d_pool + (size_t)W * pool_stride, d_pool + (size_t)W * pool_stride + lvl_elems};
     XYZZ<F>* d_grp = d_lvl[1] + lvl_elems;
     XYZZ<F>* d_win = d_grp + (size_t)W * pool_groups;
+    XYZZ<F>* d_buckets = sl.buckets.as<XYZZ<F>>();
 
-    ZA_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nkeys * 4, st));
-    ZA_CUDA(cudaMemsetAsync(d_long_count, 0, 4, st));
-    ZA_CUDA(cudaMemsetAsync(buckets.p, 0, (size_t)nkeys * sizeof(XYZZ<F>), st));
+    ZA_CUDA(cudaMemsetAsync(d_buckets, 0, (size_t)nkeys * sizeof(XYZZ<F>), st));
     ZA_CUDA(cudaMemsetAsync(d_owner, 0xff, (size_t)nchunks * 4, st));
+    ZA_CUDA(cudaMemsetAsync(d_long_count, 0, 4, st));
     ZA_CUDA(cudaMemsetAsync(d_pool, 0, (size_t)W * pool_stride * sizeof(XYZZ<F>), st));
-    {
+    if (share_sort < 0) {
+        ZA_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nkeys * 4, st));
         ProfScope prof(ctx, PROF_MSM_SORT, (double)n);
         msm_digits_hist_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_counts);
-        msm_scan_kernel<<<1, 1024, 0, st>>>(d_counts, nkeys, d_offsets, d_cursors);
-        msm_digits_scatter_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_cursors, entries.as<uint32_t>());
-        ctx->launches += 3;
+        msm_scan_totals_kernel<<<nctas, 1024, 0, st>>>(d_counts, nkeys, d_cta);
+        msm_scan_ctas_kernel<<<1, 1024, 0, st>>>(d_cta, nctas, d_offsets + nkeys);
+        msm_scan_apply_kernel<<<nctas, 1024, 0, st>>>(d_counts, nkeys, d_cta, d_offsets, d_cursors);
+        msm_digits_scatter_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_cursors, d_entries);
+        ctx->launches += 5;
     }
-    const int acc_cat = sizeof(F) == sizeof(Fq) ? PROF_ACC_G1 : PROF_ACC_G2;
     {
-        ProfScope prof(ctx, acc_cat, 0);
-        msm_accumulate_kernel<F><<<nblk(nchunks, 128), 128, 0, st>>>(d_bases, entries.as<uint32_t>(), d_offsets, nkeys, Lc,
-                                                                     buckets.as<XYZZ<F>>(), d_head, d_tail, d_owner);
+        ProfScope prof(ctx, sl.acc_cat, 0);
+        msm_accumulate_kernel<F><<<nblk(nchunks, 128), 128, 0, st>>>(d_bases, d_entries, d_offsets, nkeys, Lc, d_buckets, d_head, d_tail, d_owner);
         ctx->launches++;
     }
+    ZA_CUDA(cudaEventRecord(sl.acc_done, st));
+    ZA_CUDA(cudaStreamWaitEvent(side, sl.acc_done, 0));
     {
-        ProfScope prof(ctx, PROF_MSM_REDUCE, (double)nkeys);
-        msm_fixup_kernel<F><<<nblk(nchunks, 128), 128, 0, st>>>(d_offsets, nkeys, Lc, nchunks, d_head, d_tail, d_owner, buckets.as<XYZZ<F>>(),
-                                                                d_long_list, d_long_count);
-        msm_fixup_long_kernel<F><<<ctx->sm_count * 2, 128, 0, st>>>(d_offsets, Lc, d_head, d_tail, d_owner, buckets.as<XYZZ<F>>(), d_long_list,
-                                                                    d_long_count);
+        ProfScope prof(ctx, PROF_MSM_REDUCE, (double)nkeys, side, true);
+        msm_fixup_kernel<F><<<nblk(nchunks, 128), 128, 0, side>>>(d_offsets, nkeys, Lc, nchunks, d_head, d_tail, d_owner, d_buckets, d_long_list,
+                                                                  d_long_count);
+        msm_fixup_long_kernel<F><<<ctx->sm_count * 2, 128, 0, side>>>(d_offsets, Lc, d_head, d_tail, d_owner, d_buckets, d_long_list, d_long_count);
         ctx->launches += 2;
-        const XYZZ<F>* src = buckets.as<XYZZ<F>>();
+        const XYZZ<F>* src = d_buckets;
         int li = 0;
         for (const Level& lv : levels) {
             XYZZ<F>* dst = d_lvl[li & 1];
             // acc of level l carries weight SEG^l: every earlier level had the full segment size SEG = 2^4
             const uint32_t total = (uint32_t)W * lv.n_out;
-            msm_weighted_level_kernel<F><<<nblk(total, 128), 128, 0, st>>>(src, lv.n_in, lv.s, lv.n_out, total, 4 * li, dst, d_pool, pool_stride,
-                                                                           lv.pool_off);
+            msm_weighted_level_kernel<F><<<nblk(total, 128), 128, 0, side>>>(src, lv.n_in, lv.s, lv.n_out, total, 4 * li, dst, d_pool, pool_stride,
+                                                                             lv.pool_off);
             ctx->launches++;
             src = dst;
             li++;
         }
         // the final T (one per window) is the plain sum of all buckets: pool slot pool_len
         ZA_CUDA(cudaMemcpy2DAsync(d_pool + pool_len, (size_t)pool_stride * sizeof(XYZZ<F>), src, sizeof(XYZZ<F>), sizeof(XYZZ<F>), W,
-                                  cudaMemcpyDeviceToDevice, st));
-        msm_group_reduce_kernel<F><<<nblk((size_t)W * pool_groups * 32, 128), 128, 0, st>>>(d_pool, 64, (uint32_t)W * pool_groups, d_grp);
-        msm_group_reduce_kernel<F><<<nblk((size_t)W * 32, 128), 128, 0, st>>>(d_grp, pool_groups, (uint32_t)W, d_win);
+                                  cudaMemcpyDeviceToDevice, side));
+        msm_group_reduce_kernel<F><<<nblk((size_t)W * pool_groups * 32, 128), 128, 0, side>>>(d_pool, 64, (uint32_t)W * pool_groups, d_grp);
+        msm_group_reduce_kernel<F><<<nblk((size_t)W * 32, 128), 128, 0, side>>>(d_grp, pool_groups, (uint32_t)W, d_win);
         ctx->launches += 2;
     }
     ZA_CUDA(cudaGetLastError());
-    std::vector<XYZZ<F>> win(W);
-    ZA_CUDA(cudaMemcpyAsync(win.data(), d_win, (size_t)W * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
-    uint32_t E_host = 0;
-    if (ctx->profile) ZA_CUDA(cudaMemcpyAsync(&E_host, d_offsets + nkeys, 4, cudaMemcpyDeviceToHost, st));
-    ZA_CUDA(cudaStreamSynchronize(st));
-    if (ctx->profile) ctx->prof_work[acc_cat] += (double)E_host;   // mixed additions actually performed
+    ZA_CUDA(cudaMemcpyAsync((uint8_t*)sl.host_win + 64, d_win, (size_t)W * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, side));
+    if (ctx->profile) ZA_CUDA(cudaMemcpyAsync(sl.host_win, d_offsets + nkeys, 4, cudaMemcpyDeviceToHost, side));
+    ZA_CUDA(cudaEventRecord(sl.done, side));
+    sl.done_valid = true;
+    sl.busy = true;
+}
+template void msm_enqueue<Fq>(Ctx*, int, const Affine<Fq>*, const uint32_t*, size_t, bool, int);
+template void msm_enqueue<Fq2>(Ctx*, int, const Affine<Fq2>*, const uint32_t*, size_t, bool, int);
+
+template <class F>
+XYZZ<F> msm_finish(Ctx* ctx, int slot_id) {
+    MsmSlot& sl = ctx->slots[slot_id];
+    XYZZ<F> result = XYZZ<F>::inf();
+    if (!sl.busy) throw ZaError(ZA_ERR_INVALID, "msm_finish on an idle slot");
+    sl.busy = false;
+    if (sl.kind == 0) return result;
+    ZA_CUDA(cudaEventSynchronize(sl.done));
+    const XYZZ<F>* win = reinterpret_cast<const XYZZ<F>*>((const uint8_t*)sl.host_win + 64);
+    if (sl.kind == 1) {
+        for (int i = 0; i < sl.warps; i++) xyzz_add<F>(result, win[i]);
+        return result;
+    }
+    if (ctx->profile) {
+        uint32_t E;
+        memcpy(&E, sl.host_win, 4);
+        ctx->prof_work[sl.acc_cat] += (double)E;      // mixed additions actually performed
+    }
     // window combination on the host: result = sum_w 2^(c w) S_w   (bellman: `higher.double()` x c, then add)
-    for (int w = W - 1; w >= 0; w--) {
-        for (int k = 0; k < c; k++) result = xyzz_dbl<F>(result);
+    for (int w = sl.W - 1; w >= 0; w--) {
+        for (int k = 0; k < sl.c; k++) result = xyzz_dbl<F>(result);
         xyzz_add<F>(result, win[w]);
     }
     return result;
+}
+template XYZZ<Fq> msm_finish<Fq>(Ctx*, int);
+template XYZZ<Fq2> msm_finish<Fq2>(Ctx*, int);
+
+// One multiexp, synchronously.  d_scalars: n canonical scalars on device; has_infinity: bases may contain (0,0).
+template <class F>
+XYZZ<F> msm_run(Ctx* ctx, const Affine<F>* d_bases, const uint32_t* d_scalars, size_t n, bool has_infinity) {
+    msm_enqueue<F>(ctx, 0, d_bases, d_scalars, n, has_infinity, -1);
+    return msm_finish<F>(ctx, 0);
 }
 template XYZZ<Fq> msm_run<Fq>(Ctx*, const Affine<Fq>*, const uint32_t*, size_t, bool);
 template XYZZ<Fq2> msm_run<Fq2>(Ctx*, const Affine<Fq2>*, const uint32_t*, size_t, bool);

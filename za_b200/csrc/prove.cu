@@ -243,6 +243,10 @@ struct Circuit {
     std::vector<uint8_t> a_aux_density, b_in_density, b_aux_density;
     DevBuf a_aux_idx, b_in_idx, b_aux_idx;
     uint32_t a_aux_total = 0, b_in_total = 0, b_aux_total = 0;
+    // positions in the witness vector [inputs | aux] of the exponents of the whole A query (all inputs, then
+    // the aux with a_aux_density) and of the whole B query (inputs with b_input_density, then aux with b_aux_density)
+    DevBuf a_cat_idx, b_cat_idx;
+    uint32_t a_cat_total = 0, b_cat_total = 0;
 };
 
 __global__ void circuit_coeff_import_kernel(Fr* c, size_t n, uint32_t* flag) {
@@ -334,6 +338,17 @@ static std::unique_ptr<Circuit> circuit_upload(Ctx* ctx, const za_r1cs* cs) {
     make_idx(c->a_aux_density, c->a_aux_idx, c->a_aux_total);
     make_idx(c->b_in_density, c->b_in_idx, c->b_in_total);
     make_idx(c->b_aux_density, c->b_aux_idx, c->b_aux_total);
+    {
+        std::vector<uint32_t> a_cat, b_cat;
+        for (uint32_t i = 0; i < c->ni; i++) a_cat.push_back(i);
+        for (uint32_t i = 0; i < c->na; i++) if (c->a_aux_density[i]) a_cat.push_back(c->ni + i);
+        for (uint32_t i = 0; i < c->ni; i++) if (c->b_in_density[i]) b_cat.push_back(i);
+        for (uint32_t i = 0; i < c->na; i++) if (c->b_aux_density[i]) b_cat.push_back(c->ni + i);
+        c->a_cat_total = (uint32_t)a_cat.size(); c->b_cat_total = (uint32_t)b_cat.size();
+        c->a_cat_idx.alloc((size_t)c->a_cat_total * 4); c->b_cat_idx.alloc((size_t)c->b_cat_total * 4);
+        if (c->a_cat_total) ZA_CUDA(cudaMemcpy(c->a_cat_idx.p, a_cat.data(), (size_t)c->a_cat_total * 4, cudaMemcpyHostToDevice));
+        if (c->b_cat_total) ZA_CUDA(cudaMemcpy(c->b_cat_idx.p, b_cat.data(), (size_t)c->b_cat_total * 4, cudaMemcpyHostToDevice));
+    }
     return c;
 }
 
@@ -434,38 +449,71 @@ static inline void share(size_t cnt, int rank, int world, size_t& lo, size_t& hi
     hi = (size_t)(((unsigned __int128)cnt * (unsigned)(rank + 1)) / (unsigned)world);
 }
 
+template <class F>
+static void multiexp_enqueue(Ctx* ctx, int slot, const Bases* b, size_t offset, const uint32_t* d_scalars, size_t n, int share_sort = -1) {
+    if (offset > b->n || n > b->n - offset)
+        throw ZaError(ZA_ERR_IO, "multiexp: the base query is shorter than the exponent vector (bellman: unexpected EOF)");
+    msm_enqueue<F>(ctx, slot, b->pts.as<Affine<F>>() + offset, d_scalars, n, b->has_infinity, share_sort);
+}
+
+static void check_query_lengths(const Pk* pk, const Circuit* c, size_t m) {
+    // the whole-query length checks bellman's cursors would trip over (unexpected EOF)
+    if (pk->h->n < m - 1 || pk->l->n < c->na || pk->a->n < (size_t)c->ni + c->a_aux_total || pk->b_g1->n < (size_t)c->b_in_total + c->b_aux_total ||
+        pk->b_g2->n < (size_t)c->b_in_total + c->b_aux_total)
+        throw ZaError(ZA_ERR_IO, "create_proof: a proving-key query is shorter than the circuit needs (bellman: unexpected EOF)");
+}
+
 // ParameterSource for &Parameters: get_h -> (h,0); get_l -> (l,0); get_a -> ((a,0),(a,num_inputs));
-// get_b_g1/g2 -> ((b,0),(b,b_input_density_total)).  Each large query is cut by point range across ranks;
-// the input-sized queries run on rank 0.
+// get_b_g1/g2 -> ((b,0),(b,b_input_density_total)).  bellman runs the input part and the aux part of the A and B
+// queries as separate multiexps and adds the results; the bases are adjacent in the query, so here each query
+// is ONE multiexp over the concatenated exponent vector (the sums a_inputs + a_aux etc. are all create_proof
+// uses).  Five multiexps are in flight: H, L, A, B(G1), B(G2) — the last two share one digit sort.  Each query
+// is cut by point range across ranks.
 static void prove_msms(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* d_wit, const Fr* d_h, int rank, int world, Partials& out) {
     const uint32_t ni = c->ni, na = c->na;
     const size_t m = domain_size(c, nullptr);
     out = partials_zero();
-    const uint8_t* d_in = d_wit;
+    check_query_lengths(pk, c, m);
     const uint8_t* d_aux = d_wit + (size_t)ni * 32;
     size_t lo, hi;
-    // the whole-query length checks bellman's cursors would trip over (unexpected EOF)
-    if (pk->h->n < m - 1 || pk->l->n < na || pk->a->n < (size_t)ni + c->a_aux_total || pk->b_g1->n < (size_t)c->b_in_total + c->b_aux_total ||
-        pk->b_g2->n < (size_t)c->b_in_total + c->b_aux_total)
-        throw ZaError(ZA_ERR_IO, "create_proof: a proving-key query is shorter than the circuit needs (bellman: unexpected EOF)");
     share(m - 1, rank, world, lo, hi);
-    out.g1[0] = multiexp_dev<Fq>(ctx, pk->h.get(), lo, (const uint32_t*)(d_h + lo), hi - lo);
+    multiexp_enqueue<Fq>(ctx, 0, pk->h.get(), lo, (const uint32_t*)(d_h + lo), hi - lo);
     share(na, rank, world, lo, hi);
-    out.g1[1] = multiexp_dev<Fq>(ctx, pk->l.get(), lo, (const uint32_t*)(d_aux + lo * 32), hi - lo);
+    multiexp_enqueue<Fq>(ctx, 1, pk->l.get(), lo, (const uint32_t*)(d_aux + lo * 32), hi - lo);
+    const uint32_t* sa = gather(ctx, d_wit, c->a_cat_idx, c->a_cat_total, ctx->scratch[12]);
+    share(c->a_cat_total, rank, world, lo, hi);
+    multiexp_enqueue<Fq>(ctx, 2, pk->a.get(), lo, sa + lo * 8, hi - lo);
+    const uint32_t* sb = gather(ctx, d_wit, c->b_cat_idx, c->b_cat_total, ctx->scratch[13]);
+    share(c->b_cat_total, rank, world, lo, hi);
+    multiexp_enqueue<Fq>(ctx, 3, pk->b_g1.get(), lo, sb + lo * 8, hi - lo);
+    multiexp_enqueue<Fq2>(ctx, 4, pk->b_g2.get(), lo, sb + lo * 8, hi - lo, hi - lo > 64 ? 3 : -1);
+    out.g1[0] = msm_finish<Fq>(ctx, 0);
+    out.g1[1] = msm_finish<Fq>(ctx, 1);
+    out.g1[3] = msm_finish<Fq>(ctx, 2);      // a_inputs + a_aux
+    out.g1[5] = msm_finish<Fq>(ctx, 3);      // b1_inputs + b1_aux
+    out.g2[1] = msm_finish<Fq2>(ctx, 4);     // b2_inputs + b2_aux
+}
+
+// The same eight multiexps bellman runs, one by one (parity of every intermediate result; trace mode only).
+static void prove_msms_separate(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* d_wit, const Fr* d_h, Partials& out) {
+    const uint32_t ni = c->ni, na = c->na;
+    const size_t m = domain_size(c, nullptr);
+    out = partials_zero();
+    check_query_lengths(pk, c, m);
+    const uint8_t* d_in = d_wit;
+    const uint8_t* d_aux = d_wit + (size_t)ni * 32;
+    out.g1[0] = multiexp_dev<Fq>(ctx, pk->h.get(), 0, (const uint32_t*)d_h, m - 1);
+    out.g1[1] = multiexp_dev<Fq>(ctx, pk->l.get(), 0, (const uint32_t*)d_aux, na);
     DevBuf& gbuf = ctx->scratch[1];
-    if (rank == 0) {
-        out.g1[2] = multiexp_dev<Fq>(ctx, pk->a.get(), 0, (const uint32_t*)d_in, ni);
-        const uint32_t* sc_bin = gather(ctx, d_in, c->b_in_idx, c->b_in_total, gbuf);
-        out.g1[4] = multiexp_dev<Fq>(ctx, pk->b_g1.get(), 0, sc_bin, c->b_in_total);
-        out.g2[0] = multiexp_dev<Fq2>(ctx, pk->b_g2.get(), 0, sc_bin, c->b_in_total);
-    }
+    out.g1[2] = multiexp_dev<Fq>(ctx, pk->a.get(), 0, (const uint32_t*)d_in, ni);
+    const uint32_t* sc_bin = gather(ctx, d_in, c->b_in_idx, c->b_in_total, gbuf);
+    out.g1[4] = multiexp_dev<Fq>(ctx, pk->b_g1.get(), 0, sc_bin, c->b_in_total);
+    out.g2[0] = multiexp_dev<Fq2>(ctx, pk->b_g2.get(), 0, sc_bin, c->b_in_total);
     const uint32_t* sc = gather(ctx, d_aux, c->a_aux_idx, c->a_aux_total, gbuf);
-    share(c->a_aux_total, rank, world, lo, hi);
-    out.g1[3] = multiexp_dev<Fq>(ctx, pk->a.get(), ni + lo, sc + lo * 8, hi - lo);
+    out.g1[3] = multiexp_dev<Fq>(ctx, pk->a.get(), ni, sc, c->a_aux_total);
     sc = gather(ctx, d_aux, c->b_aux_idx, c->b_aux_total, gbuf);
-    share(c->b_aux_total, rank, world, lo, hi);
-    out.g1[5] = multiexp_dev<Fq>(ctx, pk->b_g1.get(), c->b_in_total + lo, sc + lo * 8, hi - lo);
-    out.g2[1] = multiexp_dev<Fq2>(ctx, pk->b_g2.get(), c->b_in_total + lo, sc + lo * 8, hi - lo);
+    out.g1[5] = multiexp_dev<Fq>(ctx, pk->b_g1.get(), c->b_in_total, sc, c->b_aux_total);
+    out.g2[1] = multiexp_dev<Fq2>(ctx, pk->b_g2.get(), c->b_in_total, sc, c->b_aux_total);
 }
 
 static void prove_assemble(const Pk* pk, const Partials& P, const uint8_t* r_le, const uint8_t* s_le, uint8_t* proof_out) {
@@ -504,9 +552,20 @@ static void create_proof_device(Ctx* ctx, const Pk* pk, const Circuit* c, const 
     h.ensure(m * sizeof(Fr));
     prove_h(ctx, c, d_wit, h.as<Fr>(), tr);
     Partials P;
+    if (tr && (tr->msm_g1 || tr->msm_g2)) {
+        // trace mode: bellman's eight multiexps individually, and the proof must not depend on the path taken
+        Partials S;
+        prove_msms_separate(ctx, pk, c, d_wit, h.as<Fr>(), S);
+        if (tr->msm_g1) for (int i = 0; i < 6; i++) g1_to_le(xyzz_to_affine<Fq>(S.g1[i]), tr->msm_g1 + 64 * i);
+        if (tr->msm_g2) for (int i = 0; i < 2; i++) g2_to_le(xyzz_to_affine<Fq2>(S.g2[i]), tr->msm_g2 + 128 * i);
+        uint8_t check[256];
+        prove_assemble(pk, S, r_le, s_le, check);
+        prove_msms(ctx, pk, c, d_wit, h.as<Fr>(), 0, 1, P);
+        prove_assemble(pk, P, r_le, s_le, proof_out);
+        if (memcmp(check, proof_out, 256) != 0) throw ZaError(ZA_ERR_INVALID, "internal: fused and separate multiexp paths disagree");
+        return;
+    }
     prove_msms(ctx, pk, c, d_wit, h.as<Fr>(), 0, 1, P);
-    if (tr && tr->msm_g1) for (int i = 0; i < 6; i++) g1_to_le(xyzz_to_affine<Fq>(P.g1[i]), tr->msm_g1 + 64 * i);
-    if (tr && tr->msm_g2) for (int i = 0; i < 2; i++) g2_to_le(xyzz_to_affine<Fq2>(P.g2[i]), tr->msm_g2 + 128 * i);
     prove_assemble(pk, P, r_le, s_le, proof_out);
 }
 
