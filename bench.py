@@ -269,7 +269,7 @@ def run_gpu(args):
                 "gpu_launches": int(launches), "clocks": clocks, "imad_peak_timads": imad_peak / 1e12}
 
     # ---- sub-metrics (rank-local, N = 1 only): 2^log_msm-point G1 MSM and 2^log_ntt Fr NTT, inputs resident
-    if world == 1:
+    if world == 1 and not args.no_sub:
         sub = {}
         n_msm = 1 << args.log_msm
         bases = za_b200.Bases.generate(ctx, 1, n_msm, 1)
@@ -328,6 +328,8 @@ def run_gpu(args):
             print("PARITY FAILURE: CPU oracle proof differs from the GPU proof", file=sys.stderr)
 
     if rank == 0:
+        if os.environ.get("ZA_BENCH_PRINT_PROOF"):
+            line["proof_hex"] = proof.hex()
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -347,6 +349,7 @@ def main():
     ap.add_argument("--log-ntt", dest="log_ntt", type=int, default=24)
     ap.add_argument("--cpu-log-m", dest="cpu_log_m", type=int, default=20, help="domain of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the MSM / NTT sub-metrics")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
