@@ -119,7 +119,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "ms", "cores": cores, "kind": "port", "sample": sample,
                              "note": "bellman-algorithm restatement (oracle/), not bellman itself"},
             "e2e": {"value": value, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -330,7 +330,7 @@ def run_gpu(args):
     if rank == 0:
         if os.environ.get("ZA_BENCH_PRINT_PROOF"):
             line["proof_hex"] = proof.hex()
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -338,7 +338,19 @@ def run_gpu(args):
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else (NCCL banners, library chatter) to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -181,6 +181,38 @@ ZA_HD void xyzz_madd(XYZZ<F>& acc, const F& x, const F& y, bool negate) {
 #endif
     xyzz_madd_body<F>(acc, x, y, negate);
 }
+
+#if defined(__CUDA_ARCH__)
+// The G1 mixed addition of the bucket-accumulation loop: same formula as xyzz_madd_body, inlined into the
+// kernel, but its ten field products go through the one shared copy fq_mul_call (the fully inlined version is
+// ~50 KB of code and stalls on instruction fetch: profiles/r01_ncu_summary.md, "no_instructions").
+static __device__ __forceinline__ void g1_madd_hot(XYZZ<Fq>& acc, const Fq& x, const Fq& y_in, bool negate) {
+    Fq y = negate ? -y_in : y_in;
+    if (acc.is_inf()) {
+        acc.X = x; acc.Y = y; acc.ZZ = Fq::one(); acc.ZZZ = Fq::one();
+        return;
+    }
+    Fq U2 = fq_mul_call(x, acc.ZZ);
+    Fq S2 = fq_mul_call(y, acc.ZZZ);
+    Fq P = U2 - acc.X;
+    Fq R = S2 - acc.Y;
+    if (P.is_zero()) {
+        if (R.is_zero()) acc = xyzz_dbl_affine<Fq>(x, y);
+        else acc = XYZZ<Fq>::inf();
+        return;
+    }
+    Fq PP = fq_mul_call(P, P);
+    Fq PPP = fq_mul_call(P, PP);
+    Fq Q = fq_mul_call(acc.X, PP);
+    Fq X3 = fq_mul_call(R, R) - PPP - dbl(Q);
+    acc.Y = fq_mul_call(R, Q - X3) - fq_mul_call(acc.Y, PPP);
+    acc.X = X3;
+    acc.ZZ = fq_mul_call(acc.ZZ, PP);
+    acc.ZZZ = fq_mul_call(acc.ZZZ, PPP);
+}
+static __device__ __forceinline__ void xyzz_madd_hot(XYZZ<Fq>& acc, const Fq& x, const Fq& y, bool negate) { g1_madd_hot(acc, x, y, negate); }
+static __device__ __forceinline__ void xyzz_madd_hot(XYZZ<Fq2>& acc, const Fq2& x, const Fq2& y, bool negate) { g2_madd_call(&acc, &x, &y, negate); }
+#endif
 template <class F>
 ZA_HD void xyzz_madd(XYZZ<F>& acc, const Affine<F>& p, bool negate = false) {
     if (p.is_inf()) return;

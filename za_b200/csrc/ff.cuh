@@ -408,6 +408,11 @@ typedef Fp<FqParams> Fq;
 template <class P> ZA_HD Fp<P> operator+(const Fp<P>& a, const Fp<P>& b) { return fp_add<P>(a, b); }
 template <class P> ZA_HD Fp<P> operator-(const Fp<P>& a, const Fp<P>& b) { return fp_sub<P>(a, b); }
 template <class P> ZA_HD Fp<P> operator*(const Fp<P>& a, const Fp<P>& b) { return fp_mul<P>(a, b); }
+// One shared, non-inlined copy of the Fq product for the places that would otherwise inline dozens of them
+// (Fq2 arithmetic, the G1 bucket-accumulation loop): less code than the instruction cache, seconds of ptxas.
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ Fp<FqParams> fq_mul_call(const Fp<FqParams> a, const Fp<FqParams> b) { return fp_mul<FqParams>(a, b); }
+#endif
 template <class P> ZA_HD Fp<P> operator-(const Fp<P>& a) { return fp_neg<P>(a); }
 template <class P> ZA_HD Fp<P> sqr(const Fp<P>& a) { return fp_sqr<P>(a); }
 template <class P> ZA_HD Fp<P> dbl(const Fp<P>& a) { return fp_dbl<P>(a); }
@@ -431,7 +436,6 @@ ZA_HD Fq2 dbl(const Fq2& a) { Fq2 r; r.c0 = dbl(a.c0); r.c1 = dbl(a.c1); return 
 // On the device the Fq product under Fq2 is a real call: G2 kernels would otherwise inline ~40 Montgomery
 // products per group operation (minutes of ptxas time, code far beyond the instruction cache).
 #if defined(__CUDA_ARCH__)
-static __device__ __noinline__ Fq fq_mul_call(const Fq a, const Fq b) { return fp_mul<FqParams>(a, b); }
 ZA_D Fq fq2_base_mul(const Fq& a, const Fq& b) { return fq_mul_call(a, b); }
 #else
 inline Fq fq2_base_mul(const Fq& a, const Fq& b) { return fp_mul<FqParams>(a, b); }

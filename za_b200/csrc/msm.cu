@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "api_internal.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace za {
 
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(128, (sizeof(F) == sizeof(Fq) ? 4 : 2)) msm_ac
             e = entries[pos + 1];
             P = ldg_vec(bases + (e & 0x7fffffffu));
         }
-        xyzz_madd<F>(acc, P_cur.x, P_cur.y, (e_cur >> 31) != 0);
+        xyzz_madd_hot(acc, P_cur.x, P_cur.y, (e_cur >> 31) != 0);
         const uint32_t nxt = pos + 1;
         if (nxt == bend || nxt == end) {
             const bool closes = nxt == bend;
@@ -477,6 +478,8 @@ Fq2 host_g2_b() {
 static inline unsigned nblk(size_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
 
 int msm_window_bits(size_t n) {
+    // ZA_MSM_C overrides the choice (tuning / tests of other window sizes)
+    if (const char* e = getenv("ZA_MSM_C")) { int c = atoi(e); if (c >= 2 && c <= 16) return c; }
     // minimise n*W*10 + W*2^(c-1)*28 field multiplications, with W = ceil(255/c); c <= 16 keeps the
     // bucket array (W * 2^(c-1) XYZZ points) and the reduction latency small.
     int best = 1;
@@ -575,8 +578,10 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
     const uint32_t nkeys = (uint32_t)W * B;
     const uint64_t Emax = (uint64_t)n * W;
     if (Emax >= 0xffffffffull) throw ZaError(ZA_ERR_INVALID, "multiexp too large for 32-bit entry offsets");
-    // chunk length: ~4 chunks per resident thread slot, between 16 and 2048 entries
-    uint64_t tslots = (uint64_t)ctx->sm_count * 512 * 4;
+    // chunk length: ~2 chunks per resident thread slot, between 16 and 2048 entries (measured best of 2/4/8 at 2^20)
+    uint64_t per_slot = 2;
+    if (const char* e = getenv("ZA_MSM_CHUNKS_PER_SLOT")) { int v = atoi(e); if (v >= 1 && v <= 64) per_slot = (uint64_t)v; }
+    uint64_t tslots = (uint64_t)ctx->sm_count * 512 * per_slot;
     uint32_t Lc = (uint32_t)((Emax + tslots - 1) / tslots);
     if (Lc < 16) Lc = 16;
     if (Lc > 2048) Lc = 2048;

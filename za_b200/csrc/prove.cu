@@ -469,13 +469,17 @@ static void check_query_lengths(const Pk* pk, const Circuit* c, size_t m) {
 // is ONE multiexp over the concatenated exponent vector (the sums a_inputs + a_aux etc. are all create_proof
 // uses).  Five multiexps are in flight: H, L, A, B(G1), B(G2) — the last two share one digit sort.  Each query
 // is cut by point range across ranks.
-static void prove_msms(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* d_wit, const Fr* d_h, int rank, int world, Partials& out) {
+static void prove_msms_enqueue(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* d_wit, const Fr* d_h, int rank, int world) {
     const uint32_t ni = c->ni, na = c->na;
     const size_t m = domain_size(c, nullptr);
-    out = partials_zero();
     check_query_lengths(pk, c, m);
     const uint8_t* d_aux = d_wit + (size_t)ni * 32;
     size_t lo, hi;
+    // G2 first: its (longest) bucket reduction then overlaps the G1 accumulations on the side stream
+    const uint32_t* sb = gather(ctx, d_wit, c->b_cat_idx, c->b_cat_total, ctx->scratch[13]);
+    share(c->b_cat_total, rank, world, lo, hi);
+    multiexp_enqueue<Fq>(ctx, 3, pk->b_g1.get(), lo, sb + lo * 8, hi - lo);
+    multiexp_enqueue<Fq2>(ctx, 4, pk->b_g2.get(), lo, sb + lo * 8, hi - lo, hi - lo > 64 ? 3 : -1);
     share(m - 1, rank, world, lo, hi);
     multiexp_enqueue<Fq>(ctx, 0, pk->h.get(), lo, (const uint32_t*)(d_h + lo), hi - lo);
     share(na, rank, world, lo, hi);
@@ -483,15 +487,15 @@ static void prove_msms(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* 
     const uint32_t* sa = gather(ctx, d_wit, c->a_cat_idx, c->a_cat_total, ctx->scratch[12]);
     share(c->a_cat_total, rank, world, lo, hi);
     multiexp_enqueue<Fq>(ctx, 2, pk->a.get(), lo, sa + lo * 8, hi - lo);
-    const uint32_t* sb = gather(ctx, d_wit, c->b_cat_idx, c->b_cat_total, ctx->scratch[13]);
-    share(c->b_cat_total, rank, world, lo, hi);
-    multiexp_enqueue<Fq>(ctx, 3, pk->b_g1.get(), lo, sb + lo * 8, hi - lo);
-    multiexp_enqueue<Fq2>(ctx, 4, pk->b_g2.get(), lo, sb + lo * 8, hi - lo, hi - lo > 64 ? 3 : -1);
+}
+// second half of prove_msms: wait for the five multiexps in completion order and combine their windows
+static void prove_msms_collect(Ctx* ctx, Partials& out) {
+    out = partials_zero();
+    out.g1[5] = msm_finish<Fq>(ctx, 3);      // b1_inputs + b1_aux
+    out.g2[1] = msm_finish<Fq2>(ctx, 4);     // b2_inputs + b2_aux
     out.g1[0] = msm_finish<Fq>(ctx, 0);
     out.g1[1] = msm_finish<Fq>(ctx, 1);
     out.g1[3] = msm_finish<Fq>(ctx, 2);      // a_inputs + a_aux
-    out.g1[5] = msm_finish<Fq>(ctx, 3);      // b1_inputs + b1_aux
-    out.g2[1] = msm_finish<Fq2>(ctx, 4);     // b2_inputs + b2_aux
 }
 
 // The same eight multiexps bellman runs, one by one (parity of every intermediate result; trace mode only).
@@ -516,32 +520,46 @@ static void prove_msms_separate(Ctx* ctx, const Pk* pk, const Circuit* c, const 
     out.g2[1] = multiexp_dev<Fq2>(ctx, pk->b_g2.get(), c->b_in_total, sc, c->b_aux_total);
 }
 
-static void prove_assemble(const Pk* pk, const Partials& P, const uint8_t* r_le, const uint8_t* s_le, uint8_t* proof_out) {
+// The part of the assembly that does not depend on the multiexps (steps 6-7: delta*r + alpha, delta2*s + beta2,
+// delta*rs + alpha*s + beta*r); computed on the host while the GPU runs the multiexps.
+struct AssemblePre { G1XYZZ g_a, g_c; G2XYZZ g_b; uint32_t r[8], s[8]; };
+static AssemblePre prove_assemble_pre(const Pk* pk, const uint8_t* r_le, const uint8_t* s_le) {
     if (pk->delta_g1.is_inf() || pk->delta_g2.is_inf()) throw ZaError(ZA_ERR_UNEXPECTED_IDENTITY, "create_proof: delta is the point at infinity");
     check_scalars_canonical(r_le, 1, "r"); check_scalars_canonical(s_le, 1, "s");
-    uint32_t r[8], s[8];
-    memcpy(r, r_le, 32); memcpy(s, s_le, 32);
-    Fr rf, sf; memcpy(rf.v, r, 32); memcpy(sf.v, s, 32);
+    AssemblePre A;
+    memcpy(A.r, r_le, 32); memcpy(A.s, s_le, 32);
+    Fr rf, sf; memcpy(rf.v, A.r, 32); memcpy(sf.v, A.s, 32);
     Fr rs_c = fp_from_mont<FrParams>(fp_to_mont<FrParams>(rf) * fp_to_mont<FrParams>(sf));
     G1XYZZ d1 = G1XYZZ::from_affine(pk->delta_g1), al = G1XYZZ::from_affine(pk->alpha_g1), be1 = G1XYZZ::from_affine(pk->beta_g1);
     G2XYZZ d2 = G2XYZZ::from_affine(pk->delta_g2);
-    G1XYZZ g_a = xyzz_mul<Fq>(d1, r); xyzz_madd<Fq>(g_a, pk->alpha_g1);
-    G2XYZZ g_b = xyzz_mul<Fq2>(d2, s); xyzz_madd<Fq2>(g_b, pk->beta_g2);
-    G1XYZZ g_c = xyzz_mul<Fq>(d1, rs_c.v);
-    xyzz_add<Fq>(g_c, xyzz_mul<Fq>(al, s));
-    xyzz_add<Fq>(g_c, xyzz_mul<Fq>(be1, r));
+    A.g_a = xyzz_mul<Fq>(d1, A.r); xyzz_madd<Fq>(A.g_a, pk->alpha_g1);
+    A.g_b = xyzz_mul<Fq2>(d2, A.s); xyzz_madd<Fq2>(A.g_b, pk->beta_g2);
+    A.g_c = xyzz_mul<Fq>(d1, rs_c.v);
+    xyzz_add<Fq>(A.g_c, xyzz_mul<Fq>(al, A.s));
+    xyzz_add<Fq>(A.g_c, xyzz_mul<Fq>(be1, A.r));
+    return A;
+}
+static void prove_assemble_post(const AssemblePre& A, const Partials& P, uint8_t* proof_out) {
+    G1XYZZ g_a = A.g_a, g_c = A.g_c; G2XYZZ g_b = A.g_b;
     G1XYZZ a_ans = P.g1[2]; xyzz_add<Fq>(a_ans, P.g1[3]);
     xyzz_add<Fq>(g_a, a_ans);
-    xyzz_add<Fq>(g_c, xyzz_mul<Fq>(a_ans, s));
+    xyzz_add<Fq>(g_c, xyzz_mul<Fq>(a_ans, A.s));
     G1XYZZ b1_ans = P.g1[4]; xyzz_add<Fq>(b1_ans, P.g1[5]);
     G2XYZZ b2_ans = P.g2[0]; xyzz_add<Fq2>(b2_ans, P.g2[1]);
     xyzz_add<Fq2>(g_b, b2_ans);
-    xyzz_add<Fq>(g_c, xyzz_mul<Fq>(b1_ans, r));
+    xyzz_add<Fq>(g_c, xyzz_mul<Fq>(b1_ans, A.r));
     xyzz_add<Fq>(g_c, P.g1[0]);
     xyzz_add<Fq>(g_c, P.g1[1]);
     g1_to_le(xyzz_to_affine<Fq>(g_a), proof_out);
     g2_to_le(xyzz_to_affine<Fq2>(g_b), proof_out + 64);
     g1_to_le(xyzz_to_affine<Fq>(g_c), proof_out + 192);
+}
+static void prove_assemble(const Pk* pk, const Partials& P, const uint8_t* r_le, const uint8_t* s_le, uint8_t* proof_out) {
+    prove_assemble_post(prove_assemble_pre(pk, r_le, s_le), P, proof_out);
+}
+static void prove_msms(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* d_wit, const Fr* d_h, int rank, int world, Partials& out) {
+    prove_msms_enqueue(ctx, pk, c, d_wit, d_h, rank, world);
+    prove_msms_collect(ctx, out);
 }
 
 // whole proof on one GPU, witness already on the device
@@ -565,8 +583,10 @@ static void create_proof_device(Ctx* ctx, const Pk* pk, const Circuit* c, const 
         if (memcmp(check, proof_out, 256) != 0) throw ZaError(ZA_ERR_INVALID, "internal: fused and separate multiexp paths disagree");
         return;
     }
-    prove_msms(ctx, pk, c, d_wit, h.as<Fr>(), 0, 1, P);
-    prove_assemble(pk, P, r_le, s_le, proof_out);
+    prove_msms_enqueue(ctx, pk, c, d_wit, h.as<Fr>(), 0, 1);
+    AssemblePre pre = prove_assemble_pre(pk, r_le, s_le);      // host work under the GPU's multiexps
+    prove_msms_collect(ctx, P);
+    prove_assemble_post(pre, P, proof_out);
 }
 
 static void create_proof(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* inputs, const uint8_t* aux, const uint8_t* r_le,
