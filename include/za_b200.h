@@ -190,6 +190,18 @@ int za_pk_synthetic(za_ctx *ctx, const uint32_t *counts, za_pk **out);
 /* Measured 32-bit integer multiply-add throughput of the device (dependency-free mad.lo.u32 on all SMs). */
 int za_imad_peak(za_ctx *ctx, double *imads_per_second);
 
+/* ---- verification (host side, no GPU needed) ------------------------------------------------------------
+ * Replaces bellman prepare_verifying_key + verify_proof (prover.rs:191-200, helper.rs:153-158).
+ * vk: the za_pk_vk layout (576 + 64 * n_ic bytes).  *valid = 1 / 0.  A wrong number of public inputs is
+ * ZA_ERR_INVALID (bellman: SynthesisError::MalformedVerifyingKey). */
+int za_verify_proof(const uint8_t *vk, size_t n_ic, const uint8_t *proof, const uint8_t *public_inputs,
+                    size_t n_public, int *valid);
+/* JsonVerifyingKey (format.rs:130-167): alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2, gamma_g2, ic, input_names */
+int za_vk_to_json(const uint8_t *vk, size_t n_ic, const char *const *input_names, size_t n_names, char *buf,
+                  size_t size);
+/* helper::verify (helper.rs:149-158): vk JSON + proof-with-inputs JSON -> *valid */
+int za_verify_json(const char *vk_json, const char *proof_json, int *valid);
+
 /* JsonProofAndInput (format.rs:80-128): compact JSON, "0x"+64 hex coordinates, decimal public inputs.
  * public_inputs: n canonical scalars. Returns ZA_ERR_BUFFER_TOO_SMALL if len >= size (binding/c lib.rs:23). */
 int za_proof_to_json(const uint8_t *proof, const uint8_t *public_inputs, size_t n_public, char *buf, size_t size);

@@ -249,3 +249,91 @@ def test_pk_load_rejects_bad_streams(ctx):
     with pytest.raises(za_b200.ZaError) as e:
         za_b200.Parameters.read(ctx, bytes(bad))
     assert e.value.code == -8
+
+
+def test_product_verifier_accepts_gpu_proof(ctx):
+    """generate_verified_proof's self-check (prover.rs:191-200) with the product's own verifier and vk export."""
+    import za_b200
+    ni, na, ptr, var, coeff, inputs, aux = circuits.mul_chain(50, x0=11)
+    ocs = O.CS(ni, na, ptr, var, coeff)
+    prm = O.Params.generate(ocs, [21, 22, 23, 24, 25], threads=8)
+    pk = za_b200.Parameters.read(ctx, prm.write())
+    circ = za_b200.Circuit(ctx, ni, na, ptr, var, coeff)
+    proof = za_b200.create_proof(ctx, pk, circ, inputs, aux, 1001, 1002)
+    out = O.fr_int(inputs[1])
+    vk = pk.vk()
+    assert za_b200.verify_proof(vk, proof, [out]) is True
+    assert za_b200.verify_proof(vk, proof, [out + 1]) is False
+    assert za_b200.verify(za_b200.vk_to_json(vk, ["main.out"]), za_b200.proof_to_json(proof, [out])) is True
+
+
+def test_synthetic_pk_proof_has_the_closed_form(ctx):
+    """Size-independent property used at full size by bench.py: with a synthetic proving key (every base a known
+    multiple of the generator) each proof element is (closed-form scalar) * G.  Checked here at 2^16 with the
+    oracle's H coefficients; bench.py checks the 2^20 proof against the oracle's proof."""
+    import za_b200
+    from za_b200 import synthetic
+    log_m = 16
+    nc = (1 << log_m) - 2
+    ni, na, ptr, var, coeff, inputs, aux = synthetic.mul_chain(nc, x0=77)
+    cnt = synthetic.pk_counts_for_mul_chain(nc)
+    pk = za_b200.Parameters.synthetic(ctx, cnt["ic"], cnt["h"], cnt["l"], cnt["a"], cnt["b_g1"], cnt["b_g2"])
+    circ = za_b200.Circuit(ctx, ni, na, ptr, var, coeff)
+    r, s = 0xABCDEF0123456789, 0x1122334455667788
+    proof, tr = za_b200.create_proof(ctx, pk, circ, inputs, aux, r, s, trace=True)
+    # independent H: the oracle's EvaluationDomain pipeline on the oracle's a, b, c evaluation
+    ocs = O.CS(ni, na, ptr, var, coeff)
+    R = P.R_MOD
+    w_in = O.np_to_frs(inputs); w_aux = O.np_to_frs(aux)
+    a_ev = np.zeros((nc + ni, 32), np.uint8); b_ev = np.zeros_like(a_ev); c_ev = np.zeros_like(a_ev)
+    a_ev[:nc] = aux; b_ev[:nc] = aux                       # A = B = x_k
+    c_ev[:nc - 1] = aux[1:]; c_ev[nc - 1] = inputs[1]      # C = x_{k+1} (last: the public output)
+    a_ev[nc:] = inputs
+    h = O.np_to_frs(O.h_poly(a_ev, b_ev, c_ev, threads=8))
+    assert np.array_equal(tr["h_coeffs"], O.h_poly(a_ev, b_ev, c_ev, threads=8))
+    mult = lambda q, i: ((q + 1) << 32) + i + 1
+    H = sum(mult(0, i) * x for i, x in enumerate(h)) % R
+    L = sum(mult(1, i) * x for i, x in enumerate(w_aux)) % R
+    Aq = sum(mult(2, i) * x for i, x in enumerate(w_in + w_aux)) % R
+    Bq = sum(mult(3, i) * x for i, x in enumerate(w_aux)) % R          # no input occurs in a B row
+    a_s = (11 * r + 3 + Aq) % R
+    b_s = (11 * s + 5 + Bq) % R
+    c_s = (11 * r * s + 3 * s + 5 * r + s * Aq + r * Bq + H + L) % R
+    assert O.g1_tuple(proof[:64]) == O.g1_mul(P.G1_GEN, a_s)
+    assert O.g2_tuple(proof[64:192]) == O.g2_mul(P.G2_GEN, b_s)
+    assert O.g1_tuple(proof[192:]) == O.g1_mul(P.G1_GEN, c_s)
+
+
+def test_generated_bases_are_the_stated_multiples(ctx):
+    import za_b200
+    for group, n, first in ((1, 1000, 1), (1, 70, (1 << 32) + 5), (2, 300, 7)):
+        b = za_b200.Bases.generate(ctx, group, n, first)
+        got = b.download()
+        for i in (0, 1, 31, 32, 33, n - 1):
+            if group == 1:
+                assert O.g1_tuple(got[i]) == O.g1_mul(P.G1_GEN, first + i)
+            else:
+                assert O.g2_tuple(got[i]) == O.g2_mul(P.G2_GEN, first + i)
+
+
+def test_staged_prove_equals_single_call(ctx):
+    """The one-process-per-GPU stages run on one device with world = 1, 2, 3: same proof."""
+    import torch
+    import za_b200
+    ni, na, ptr, var, coeff, inputs, aux = circuits.mul_chain(700, x0=13)
+    ocs = O.CS(ni, na, ptr, var, coeff)
+    prm = O.Params.generate(ocs, [31, 32, 33, 34, 35], threads=8)
+    pk = za_b200.Parameters.read(ctx, prm.write())
+    circ = za_b200.Circuit(ctx, ni, na, ptr, var, coeff)
+    ref = za_b200.create_proof(ctx, pk, circ, inputs, aux, 5, 6)
+    rc, exp = prm.create_proof(ocs, inputs, aux, 5, 6, threads=8)
+    assert rc == 0 and ref == exp
+    wit = torch.from_numpy(np.concatenate([inputs, aux])).cuda()
+    m = 1 << circ.info()["log_m"]
+    h = torch.zeros((m, 32), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    assert za_b200.create_proof_device(ctx, pk, circ, wit.data_ptr(), 5, 6) == ref
+    za_b200.prove_h_device(ctx, circ, wit.data_ptr(), h.data_ptr())
+    for world in (1, 2, 3):
+        parts = [za_b200.prove_msm_partials(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), k, world) for k in range(world)]
+        assert za_b200.prove_assemble(pk, np.stack(parts), 5, 6) == ref

@@ -1,0 +1,95 @@
+"""CPU: the product's host-side verifier and JSON formats (no GPU needed) against the committed golden proof
+(closed form, python integers) and against the oracle's prover / verifier."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import za_b200
+from tests import oracle as O
+from tests import pyref as P
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def vk_from_params_bytes(blob):
+    """bellman VerifyingKey::write layout (big-endian, G2 as c1 || c0) -> the za_pk_vk interchange layout."""
+    def g1(b): return b[31::-1] + b[63:31:-1]
+    def g2(b): return b[63:31:-1] + b[31::-1] + b[127:95:-1] + b[95:63:-1]
+    o = 0
+    alpha = g1(blob[o:o + 64]); o += 64
+    beta1 = g1(blob[o:o + 64]); o += 64
+    beta2 = g2(blob[o:o + 128]); o += 128
+    gamma = g2(blob[o:o + 128]); o += 128
+    delta1 = g1(blob[o:o + 64]); o += 64
+    delta2 = g2(blob[o:o + 128]); o += 128
+    n = int.from_bytes(blob[o:o + 4], "big"); o += 4
+    ic = [g1(blob[o + 64 * i:o + 64 * i + 64]) for i in range(n)]
+    return dict(alpha_g1=alpha, beta_g1=beta1, beta_g2=beta2, gamma_g2=gamma, delta_g1=delta1, delta_g2=delta2, ic=ic)
+
+
+def golden():
+    return json.load(open(os.path.join(G, "groth16_example.json")))
+
+
+def test_golden_proof_verifies_and_wrong_input_fails():
+    g = golden()
+    vk = {k: bytes.fromhex(v) for k, v in g["vk"].items() if k != "ic"}
+    vk["ic"] = [bytes.fromhex(x) for x in g["vk"]["ic"]]
+    proof = bytes.fromhex(g["proof_hex"])
+    assert za_b200.verify_proof(vk, proof, [6]) is True            # prover.rs:294-298
+    assert za_b200.verify_proof(vk, proof, [7]) is False           # prover.rs:300-305
+    with pytest.raises(za_b200.ZaError):                           # MalformedVerifyingKey
+        za_b200.verify_proof(vk, proof, [])
+    bad = bytearray(proof); bad[0] ^= 1
+    with pytest.raises(za_b200.ZaError):                           # point off the curve: "bad coordinates"
+        za_b200.verify_proof(vk, bytes(bad), [6])
+
+
+def test_json_round_trip_like_helper_verify():
+    g = golden()
+    vk = {k: bytes.fromhex(v) for k, v in g["vk"].items() if k != "ic"}
+    vk["ic"] = [bytes.fromhex(x) for x in g["vk"]["ic"]]
+    vk_json = za_b200.vk_to_json(vk, ["main.r"])
+    d = json.loads(vk_json)
+    assert list(d) == ["alpha_g1", "beta_g1", "beta_g2", "delta_g1", "delta_g2", "gamma_g2", "ic", "input_names"]   # format.rs:131-140
+    assert d["input_names"] == ["main.r"] and len(d["ic"]) == 2 and " " not in vk_json
+    assert d["alpha_g1"][0] == "0x" + vk["alpha_g1"][31::-1].hex()
+    assert za_b200.verify(vk_json, g["proof_json"]) is True         # helper.rs:149-158
+    tampered = json.loads(g["proof_json"]); tampered["public_inputs"] = ["7"]
+    assert za_b200.verify(vk_json, json.dumps(tampered)) is False
+    # decimal coordinates are accepted too (str_to_fq goes through FS::parse, format.rs:33-36)
+    dec = json.loads(g["proof_json"]); dec["a"] = [str(int(x, 16)) for x in dec["a"]]
+    assert za_b200.verify(vk_json, json.dumps(dec)) is True
+    for broken in ('{"a":1}', "[1,2", '{"a":["0x1","0x2"],"b":[],"c":[],"public_inputs":[]}'):
+        with pytest.raises(za_b200.ZaError):
+            za_b200.verify(vk_json, broken)
+    lead = json.loads(g["proof_json"]); lead["public_inputs"] = ["06"]      # Fr::from_str rejects leading zeros
+    with pytest.raises(za_b200.ZaError):
+        za_b200.verify(vk_json, json.dumps(lead))
+
+
+def test_agrees_with_oracle_on_random_circuits():
+    from tests import circuits
+    rng = np.random.default_rng(7)
+    for nc in (3, 17):
+        ni, na, ptr, var, coeff, inputs, aux = circuits.mul_chain(nc, x0=int(rng.integers(2, 1000)))
+        ocs = O.CS(ni, na, ptr, var, coeff)
+        prm = O.Params.generate(ocs, [int(x) for x in rng.integers(2, 2 ** 62, 5)])
+        rc, proof = prm.create_proof(ocs, inputs, aux, int(rng.integers(1, 2 ** 62)), int(rng.integers(1, 2 ** 62)))
+        assert rc == 0
+        vk = vk_from_params_bytes(prm.write())
+        out = O.fr_int(inputs[1])
+        assert prm.verify(proof, [out]) == 1 and za_b200.verify_proof(vk, proof, [out]) is True
+        assert prm.verify(proof, [out + 1]) == 0 and za_b200.verify_proof(vk, proof, [out + 1]) is False
+        js = za_b200.proof_to_json(proof, [out])
+        assert za_b200.verify(za_b200.vk_to_json(vk), js) is True
+
+
+def test_pairing_constants_rederived():
+    q, r = P.Q_MOD, P.R_MOD
+    u = 4965661367192848881
+    assert 36 * u ** 4 + 36 * u ** 3 + 24 * u ** 2 + 6 * u + 1 == q and 36 * u ** 4 + 36 * u ** 3 + 18 * u ** 2 + 6 * u + 1 == r
+    assert 6 * u + 2 == (1 << 64) + 0x9d797039be763ba8
+    assert (q ** 12 - 1) % r == 0 and ((q ** 12 - 1) // r) >> (43 * 64) == 0x2f4b6dc970

@@ -81,6 +81,9 @@ SYMBOLS = {
     "za_bases_download": (ci, [vp, vp, sz, sz, vp]),
     "za_pk_synthetic": (ci, [vp, vp, ctypes.POINTER(vp)]),
     "za_imad_peak": (ci, [vp, ctypes.POINTER(ctypes.c_double)]),
+    "za_verify_proof": (ci, [vp, sz, vp, vp, sz, ctypes.POINTER(ci)]),
+    "za_vk_to_json": (ci, [vp, sz, ctypes.POINTER(ctypes.c_char_p), sz, ctypes.c_char_p, sz]),
+    "za_verify_json": (ci, [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ci)]),
     "za_proof_to_json": (ci, [vp, vp, sz, ctypes.c_char_p, sz]),
 }
 

@@ -1,0 +1,349 @@
+// Groth16 verification and the JSON formats around it (host side; a pairing check is a few milliseconds of
+// CPU work and the reference also runs it on the CPU).
+//
+// Replaces bellman_ce groth16/verifier.rs `prepare_verifying_key` + `verify_proof` as called from
+// /root/reference/prover/src/groth16/prover.rs:191-200 (self-verification) and helper.rs:149-158
+// (`helper::verify`), and the serde structs JsonVerifyingKey / JsonProofAndInput of format.rs:80-194.
+//
+// Pairing: textbook optimal ate on BN254 over the tower Fq2 = Fq[u]/(u^2+1), Fq6 = Fq2[v]/(v^3-(9+u)),
+// Fq12 = Fq6[w]/(w^2-v).  G2 points are kept on the twist in affine form; a line through twist
+// points with slope l evaluated at P = (xP, yP) is  yP - l*xP * w + (l*xT - yT) * w^3  (untwist (x,y) ->
+// (x w^2, y w^3)); vertical lines and other Fq6 factors vanish in the final exponentiation, which is a plain
+// square-and-multiply by (q^12-1)/r.  The check is written as one product
+//   e(A,B) * e(acc,-gamma) * e(C,-delta) * e(-alpha,beta) == 1
+// so a single final exponentiation is needed.
+#include "common.cuh"
+#include <string.h>
+#include <string>
+#include <vector>
+
+namespace za {
+
+struct Fq6 { Fq2 a0, a1, a2; };
+struct Fq12 { Fq6 c0, c1; };
+
+static Fq2 mul_xi(const Fq2& a) {            // (a0 + a1 u)(9 + u)
+    Fq t0 = dbl(dbl(dbl(a.c0))) + a.c0, t1 = dbl(dbl(dbl(a.c1))) + a.c1;
+    Fq2 r; r.c0 = t0 - a.c1; r.c1 = t1 + a.c0; return r;
+}
+static Fq6 fq6_zero() { Fq6 z; z.a0 = Fq2::zero(); z.a1 = Fq2::zero(); z.a2 = Fq2::zero(); return z; }
+static Fq6 operator+(const Fq6& a, const Fq6& b) { Fq6 r; r.a0 = a.a0 + b.a0; r.a1 = a.a1 + b.a1; r.a2 = a.a2 + b.a2; return r; }
+static Fq6 operator*(const Fq6& a, const Fq6& b) {
+    // Karatsuba-style: 6 Fq2 products
+    Fq2 v0 = a.a0 * b.a0, v1 = a.a1 * b.a1, v2 = a.a2 * b.a2;
+    Fq6 r;
+    r.a0 = v0 + mul_xi((a.a1 + a.a2) * (b.a1 + b.a2) - v1 - v2);
+    r.a1 = (a.a0 + a.a1) * (b.a0 + b.a1) - v0 - v1 + mul_xi(v2);
+    r.a2 = (a.a0 + a.a2) * (b.a0 + b.a2) - v0 - v2 + v1;
+    return r;
+}
+static Fq6 mul_v(const Fq6& a) { Fq6 r; r.a0 = mul_xi(a.a2); r.a1 = a.a0; r.a2 = a.a1; return r; }
+static Fq12 fq12_one() { Fq12 r; r.c0 = fq6_zero(); r.c1 = fq6_zero(); r.c0.a0 = Fq2::one(); return r; }
+static Fq12 operator*(const Fq12& a, const Fq12& b) {
+    Fq6 v0 = a.c0 * b.c0, v1 = a.c1 * b.c1;
+    Fq12 r;
+    r.c1 = (a.c0 + a.c1) * (b.c0 + b.c1);
+    // c1 = (a0+a1)(b0+b1) - v0 - v1 ; subtraction via explicit components
+    r.c1.a0 = r.c1.a0 - v0.a0 - v1.a0; r.c1.a1 = r.c1.a1 - v0.a1 - v1.a1; r.c1.a2 = r.c1.a2 - v0.a2 - v1.a2;
+    r.c0 = v0 + mul_v(v1);
+    return r;
+}
+static bool fq12_is_one(const Fq12& a) {
+    Fq12 o = fq12_one();
+    return memcmp(&a, &o, sizeof(Fq12)) == 0;
+}
+
+static Fq2 fq2_pow(const Fq2& a, const uint64_t* e, int nlimbs) {
+    Fq2 r = Fq2::one();
+    for (int i = nlimbs * 64 - 1; i >= 0; i--) {
+        r = sqr(r);
+        if ((e[i >> 6] >> (i & 63)) & 1) r = r * a;
+    }
+    return r;
+}
+
+// (q^12 - 1) / r and the Frobenius exponents, computed with python integers from q and r (tests re-derive them)
+static const uint64_t FINAL_EXP[44] = {0x86964b64ca86f120ULL, 0x40a4efb7e54523a4ULL, 0x837fa97896e84abbULL, 0x361102b6b9b2b918ULL, 0xc0de81def35692daULL, 0xbe04c7e8a6c3c760ULL, 0xd766f9c9d570bb7fULL, 0xc230974d83561841ULL, 0x5bba1668c3be69a3ULL, 0x7f3811c410526294ULL, 0x29baee7ddadda71cULL, 0xbf813b8d145da900ULL, 0x641bbadf423f9a2cULL, 0xa80bb4ea44eacc5eULL, 0xcd65664814fde37cULL, 0x4a0364b9580291d2ULL, 0xee93dfb10826f0ddULL, 0x6b42db8dc5514724ULL, 0xbb10cf430b0f3785ULL, 0x40494e406f804216ULL, 0x55cfe107acf3aafbULL, 0x2088ec80e0ebae87ULL, 0x846a3ed011a337a0ULL, 0x48a45a4a1e3a5195ULL, 0xe5664568dfc50e16ULL, 0xab6a41294c0cc4ebULL, 0x82d0d602d268c7daULL, 0x6668449aed3cc48aULL, 0x5062cd0fb2015dfcULL, 0x7f2940a8b1ddb3d1ULL, 0x77f5b63a2a226448ULL, 0xfef0781361e443aeULL, 0xf977870e88d5c6c8ULL, 0x790364a61f676baaULL, 0x5887e72eceaddea3ULL, 0x1377e563a09a1b70ULL, 0x0c54efee1bd8c3b2ULL, 0x3ec3d15ad524d8f7ULL, 0xdaf15466b2383a5dULL, 0xe1e30a73bb94fec0ULL, 0x6a1c71015f3f7be2ULL, 0x842d43bf6369b1ffULL, 0x20fddadf107d20bcULL, 0x0000002f4b6dc970ULL};
+static const uint64_t EXP_QM1_3[4] = {0x69602eb24829a9c2ULL, 0xdd2b2385cd7b4384ULL, 0xe81ac1e7808072c9ULL, 0x10216f7ba065e00dULL};
+static const uint64_t EXP_QM1_2[4] = {0x9e10460b6c3e7ea3ULL, 0xcbc0b548b438e546ULL, 0xdc2822db40c0ac2eULL, 0x183227397098d014ULL};
+static const uint64_t EXP_Q2M1_3[8] = {0x691c1d8b62747890ULL, 0x8cab57b9adf8eb00ULL, 0x18c55d8979dcee49ULL, 0x56cd8a31d35b6b98ULL, 0xb7a4a8c966ece684ULL, 0xe5592c705cbd1cacULL, 0x1dde2529566d9b5eULL, 0x030c96e827699534ULL};
+static const uint64_t EXP_Q2M1_2[8] = {0x9daa2c5113aeb4d8ULL, 0x5301039684f56080ULL, 0x25280c4e36cb656eULL, 0x82344f4abd092164ULL, 0x1376fd2e1a6359c6ULL, 0x5805c2a88b1bab03ULL, 0x2ccd37be01a4690eULL, 0x0492e25c3b1e5fceULL};
+static const uint64_t ATE_LOOP_LOW = 0x9d797039be763ba8ULL;      // 6u+2 = 2^64 + this, u = 4965661367192848881
+
+static Fq12 line_at(const Fq2& lam, const G2Affine& T, const Fq& xp, const Fq& yp) {
+    Fq12 l; l.c0 = fq6_zero(); l.c1 = fq6_zero();
+    l.c0.a0.c0 = yp;
+    Fq2 t; t.c0 = lam.c0 * xp; t.c1 = lam.c1 * xp;
+    l.c1.a0 = -t;
+    l.c1.a1 = lam * T.x - T.y;
+    return l;
+}
+// T <- T + S on the twist (affine), returns the line value at P; `dead` marks T = infinity afterwards
+static Fq12 line_step(G2Affine& T, bool& dead, const G2Affine& S, const Fq& xp, const Fq& yp) {
+    if (dead) return fq12_one();
+    Fq2 lam;
+    if (T.x == S.x) {
+        if (T.y != S.y || T.y.is_zero()) { dead = true; return fq12_one(); }     // vertical line
+        Fq2 x2 = sqr(T.x);
+        lam = (dbl(x2) + x2) * inv(dbl(T.y));
+    } else {
+        lam = (S.y - T.y) * inv(S.x - T.x);
+    }
+    Fq12 l = line_at(lam, T, xp, yp);
+    Fq2 x3 = sqr(lam) - T.x - S.x;
+    Fq2 y3 = lam * (T.x - x3) - T.y;
+    T.x = x3; T.y = y3;
+    return l;
+}
+static Fq12 miller_loop(const G1Affine& P, const G2Affine& Q) {
+    Fq12 f = fq12_one();
+    if (P.is_inf() || Q.is_inf()) return f;
+    G2Affine T = Q;
+    bool dead = false;
+    for (int i = 63; i >= 0; i--) {
+        f = f * f;
+        f = f * line_step(T, dead, T, P.x, P.y);
+        if ((ATE_LOOP_LOW >> i) & 1) f = f * line_step(T, dead, Q, P.x, P.y);
+    }
+    Fq2 xi; xi.c0 = fp_from_u64<FqParams>(9); xi.c1 = fp_from_u64<FqParams>(1);
+    static const Fq2 g12 = fq2_pow(xi, EXP_QM1_3, 4), g13 = fq2_pow(xi, EXP_QM1_2, 4);
+    static const Fq2 g22 = fq2_pow(xi, EXP_Q2M1_3, 8), g23 = fq2_pow(xi, EXP_Q2M1_2, 8);
+    auto conj = [](const Fq2& a) { Fq2 r; r.c0 = a.c0; r.c1 = -a.c1; return r; };
+    G2Affine Q1, Q2;
+    Q1.x = conj(Q.x) * g12; Q1.y = conj(Q.y) * g13;          // pi(Q)
+    Q2.x = Q.x * g22; Q2.y = -(Q.y * g23);                   // -pi^2(Q)
+    f = f * line_step(T, dead, Q1, P.x, P.y);
+    f = f * line_step(T, dead, Q2, P.x, P.y);
+    return f;
+}
+static Fq12 final_exponentiation(const Fq12& f) {
+    Fq12 r = fq12_one();
+    bool started = false;
+    for (int i = 44 * 64 - 1; i >= 0; i--) {
+        if (started) r = r * r;
+        if ((FINAL_EXP[i >> 6] >> (i & 63)) & 1) { r = started ? r * f : f; started = true; }
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------ interchange decoding
+static bool all_zero_b(const uint8_t* p, size_t n) { for (size_t i = 0; i < n; i++) if (p[i]) return false; return true; }
+static bool fq_from_le_checked(const uint8_t* p, Fq& out) {
+    Fq c; memcpy(c.v, p, 32);
+    if (!fp_is_canonical<FqParams>(c.v)) return false;
+    out = fp_to_mont<FqParams>(c); return true;
+}
+static Fq g1_b_coeff() { return fp_from_u64<FqParams>(3); }
+static Fq2 g2_b_coeff() {
+    Fq2 xi; xi.c0 = fp_from_u64<FqParams>(9); xi.c1 = fp_from_u64<FqParams>(1);
+    Fq2 three; three.c0 = fp_from_u64<FqParams>(3); three.c1 = Fq::zero();
+    return three * inv(xi);
+}
+static void g1_decode(const uint8_t* p, G1Affine& a, const char* what) {
+    if (all_zero_b(p, 64)) { a = G1Affine::inf(); return; }
+    if (!fq_from_le_checked(p, a.x) || !fq_from_le_checked(p + 32, a.y)) throw ZaError(ZA_ERR_BAD_ENCODING, std::string(what) + ": coordinate not canonical");
+    if (!affine_on_curve<Fq>(a, g1_b_coeff())) throw ZaError(ZA_ERR_NOT_ON_CURVE, std::string(what) + ": bad coordinates (not on the curve)");
+}
+static void g2_decode(const uint8_t* p, G2Affine& a, const char* what) {
+    if (all_zero_b(p, 128)) { a = G2Affine::inf(); return; }
+    if (!fq_from_le_checked(p, a.x.c0) || !fq_from_le_checked(p + 32, a.x.c1) || !fq_from_le_checked(p + 64, a.y.c0) || !fq_from_le_checked(p + 96, a.y.c1))
+        throw ZaError(ZA_ERR_BAD_ENCODING, std::string(what) + ": coordinate not canonical");
+    if (!affine_on_curve<Fq2>(a, g2_b_coeff())) throw ZaError(ZA_ERR_NOT_ON_CURVE, std::string(what) + ": bad coordinates (not on the curve)");
+}
+
+// bellman verify_proof.  vk: alpha_g1 beta_g1 beta_g2 gamma_g2 delta_g1 delta_g2 ic[n_ic] (interchange bytes)
+static bool verify_proof(const uint8_t* vk, size_t n_ic, const uint8_t* proof, const uint8_t* public_inputs, size_t n_public) {
+    if (n_public + 1 != n_ic) throw ZaError(ZA_ERR_INVALID, "verify_proof: malformed verifying key (inputs + 1 != |ic|)");
+    G1Affine alpha, A, C; G2Affine beta, gamma, delta, B;
+    g1_decode(vk, alpha, "alpha_g1"); g2_decode(vk + 128, beta, "beta_g2"); g2_decode(vk + 256, gamma, "gamma_g2");
+    g2_decode(vk + 448, delta, "delta_g2");
+    g1_decode(proof, A, "proof.a"); g2_decode(proof + 64, B, "proof.b"); g1_decode(proof + 192, C, "proof.c");
+    const uint8_t* ic = vk + 576;
+    G1Affine ic0; g1_decode(ic, ic0, "ic[0]");
+    G1XYZZ acc = G1XYZZ::from_affine(ic0);
+    for (size_t i = 0; i < n_public; i++) {
+        uint32_t k[8]; memcpy(k, public_inputs + 32 * i, 32);
+        if (!fp_is_canonical<FrParams>(k)) throw ZaError(ZA_ERR_NOT_CANONICAL, "verify_proof: public input >= r");
+        G1Affine b; g1_decode(ic + 64 * (i + 1), b, "ic");
+        xyzz_add<Fq>(acc, xyzz_mul<Fq>(G1XYZZ::from_affine(b), k));
+    }
+    G1Affine acc_a = xyzz_to_affine<Fq>(acc);
+    auto neg2 = [](G2Affine p) { if (!p.is_inf()) p.y = -p.y; return p; };
+    G1Affine nalpha = alpha; if (!nalpha.is_inf()) nalpha.y = -nalpha.y;
+    Fq12 f = miller_loop(A, B) * miller_loop(acc_a, neg2(gamma)) * miller_loop(C, neg2(delta)) * miller_loop(nalpha, beta);
+    return fq12_is_one(final_exponentiation(f));
+}
+
+// ------------------------------------------------------------------ JSON (the two fixed schemas of format.rs)
+struct JVal {
+    enum Kind { STR, NUM, ARR, OBJ } kind = STR;
+    std::string s;
+    std::vector<JVal> arr;
+    std::vector<std::pair<std::string, JVal>> obj;
+    const JVal* get(const char* key) const { for (auto& kv : obj) if (kv.first == key) return &kv.second; return nullptr; }
+};
+struct JParser {
+    const char* p; const char* end;
+    void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++; }
+    [[noreturn]] void bad(const char* m) { throw ZaError(ZA_ERR_BAD_ENCODING, std::string("json: ") + m); }
+    std::string str() {
+        if (p >= end || *p != '"') bad("expected string");
+        p++;
+        std::string out;
+        while (p < end && *p != '"') {
+            if (*p == '\\') { p++; if (p >= end) bad("bad escape"); char c = *p; out.push_back(c == 'n' ? '\n' : c == 't' ? '\t' : c); p++; }
+            else out.push_back(*p++);
+        }
+        if (p >= end) bad("unterminated string");
+        p++;
+        return out;
+    }
+    JVal val() {
+        ws();
+        if (p >= end) bad("unexpected end");
+        JVal v;
+        if (*p == '"') { v.kind = JVal::STR; v.s = str(); }
+        else if (*p == '[') {
+            v.kind = JVal::ARR; p++; ws();
+            if (p < end && *p == ']') { p++; return v; }
+            for (;;) { v.arr.push_back(val()); ws(); if (p < end && *p == ',') { p++; continue; } if (p < end && *p == ']') { p++; break; } bad("expected , or ]"); }
+        } else if (*p == '{') {
+            v.kind = JVal::OBJ; p++; ws();
+            if (p < end && *p == '}') { p++; return v; }
+            for (;;) {
+                ws(); std::string k = str(); ws();
+                if (p >= end || *p != ':') bad("expected :");
+                p++;
+                JVal x = val();
+                v.obj.emplace_back(k, std::move(x)); ws();
+                if (p < end && *p == ',') { p++; continue; }
+                if (p < end && *p == '}') { p++; break; }
+                bad("expected , or }");
+            }
+        } else if ((*p >= '0' && *p <= '9') || *p == '-') {
+            v.kind = JVal::NUM;
+            while (p < end && ((*p >= '0' && *p <= '9') || *p == '-' || *p == '.' || *p == 'e' || *p == 'E' || *p == '+')) v.s.push_back(*p++);
+        } else bad("unsupported value");
+        return v;
+    }
+};
+// FS::parse (compiler/src/algebra/fs.rs:43-55): "0x" hex or decimal -> 256-bit little-endian; returns false on overflow / junk
+static bool parse_uint256(const std::string& s, uint8_t* out, bool allow_hex) {
+    uint32_t w[8] = {0};
+    auto mul_add = [&](uint32_t mul, uint32_t add) {
+        uint64_t carry = add;
+        for (int i = 0; i < 8; i++) { uint64_t t = (uint64_t)w[i] * mul + carry; w[i] = (uint32_t)t; carry = t >> 32; }
+        return carry == 0;
+    };
+    if (allow_hex && s.size() > 2 && s[0] == '0' && (s[1] == 'x' || s[1] == 'X')) {
+        for (size_t i = 2; i < s.size(); i++) {
+            char c = s[i]; int d = c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1;
+            if (d < 0 || !mul_add(16, (uint32_t)d)) return false;
+        }
+    } else {
+        if (s.empty()) return false;
+        for (char c : s) { if (c < '0' || c > '9' || !mul_add(10, (uint32_t)(c - '0'))) return false; }
+    }
+    memcpy(out, w, 32);
+    return true;
+}
+static void json_fq(const JVal& v, uint8_t* out) {
+    if (v.kind != JVal::STR || !parse_uint256(v.s, out, true)) throw ZaError(ZA_ERR_BAD_ENCODING, "json: bad field element '" + v.s + "'");
+    // str_to_fq (format.rs:33-36) goes through FS (mod r) and Fq::from_str: values must be canonical
+}
+static void json_g1(const JVal* v, uint8_t* out, const char* what) {
+    if (!v || v->kind != JVal::ARR || v->arr.size() != 2) throw ZaError(ZA_ERR_BAD_ENCODING, std::string("json: ") + what + " is not [x, y]");
+    json_fq(v->arr[0], out); json_fq(v->arr[1], out + 32);
+}
+static void json_g2(const JVal* v, uint8_t* out, const char* what) {
+    if (!v || v->kind != JVal::ARR || v->arr.size() != 2 || v->arr[0].arr.size() != 2 || v->arr[1].arr.size() != 2)
+        throw ZaError(ZA_ERR_BAD_ENCODING, std::string("json: ") + what + " is not [[x.c0, x.c1], [y.c0, y.c1]]");
+    json_fq(v->arr[0].arr[0], out); json_fq(v->arr[0].arr[1], out + 32); json_fq(v->arr[1].arr[0], out + 64); json_fq(v->arr[1].arr[1], out + 96);
+}
+static std::string hex_coord(const uint8_t* le) {
+    static const char* d = "0123456789abcdef";
+    std::string s = "\"0x";
+    for (int i = 31; i >= 0; i--) { s.push_back(d[le[i] >> 4]); s.push_back(d[le[i] & 15]); }
+    s.push_back('"');
+    return s;
+}
+static std::string g1_json(const uint8_t* p) { return "[" + hex_coord(p) + "," + hex_coord(p + 32) + "]"; }
+static std::string g2_json(const uint8_t* p) { return "[[" + hex_coord(p) + "," + hex_coord(p + 32) + "],[" + hex_coord(p + 64) + "," + hex_coord(p + 96) + "]]"; }
+
+}  // namespace za
+
+using namespace za;
+
+#define ZA_TRY try {
+#define ZA_CATCH                                                                   \
+    }                                                                              \
+    catch (const ZaError& e) { return fail(e.code, "%s", e.what()); }              \
+    catch (const std::bad_alloc&) { return fail(ZA_ERR_INVALID, "out of host memory"); } \
+    catch (const std::exception& e) { return fail(ZA_ERR_INVALID, "%s", e.what()); }
+
+extern "C" {
+
+int za_verify_proof(const uint8_t* vk, size_t n_ic, const uint8_t* proof, const uint8_t* public_inputs, size_t n_public, int* valid) {
+    if (!vk || !proof || !valid || (n_public && !public_inputs)) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    *valid = verify_proof(vk, n_ic, proof, public_inputs, n_public) ? 1 : 0;
+    return ZA_OK;
+    ZA_CATCH
+}
+
+// JsonVerifyingKey (format.rs:130-167): serde field order alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2, gamma_g2, ic, input_names
+int za_vk_to_json(const uint8_t* vk, size_t n_ic, const char* const* input_names, size_t n_names, char* buf, size_t size) {
+    if (!vk || !buf) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    std::string s = "{\"alpha_g1\":" + g1_json(vk) + ",\"beta_g1\":" + g1_json(vk + 64) + ",\"beta_g2\":" + g2_json(vk + 128) +
+                    ",\"delta_g1\":" + g1_json(vk + 384) + ",\"delta_g2\":" + g2_json(vk + 448) + ",\"gamma_g2\":" + g2_json(vk + 256) + ",\"ic\":[";
+    for (size_t i = 0; i < n_ic; i++) { if (i) s += ","; s += g1_json(vk + 576 + 64 * i); }
+    s += "],\"input_names\":[";
+    for (size_t i = 0; i < n_names; i++) {
+        if (i) s += ",";
+        s += "\"";
+        for (const char* c = input_names[i]; *c; c++) { if (*c == '"' || *c == '\\') s.push_back('\\'); s.push_back(*c); }
+        s += "\"";
+    }
+    s += "]}";
+    if (s.size() >= size) return fail(ZA_ERR_BUFFER_TOO_SMALL, "vk json needs %zu bytes", s.size() + 1);
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return ZA_OK;
+    ZA_CATCH
+}
+
+// helper::verify (helper.rs:149-158): JsonVerifyingKey + JsonProofAndInput -> verify_proof
+int za_verify_json(const char* vk_json, const char* proof_json, int* valid) {
+    if (!vk_json || !proof_json || !valid) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    JParser pv{vk_json, vk_json + strlen(vk_json)};
+    JVal v = pv.val();
+    JParser pp{proof_json, proof_json + strlen(proof_json)};
+    JVal p = pp.val();
+    if (v.kind != JVal::OBJ || p.kind != JVal::OBJ) throw ZaError(ZA_ERR_BAD_ENCODING, "json: expected an object");
+    const JVal* ic = v.get("ic");
+    if (!ic || ic->kind != JVal::ARR) throw ZaError(ZA_ERR_BAD_ENCODING, "json: vk.ic missing");
+    std::vector<uint8_t> vk(576 + 64 * ic->arr.size());
+    json_g1(v.get("alpha_g1"), vk.data(), "alpha_g1"); json_g1(v.get("beta_g1"), vk.data() + 64, "beta_g1");
+    json_g2(v.get("beta_g2"), vk.data() + 128, "beta_g2"); json_g2(v.get("gamma_g2"), vk.data() + 256, "gamma_g2");
+    json_g1(v.get("delta_g1"), vk.data() + 384, "delta_g1"); json_g2(v.get("delta_g2"), vk.data() + 448, "delta_g2");
+    for (size_t i = 0; i < ic->arr.size(); i++) json_g1(&ic->arr[i], vk.data() + 576 + 64 * i, "ic");
+    uint8_t proof[256];
+    json_g1(p.get("a"), proof, "a"); json_g2(p.get("b"), proof + 64, "b"); json_g1(p.get("c"), proof + 192, "c");
+    const JVal* pi = p.get("public_inputs");
+    if (!pi || pi->kind != JVal::ARR) throw ZaError(ZA_ERR_BAD_ENCODING, "json: public_inputs missing");
+    std::vector<uint8_t> inputs(32 * pi->arr.size() + 1);
+    for (size_t i = 0; i < pi->arr.size(); i++) {
+        // Fr::from_str (format.rs:117): decimal only, no leading zeros, < r
+        const JVal& x = pi->arr[i];
+        if (x.kind != JVal::STR || (x.s.size() > 1 && x.s[0] == '0') || !parse_uint256(x.s, inputs.data() + 32 * i, false))
+            throw ZaError(ZA_ERR_BAD_ENCODING, "json: bad format (public input)");
+        uint32_t w[8]; memcpy(w, inputs.data() + 32 * i, 32);
+        if (!fp_is_canonical<FrParams>(w)) throw ZaError(ZA_ERR_BAD_ENCODING, "json: bad format (public input >= r)");
+    }
+    *valid = verify_proof(vk.data(), ic->arr.size(), proof, inputs.data(), pi->arr.size()) ? 1 : 0;
+    return ZA_OK;
+    ZA_CATCH
+}
+
+}  // extern "C"

@@ -367,6 +367,44 @@ def imad_peak(ctx):
     return v.value
 
 
+def vk_bytes(vk):
+    """vk dict (Parameters.vk()) or raw bytes -> (bytes, n_ic) in the za_pk_vk layout."""
+    if isinstance(vk, dict):
+        b = vk["alpha_g1"] + vk["beta_g1"] + vk["beta_g2"] + vk["gamma_g2"] + vk["delta_g1"] + vk["delta_g2"] + b"".join(vk["ic"])
+    else:
+        b = bytes(vk)
+    return b, (len(b) - 576) // 64
+
+
+def verify_proof(vk, proof, public_inputs):
+    """bellman verify_proof(prepare_verifying_key(vk), proof, public_inputs) -> bool (host-side pairing check)."""
+    b, n_ic = vk_bytes(vk)
+    vb = np.frombuffer(b, np.uint8)
+    p = np.frombuffer(bytes(proof), np.uint8)
+    pi = np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in public_inputs), np.uint8) if public_inputs else None
+    ok = ctypes.c_int(0)
+    check(lib().za_verify_proof(_p(vb), n_ic, _p(p), _p(pi), len(public_inputs), ctypes.byref(ok)))
+    return bool(ok.value)
+
+
+def vk_to_json(vk, input_names=()):
+    """JsonVerifyingKey::to_json (format.rs:130-193)."""
+    b, n_ic = vk_bytes(vk)
+    vb = np.frombuffer(b, np.uint8)
+    names = (ctypes.c_char_p * max(len(input_names), 1))(*[n.encode() for n in input_names])
+    size = 4096 + 160 * n_ic + sum(len(n) + 8 for n in input_names)
+    buf = ctypes.create_string_buffer(size)
+    check(lib().za_vk_to_json(_p(vb), n_ic, names, len(input_names), buf, size))
+    return buf.value.decode()
+
+
+def verify(vk_json, proof_json):
+    """helper::verify (helper.rs:149-158): both arguments are JSON text -> bool."""
+    ok = ctypes.c_int(0)
+    check(lib().za_verify_json(vk_json.encode(), proof_json.encode(), ctypes.byref(ok)))
+    return bool(ok.value)
+
+
 def proof_to_json(proof, public_inputs):
     """JsonProofAndInput (format.rs:80-128).  public_inputs: ints (decimal strings in the JSON)."""
     p = np.frombuffer(bytes(proof), np.uint8)
