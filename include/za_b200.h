@@ -182,6 +182,11 @@ int za_prove_assemble(const za_pk *pk, const uint8_t *partials, int world, const
  * multiexp is checkable with one scalar multiplication.  Generated on the GPU. */
 int za_bases_generate(za_ctx *ctx, int group, size_t n, uint64_t first_multiple, za_bases **out);
 int za_bases_download(za_ctx *ctx, const za_bases *bases, size_t offset, size_t n, uint8_t *out);
+/* Build the fixed-base table of a bases array (entry i*W + w = 2^(c w) * P_i; W = ceil(255 / c) copies of the
+ * array): every later multiexp over it uses ONE bucket space for all windows and c up to 20 (13 windows instead
+ * of 16).  Proving-key queries get their table at load.  Returns the window size c (> 0), 0 if no table was
+ * built (fewer than 4096 points, a point at infinity, or more than 24 GiB), or a negative error. */
+int za_bases_precompute(za_ctx *ctx, za_bases *bases);
 /* A proving key of the given query sizes (counts[6] = |ic|, |h|, |l|, |a|, |b_g1|, |b_g2|) whose bases are
  * known multiples of the generators: query q entry i = ((q+1) * 2^32 + i + 1) * G with q = 0..3 for
  * h, l, a, b (b_g1 and b_g2 share multipliers); alpha, beta, gamma, delta = 3, 5, 7, 11; ic[i] = 13 + i.

@@ -337,3 +337,25 @@ def test_staged_prove_equals_single_call(ctx):
     for world in (1, 2, 3):
         parts = [za_b200.prove_msm_partials(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), k, world) for k in range(world)]
         assert za_b200.prove_assemble(pk, np.stack(parts), 5, 6) == ref
+
+
+@pytest.mark.parametrize("group,n", [(1, 5000), (1, 1 << 16), (2, 4096), (2, 20000)])
+def test_multiexp_with_fixed_base_table(ctx, group, n):
+    """The fixed-base table path (one bucket space, 2^(c w) P_i precomputed) against the oracle and against the
+    table-free path, including a sub-range of the query (offset) and witness-like scalars."""
+    import za_b200
+    pts = O.g1_multiples(n) if group == 1 else O.g2_multiples(n)
+    s = O.random_frs(n, 500 + n)
+    plain = za_b200.Bases(ctx, group, pts)
+    tab = za_b200.Bases(ctx, group, pts)
+    c = tab.precompute()
+    assert c >= 12
+    rc, exp = O.multiexp("g1" if group == 1 else "g2", pts, s, threads=8)
+    assert rc == 0
+    assert za_b200.multiexp(ctx, tab, s) == exp == za_b200.multiexp(ctx, plain, s)
+    off, cnt = 1234, n - 2000
+    rc, exp2 = O.multiexp("g1" if group == 1 else "g2", pts[off:off + cnt], s[:cnt], threads=8)
+    assert za_b200.multiexp(ctx, tab, s[:cnt], offset=off) == exp2
+    w = circuits.witness_like(n, 9)
+    rc, exp3 = O.multiexp("g1" if group == 1 else "g2", pts, w, threads=8)
+    assert za_b200.multiexp(ctx, tab, w) == exp3

@@ -79,6 +79,7 @@ SYMBOLS = {
     "za_prove_assemble": (ci, [vp, vp, ci, vp, vp, vp]),
     "za_bases_generate": (ci, [vp, ci, sz, ctypes.c_uint64, ctypes.POINTER(vp)]),
     "za_bases_download": (ci, [vp, vp, sz, sz, vp]),
+    "za_bases_precompute": (ci, [vp, vp]),
     "za_pk_synthetic": (ci, [vp, vp, ctypes.POINTER(vp)]),
     "za_imad_peak": (ci, [vp, ctypes.POINTER(ctypes.c_double)]),
     "za_verify_proof": (ci, [vp, sz, vp, vp, sz, ctypes.POINTER(ci)]),

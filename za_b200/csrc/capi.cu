@@ -26,6 +26,7 @@ Ctx::~Ctx() {
         if (sl.host_win) cudaFreeHost(sl.host_win);
         if (sl.acc_done) cudaEventDestroy(sl.acc_done);
         if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.side) cudaStreamDestroy(sl.side);
     }
     if (side) cudaStreamDestroy(side);
     if (own_stream && stream) cudaStreamDestroy(stream);

@@ -80,6 +80,8 @@ struct MsmSlot {
     void* host_win = nullptr;            // pinned: window sums (+ entry count when profiling)
     size_t host_win_bytes = 0;
     cudaEvent_t acc_done = nullptr, done = nullptr;
+    cudaStream_t side = nullptr;         // this slot's reduction stream (high priority, so it is not starved by accumulations)
+    cudaEvent_t dbg_start = nullptr, dbg_acc = nullptr, dbg_done = nullptr;   // ZA_DEBUG_TIMELINE only
     bool busy = false;                   // enqueued, not yet finished
     bool done_valid = false;             // `done` has been recorded at least once
     uint32_t sort_users = 0;             // slots that reuse this slot's digit sort since its last enqueue

@@ -70,7 +70,8 @@ static __device__ __forceinline__ int next_digit(const uint32_t* s, int w, int c
 }
 
 // K3 + K4a: per-bucket entry counts
-__global__ void msm_digits_hist_kernel(const uint32_t* __restrict__ scalars, size_t n, int c, int W, uint32_t B, uint32_t* counts) {
+// `single` != 0: fixed-base table mode — one bucket space for all windows, entry = (i * W + w) | sign.
+__global__ void msm_digits_hist_kernel(const uint32_t* __restrict__ scalars, size_t n, int c, int W, uint32_t B, uint32_t* counts, int single) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -81,14 +82,14 @@ __global__ void msm_digits_hist_kernel(const uint32_t* __restrict__ scalars, siz
     uint32_t carry = 0;
     for (int w = 0; w < W; w++) {
         int d = next_digit(s, w, c, carry);
-        if (d != 0) atomicAdd(&counts[(uint32_t)w * B + (uint32_t)(d < 0 ? -d : d) - 1], 1u);
+        if (d != 0) atomicAdd(&counts[(single ? 0u : (uint32_t)w * B) + (uint32_t)(d < 0 ? -d : d) - 1], 1u);
     }
 }
 
 // K4c: scatter (point index | sign << 31) into bucket order.  Order inside a bucket is arbitrary;
 // the bucket sum is not (group addition is commutative and exact).
 __global__ void msm_digits_scatter_kernel(const uint32_t* __restrict__ scalars, size_t n, int c, int W, uint32_t B, uint32_t* cursors,
-                                          uint32_t* entries) {
+                                          uint32_t* entries, int single) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -100,8 +101,8 @@ __global__ void msm_digits_scatter_kernel(const uint32_t* __restrict__ scalars, 
     for (int w = 0; w < W; w++) {
         int d = next_digit(s, w, c, carry);
         if (d != 0) {
-            uint32_t pos = atomicAdd(&cursors[(uint32_t)w * B + (uint32_t)(d < 0 ? -d : d) - 1], 1u);
-            entries[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+            uint32_t pos = atomicAdd(&cursors[(single ? 0u : (uint32_t)w * B) + (uint32_t)(d < 0 ? -d : d) - 1], 1u);
+            entries[pos] = (single ? (uint32_t)i * (uint32_t)W + (uint32_t)w : (uint32_t)i) | (d < 0 ? 0x80000000u : 0u);
         }
     }
 }
@@ -429,17 +430,32 @@ __global__ void __launch_bounds__(128) bases_gen_normalise_kernel(const XYZZ<F>*
     for (int j = 0; j < cnt; j++) {
         XYZZ<F> p = ld_vec(in + start + j);
         pre[j] = run;
-        run = run * (p.ZZ * p.ZZZ);
+        if (!p.is_inf()) run = run * (p.ZZ * p.ZZZ);
     }
     F iv = inv(run);
     for (int j = cnt - 1; j >= 0; j--) {
         XYZZ<F> p = ld_vec(in + start + j);
+        if (p.is_inf()) { st_vec(out + start + j, Affine<F>::inf()); continue; }
         F tj = iv * pre[j];               // 1 / (ZZ_j ZZZ_j)
         iv = iv * (p.ZZ * p.ZZZ);
         Affine<F> a;
         a.x = p.X * (tj * p.ZZZ);
         a.y = p.Y * (tj * p.ZZ);
         st_vec(out + start + j, a);
+    }
+}
+
+// Fixed-base table (Groth16 queries never change): out[i*W + w] = 2^(c w) * P_i, so that all windows of a
+// multiexp share ONE bucket space and the window size can grow (c = 20: 13 windows instead of 16).
+template <class F>
+__global__ void __launch_bounds__(128) bases_table_kernel(const Affine<F>* __restrict__ pts, size_t n, int c, int W, XYZZ<F>* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> a = ldg_vec(pts + i);
+    XYZZ<F> P = XYZZ<F>::from_affine(a);
+    for (int w = 0; w < W; w++) {
+        st_vec(out + i * (size_t)W + w, P);
+        if (w + 1 < W) for (int k = 0; k < c; k++) P = xyzz_dbl<F>(P);
     }
 }
 
@@ -526,9 +542,15 @@ template uint32_t bases_import<Fq2>(Ctx*, void*, size_t);
 // share_sort >= 0: reuse the digit sort of that slot (same scalar vector, e.g. the G1 and G2 B queries).
 // msm_finish waits for the slot and does the window combination on the host.
 template <class F>
-void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t* d_scalars, size_t n, bool has_infinity, int share_sort) {
+void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t* d_scalars, size_t n, bool has_infinity, int share_sort,
+                 const Affine<F>* d_table, int tab_c, int tab_W) {
     MsmSlot& sl = ctx->slots[slot_id];
-    cudaStream_t st = ctx->stream, side = ctx->side;
+    if (!sl.side) {
+        int lo_prio = 0, hi_prio = 0;
+        ZA_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        ZA_CUDA(cudaStreamCreateWithPriority(&sl.side, cudaStreamNonBlocking, hi_prio));
+    }
+    cudaStream_t st = ctx->stream, side = sl.side;
     if (sl.busy) throw ZaError(ZA_ERR_INVALID, "msm slot enqueued twice without msm_finish");
     sl.kind = 0; sl.n = n;
     if (n == 0) { sl.busy = true; return; }
@@ -541,6 +563,11 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
     if (!sl.done) {
         ZA_CUDA(cudaEventCreateWithFlags(&sl.acc_done, cudaEventDisableTiming));
         ZA_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
+    static const bool timeline = getenv("ZA_DEBUG_TIMELINE") != nullptr;
+    if (timeline) {
+        if (!sl.dbg_start) { cudaEventCreate(&sl.dbg_start); cudaEventCreate(&sl.dbg_acc); cudaEventCreate(&sl.dbg_done); }
+        cudaEventRecord(sl.dbg_start, st);
     }
     const size_t want_host = 64 + 128 * sizeof(XYZZ<Fq2>);     // header (entry count) + up to 128 windows
     if (sl.host_win_bytes < want_host) {
@@ -572,11 +599,15 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
         sl.busy = true;
         return;
     }
-    const int c = msm_window_bits(n);
-    const int W = (255 + c - 1) / c;
+    // d_table != nullptr: fixed-base table of this query range (entry i*W + w = 2^(c w) P_i): one bucket space
+    const bool single = d_table != nullptr;
+    const int c = single ? tab_c : msm_window_bits(n);
+    const int W = single ? tab_W : (255 + c - 1) / c;
     const uint32_t B = 1u << (c - 1);
-    const uint32_t nkeys = (uint32_t)W * B;
+    const int Wr = single ? 1 : W;                  // bucket spaces to reduce
+    const uint32_t nkeys = (uint32_t)Wr * B;
     const uint64_t Emax = (uint64_t)n * W;
+    if (single) d_bases = d_table;
     if (Emax >= 0xffffffffull) throw ZaError(ZA_ERR_INVALID, "multiexp too large for 32-bit entry offsets");
     // chunk length: ~2 chunks per resident thread slot, between 16 and 2048 entries (measured best of 2/4/8 at 2^20)
     uint64_t per_slot = 2;
@@ -586,7 +617,7 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
     if (Lc < 16) Lc = 16;
     if (Lc > 2048) Lc = 2048;
     const uint32_t nchunks = (uint32_t)((Emax + Lc - 1) / Lc);
-    sl.kind = 2; sl.c = c; sl.W = W; sl.nkeys = nkeys; sl.Lc = Lc; sl.nchunks = nchunks;
+    sl.kind = 2; sl.c = c; sl.W = Wr; sl.nkeys = nkeys; sl.Lc = Lc; sl.nchunks = nchunks;
     sl.acc_cat = sizeof(F) == sizeof(Fq) ? PROF_ACC_G1 : PROF_ACC_G2;
 
     const uint32_t nctas = (nkeys + SCAN_PER_CTA - 1) / SCAN_PER_CTA;
@@ -594,7 +625,7 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
     uint32_t* d_entries;
     if (share_sort >= 0) {
         const MsmSlot& src = ctx->slots[share_sort];
-        if (src.kind != 2 || src.n != n || src.c != c) throw ZaError(ZA_ERR_INVALID, "msm sort sharing needs an identical scalar vector");
+        if (src.kind != 2 || src.n != n || src.c != c || src.W != Wr) throw ZaError(ZA_ERR_INVALID, "msm sort sharing needs an identical scalar vector and window layout");
         d_offsets = src.d_offsets;
         d_entries = src.d_entries;
         ctx->slots[share_sort].sort_users |= 1u << slot_id;
@@ -630,26 +661,26 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
     const uint32_t pool_used = pool_len + 1;                         // + the final plain sum T
     const uint32_t pool_stride = (pool_used + 63) / 64 * 64;         // padded with points at infinity
     const uint32_t pool_groups = pool_stride / 64;
-    const size_t lvl_elems = (size_t)W * (B / (B < SEG ? B : SEG) + 1);
-    sl.segs.ensure(((size_t)W * pool_stride + 2 * lvl_elems + (size_t)W * pool_groups + W) * sizeof(XYZZ<F>));
+    const size_t lvl_elems = (size_t)Wr * (B / (B < SEG ? B : SEG) + 1);
+    sl.segs.ensure(((size_t)Wr * pool_stride + 2 * lvl_elems + (size_t)Wr * pool_groups + Wr) * sizeof(XYZZ<F>));
     XYZZ<F>* d_pool = sl.segs.as<XYZZ<F>>();
-    XYZZ<F>* d_lvl[2] = {d_pool + (size_t)W * pool_stride, d_pool + (size_t)W * pool_stride + lvl_elems};
+    XYZZ<F>* d_lvl[2] = {d_pool + (size_t)Wr * pool_stride, d_pool + (size_t)Wr * pool_stride + lvl_elems};
     XYZZ<F>* d_grp = d_lvl[1] + lvl_elems;
-    XYZZ<F>* d_win = d_grp + (size_t)W * pool_groups;
+    XYZZ<F>* d_win = d_grp + (size_t)Wr * pool_groups;
     XYZZ<F>* d_buckets = sl.buckets.as<XYZZ<F>>();
 
     ZA_CUDA(cudaMemsetAsync(d_buckets, 0, (size_t)nkeys * sizeof(XYZZ<F>), st));
     ZA_CUDA(cudaMemsetAsync(d_owner, 0xff, (size_t)nchunks * 4, st));
     ZA_CUDA(cudaMemsetAsync(d_long_count, 0, 4, st));
-    ZA_CUDA(cudaMemsetAsync(d_pool, 0, (size_t)W * pool_stride * sizeof(XYZZ<F>), st));
+    ZA_CUDA(cudaMemsetAsync(d_pool, 0, (size_t)Wr * pool_stride * sizeof(XYZZ<F>), st));
     if (share_sort < 0) {
         ZA_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nkeys * 4, st));
         ProfScope prof(ctx, PROF_MSM_SORT, (double)n);
-        msm_digits_hist_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_counts);
+        msm_digits_hist_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_counts, single ? 1 : 0);
         msm_scan_totals_kernel<<<nctas, 1024, 0, st>>>(d_counts, nkeys, d_cta);
         msm_scan_ctas_kernel<<<1, 1024, 0, st>>>(d_cta, nctas, d_offsets + nkeys);
         msm_scan_apply_kernel<<<nctas, 1024, 0, st>>>(d_counts, nkeys, d_cta, d_offsets, d_cursors);
-        msm_digits_scatter_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_cursors, d_entries);
+        msm_digits_scatter_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_cursors, d_entries, single ? 1 : 0);
         ctx->launches += 5;
     }
     {
@@ -658,6 +689,7 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
         ctx->launches++;
     }
     ZA_CUDA(cudaEventRecord(sl.acc_done, st));
+    if (timeline) cudaEventRecord(sl.dbg_acc, st);
     ZA_CUDA(cudaStreamWaitEvent(side, sl.acc_done, 0));
     {
         ProfScope prof(ctx, PROF_MSM_REDUCE, (double)nkeys, side, true);
@@ -670,7 +702,7 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
         for (const Level& lv : levels) {
             XYZZ<F>* dst = d_lvl[li & 1];
             // acc of level l carries weight SEG^l: every earlier level had the full segment size SEG = 2^4
-            const uint32_t total = (uint32_t)W * lv.n_out;
+            const uint32_t total = (uint32_t)Wr * lv.n_out;
             msm_weighted_level_kernel<F><<<nblk(total, 128), 128, 0, side>>>(src, lv.n_in, lv.s, lv.n_out, total, 4 * li, dst, d_pool, pool_stride,
                                                                              lv.pool_off);
             ctx->launches++;
@@ -678,21 +710,22 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
             li++;
         }
         // the final T (one per window) is the plain sum of all buckets: pool slot pool_len
-        ZA_CUDA(cudaMemcpy2DAsync(d_pool + pool_len, (size_t)pool_stride * sizeof(XYZZ<F>), src, sizeof(XYZZ<F>), sizeof(XYZZ<F>), W,
+        ZA_CUDA(cudaMemcpy2DAsync(d_pool + pool_len, (size_t)pool_stride * sizeof(XYZZ<F>), src, sizeof(XYZZ<F>), sizeof(XYZZ<F>), Wr,
                                   cudaMemcpyDeviceToDevice, side));
-        msm_group_reduce_kernel<F><<<nblk((size_t)W * pool_groups * 32, 128), 128, 0, side>>>(d_pool, 64, (uint32_t)W * pool_groups, d_grp);
-        msm_group_reduce_kernel<F><<<nblk((size_t)W * 32, 128), 128, 0, side>>>(d_grp, pool_groups, (uint32_t)W, d_win);
+        msm_group_reduce_kernel<F><<<nblk((size_t)Wr * pool_groups * 32, 128), 128, 0, side>>>(d_pool, 64, (uint32_t)Wr * pool_groups, d_grp);
+        msm_group_reduce_kernel<F><<<nblk((size_t)Wr * 32, 128), 128, 0, side>>>(d_grp, pool_groups, (uint32_t)Wr, d_win);
         ctx->launches += 2;
     }
     ZA_CUDA(cudaGetLastError());
-    ZA_CUDA(cudaMemcpyAsync((uint8_t*)sl.host_win + 64, d_win, (size_t)W * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, side));
+    ZA_CUDA(cudaMemcpyAsync((uint8_t*)sl.host_win + 64, d_win, (size_t)Wr * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, side));
     if (ctx->profile) ZA_CUDA(cudaMemcpyAsync(sl.host_win, d_offsets + nkeys, 4, cudaMemcpyDeviceToHost, side));
     ZA_CUDA(cudaEventRecord(sl.done, side));
+    if (timeline) cudaEventRecord(sl.dbg_done, side);
     sl.done_valid = true;
     sl.busy = true;
 }
-template void msm_enqueue<Fq>(Ctx*, int, const Affine<Fq>*, const uint32_t*, size_t, bool, int);
-template void msm_enqueue<Fq2>(Ctx*, int, const Affine<Fq2>*, const uint32_t*, size_t, bool, int);
+template void msm_enqueue<Fq>(Ctx*, int, const Affine<Fq>*, const uint32_t*, size_t, bool, int, const Affine<Fq>*, int, int);
+template void msm_enqueue<Fq2>(Ctx*, int, const Affine<Fq2>*, const uint32_t*, size_t, bool, int, const Affine<Fq2>*, int, int);
 
 template <class F>
 XYZZ<F> msm_finish(Ctx* ctx, int slot_id) {
@@ -725,7 +758,7 @@ template XYZZ<Fq2> msm_finish<Fq2>(Ctx*, int);
 // One multiexp, synchronously.  d_scalars: n canonical scalars on device; has_infinity: bases may contain (0,0).
 template <class F>
 XYZZ<F> msm_run(Ctx* ctx, const Affine<F>* d_bases, const uint32_t* d_scalars, size_t n, bool has_infinity) {
-    msm_enqueue<F>(ctx, 0, d_bases, d_scalars, n, has_infinity, -1);
+    msm_enqueue<F>(ctx, 0, d_bases, d_scalars, n, has_infinity, -1, nullptr, 0, 0);
     return msm_finish<F>(ctx, 0);
 }
 template XYZZ<Fq> msm_run<Fq>(Ctx*, const Affine<Fq>*, const uint32_t*, size_t, bool);
@@ -744,6 +777,22 @@ void bases_generate(Ctx* ctx, Affine<F>* d_out, size_t n, uint64_t first, const 
 }
 template void bases_generate<Fq>(Ctx*, Affine<Fq>*, size_t, uint64_t, const Affine<Fq>&);
 template void bases_generate<Fq2>(Ctx*, Affine<Fq2>*, size_t, uint64_t, const Affine<Fq2>&);
+
+// Build the fixed-base table of `n` points: d_table[i*W + w] = 2^(c w) * P_i (affine).
+template <class F>
+void bases_table_build(Ctx* ctx, const Affine<F>* d_pts, size_t n, int c, int W, Affine<F>* d_table) {
+    if (!n) return;
+    const size_t total = n * (size_t)W;
+    DevBuf tmp(total * sizeof(XYZZ<F>));
+    bases_table_kernel<F><<<nblk(n, 128), 128, 0, ctx->stream>>>(d_pts, n, c, W, tmp.as<XYZZ<F>>());
+    size_t threads = (total + GEN_CHUNK - 1) / GEN_CHUNK;
+    bases_gen_normalise_kernel<F><<<nblk(threads, 128), 128, 0, ctx->stream>>>(tmp.as<XYZZ<F>>(), d_table, total);
+    ctx->launches += 2;
+    ZA_CUDA(cudaGetLastError());
+    ZA_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+template void bases_table_build<Fq>(Ctx*, const Affine<Fq>*, size_t, int, int, Affine<Fq>*);
+template void bases_table_build<Fq2>(Ctx*, const Affine<Fq2>*, size_t, int, int, Affine<Fq2>*);
 
 // measured 32-bit multiply-add throughput of the whole chip, in IMAD/s
 double imad_peak(Ctx* ctx) {

@@ -7,7 +7,9 @@
 #include "common.cuh"
 #include "api_internal.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <memory>
+#include <chrono>
 
 namespace za {
 
@@ -55,7 +57,32 @@ struct Bases {
     size_t n;
     bool has_infinity;
     DevBuf pts;           // Affine<Fq> or Affine<Fq2>, Montgomery form
+    // optional fixed-base table: table[i*W + w] = 2^(c w) * pts[i]  (see bases_table_kernel)
+    DevBuf table;
+    int tab_c = 0, tab_W = 0;
 };
+
+// Window size of the fixed-base table: with one bucket space for all windows the bucket count is 2^(c-1)
+// regardless of W, so c grows with log2(n) up to 20 (13 windows).  0 = no table (small or too large).
+static int table_window_bits(size_t n, size_t point_bytes) {
+    if (const char* e = getenv("ZA_MSM_TABLE")) { int v = atoi(e); if (v == 0) return 0; if (v >= 8 && v <= 22) return v; }
+    if (n < 4096) return 0;
+    int lg = 0; while (((size_t)1 << (lg + 1)) <= n) lg++;
+    int c = lg > 20 ? 20 : lg;
+    size_t W = (255 + c - 1) / c;
+    if (n * W * point_bytes > ((size_t)24 << 30)) return 0;     // keep one query's table under 24 GiB
+    return c;
+}
+static void bases_build_table(Ctx* ctx, Bases* b) {
+    const size_t pb = b->group == 1 ? sizeof(G1Affine) : sizeof(G2Affine);
+    const int c = table_window_bits(b->n, pb);
+    if (!c || b->has_infinity) return;
+    const int W = (255 + c - 1) / c;
+    b->table.alloc(b->n * (size_t)W * pb);
+    if (b->group == 1) bases_table_build<Fq>(ctx, b->pts.as<G1Affine>(), b->n, c, W, b->table.as<G1Affine>());
+    else bases_table_build<Fq2>(ctx, b->pts.as<G2Affine>(), b->n, c, W, b->table.as<G2Affine>());
+    b->tab_c = c; b->tab_W = W;
+}
 
 static std::unique_ptr<Bases> bases_from_le(Ctx* ctx, int group, const uint8_t* le, size_t n, bool allow_infinity, const char* what) {
     std::unique_ptr<Bases> b(new Bases());
@@ -100,7 +127,9 @@ template <class F>
 static XYZZ<F> multiexp_dev(Ctx* ctx, const Bases* b, size_t offset, const uint32_t* d_scalars, size_t n) {
     if (offset > b->n || n > b->n - offset)
         throw ZaError(ZA_ERR_IO, "multiexp: the base query is shorter than the exponent vector (bellman: unexpected EOF)");
-    return msm_run<F>(ctx, b->pts.as<Affine<F>>() + offset, d_scalars, n, b->has_infinity);
+    const Affine<F>* table = b->tab_c && n > 64 ? b->table.as<Affine<F>>() + offset * (size_t)b->tab_W : nullptr;
+    msm_enqueue<F>(ctx, 0, b->pts.as<Affine<F>>() + offset, d_scalars, n, b->has_infinity, -1, table, b->tab_c, b->tab_W);
+    return msm_finish<F>(ctx, 0);
 }
 
 // ------------------------------------------------------------------ proving key
@@ -182,6 +211,7 @@ static std::unique_ptr<Bases> read_query(Ctx* ctx, Reader& r, int group, bool ch
     // Parameters::read rejects points at infinity in every query
     std::unique_ptr<Bases> b = bases_from_le(ctx, group, le.data(), n, false, what);
     if (checked && group == 2) g2_subgroup_check(ctx, b.get(), what);
+    bases_build_table(ctx, b.get());
     return b;
 }
 
@@ -453,7 +483,8 @@ template <class F>
 static void multiexp_enqueue(Ctx* ctx, int slot, const Bases* b, size_t offset, const uint32_t* d_scalars, size_t n, int share_sort = -1) {
     if (offset > b->n || n > b->n - offset)
         throw ZaError(ZA_ERR_IO, "multiexp: the base query is shorter than the exponent vector (bellman: unexpected EOF)");
-    msm_enqueue<F>(ctx, slot, b->pts.as<Affine<F>>() + offset, d_scalars, n, b->has_infinity, share_sort);
+    const Affine<F>* table = b->tab_c && n > 64 ? b->table.as<Affine<F>>() + offset * (size_t)b->tab_W : nullptr;
+    msm_enqueue<F>(ctx, slot, b->pts.as<Affine<F>>() + offset, d_scalars, n, b->has_infinity, share_sort, table, b->tab_c, b->tab_W);
 }
 
 static void check_query_lengths(const Pk* pk, const Circuit* c, size_t m) {
@@ -583,10 +614,28 @@ static void create_proof_device(Ctx* ctx, const Pk* pk, const Circuit* c, const 
         if (memcmp(check, proof_out, 256) != 0) throw ZaError(ZA_ERR_INVALID, "internal: fused and separate multiexp paths disagree");
         return;
     }
+    static const bool timeline = getenv("ZA_DEBUG_TIMELINE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+    if (timeline) { cudaStreamSynchronize(ctx->stream); t0 = now(); }
     prove_msms_enqueue(ctx, pk, c, d_wit, h.as<Fr>(), 0, 1);
+    if (timeline) t1 = now();
     AssemblePre pre = prove_assemble_pre(pk, r_le, s_le);      // host work under the GPU's multiexps
+    if (timeline) t2 = now();
     prove_msms_collect(ctx, P);
+    if (timeline) t3 = now();
     prove_assemble_post(pre, P, proof_out);
+    if (timeline) {
+        const int order[5] = {3, 4, 0, 1, 2};
+        cudaEvent_t base = ctx->slots[3].dbg_start;
+        for (int k = 0; k < 5; k++) {
+            MsmSlot& sl = ctx->slots[order[k]];
+            float a = 0, b = 0, d = 0;
+            if (sl.dbg_start && sl.kind == 2) { cudaEventElapsedTime(&a, base, sl.dbg_start); cudaEventElapsedTime(&b, base, sl.dbg_acc); cudaEventElapsedTime(&d, base, sl.dbg_done); }
+            fprintf(stderr, "[za timeline] slot %d: start %.3f  accumulate done %.3f  reduce done %.3f\n", order[k], a, b, d);
+        }
+    }
+    if (timeline) { t4 = now(); fprintf(stderr, "[za timeline] after H: enqueue %.3f ms, host pre %.3f, wait+combine %.3f, host post %.3f\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3); }
 }
 
 static void create_proof(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* inputs, const uint8_t* aux, const uint8_t* r_le,
@@ -791,6 +840,15 @@ int za_bases_generate(za_ctx* ctx, int group, size_t n, uint64_t first_multiple,
     ZA_CATCH
 }
 
+int za_bases_precompute(za_ctx* ctx, za_bases* bases) {
+    if (!ctx || !bases) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    ZA_CUDA(cudaSetDevice(ctx->c.device));
+    if (!bases->b->tab_c) bases_build_table(&ctx->c, bases->b.get());
+    return bases->b->tab_c;
+    ZA_CATCH
+}
+
 int za_bases_download(za_ctx* ctx, const za_bases* bases, size_t offset, size_t n, uint8_t* out) {
     if (!ctx || !bases || !out) return fail(ZA_ERR_INVALID, "NULL argument");
     ZA_TRY
@@ -832,6 +890,7 @@ int za_pk_synthetic(za_ctx* ctx, const uint32_t* counts, za_pk** out) {
         pk->a = bases_generated(c, 1, counts[3], ((uint64_t)3 << 32) + 1);
         pk->b_g1 = bases_generated(c, 1, counts[4], ((uint64_t)4 << 32) + 1);
         pk->b_g2 = bases_generated(c, 2, counts[5], ((uint64_t)4 << 32) + 1);
+        for (Bases* q : {pk->h.get(), pk->l.get(), pk->a.get(), pk->b_g1.get(), pk->b_g2.get()}) bases_build_table(c, q);
     } catch (...) { delete h; throw; }
     *out = h;
     return ZA_OK;

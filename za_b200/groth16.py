@@ -136,6 +136,13 @@ class Bases:
         self.h = h
         return self
 
+    def precompute(self):
+        """Build the fixed-base table (2^(c w) * P_i); returns the window size c, 0 if none was built."""
+        rc = lib().za_bases_precompute(self.ctx.h, self.h)
+        if rc < 0:
+            check(rc)
+        return rc
+
     def download(self, offset=0, n=None):
         n = len(self) - offset if n is None else n
         out = np.zeros((n, 64 if self.group == 1 else 128), np.uint8)
