@@ -69,6 +69,24 @@ static __device__ __forceinline__ int next_digit(const uint32_t* s, int w, int c
     return (int)raw;
 }
 
+// Warp-aggregated atomics: lanes of a warp that hit the same bucket (witness vectors are full of 0/1 scalars, and
+// the top window of a 254-bit scalar has few significant bits) are combined into ONE atomic on that counter —
+// same-address atomics serialise in L2 and used to dominate the sort for such inputs.
+static __device__ __forceinline__ void warp_count_add(uint32_t* counts, uint32_t key) {
+    const unsigned peers = __match_any_sync(__activemask(), key);
+    const unsigned lane = threadIdx.x & 31;
+    if ((unsigned)(__ffs(peers) - 1) == lane) atomicAdd(&counts[key], (uint32_t)__popc(peers));
+}
+static __device__ __forceinline__ uint32_t warp_cursor_take(uint32_t* cursors, uint32_t key) {
+    const unsigned peers = __match_any_sync(__activemask(), key);
+    const unsigned lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((unsigned)leader == lane) base = atomicAdd(&cursors[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + (uint32_t)__popc(peers & ((1u << lane) - 1));
+}
+
 // K3 + K4a: per-bucket entry counts
 // `single` != 0: fixed-base table mode — one bucket space for all windows, entry = (i * W + w) | sign.
 __global__ void msm_digits_hist_kernel(const uint32_t* __restrict__ scalars, size_t n, int c, int W, uint32_t B, uint32_t* counts, int single) {
@@ -82,7 +100,7 @@ __global__ void msm_digits_hist_kernel(const uint32_t* __restrict__ scalars, siz
     uint32_t carry = 0;
     for (int w = 0; w < W; w++) {
         int d = next_digit(s, w, c, carry);
-        if (d != 0) atomicAdd(&counts[(single ? 0u : (uint32_t)w * B) + (uint32_t)(d < 0 ? -d : d) - 1], 1u);
+        if (d != 0) warp_count_add(counts, (single ? 0u : (uint32_t)w * B) + (uint32_t)(d < 0 ? -d : d) - 1);
     }
 }
 
@@ -101,7 +119,7 @@ __global__ void msm_digits_scatter_kernel(const uint32_t* __restrict__ scalars, 
     for (int w = 0; w < W; w++) {
         int d = next_digit(s, w, c, carry);
         if (d != 0) {
-            uint32_t pos = atomicAdd(&cursors[(single ? 0u : (uint32_t)w * B) + (uint32_t)(d < 0 ? -d : d) - 1], 1u);
+            uint32_t pos = warp_cursor_take(cursors, (single ? 0u : (uint32_t)w * B) + (uint32_t)(d < 0 ? -d : d) - 1);
             entries[pos] = (single ? (uint32_t)i * (uint32_t)W + (uint32_t)w : (uint32_t)i) | (d < 0 ? 0x80000000u : 0u);
         }
     }

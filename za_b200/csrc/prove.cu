@@ -68,7 +68,8 @@ static int table_window_bits(size_t n, size_t point_bytes) {
     if (const char* e = getenv("ZA_MSM_TABLE")) { int v = atoi(e); if (v == 0) return 0; if (v >= 8 && v <= 22) return v; }
     if (n < 4096) return 0;
     int lg = 0; while (((size_t)1 << (lg + 1)) <= n) lg++;
-    int c = lg > 20 ? 20 : lg;
+    // measured on B200 (scratch/sweep_c.py): 2^16 -> 16, 2^18 -> 17, 2^20 and up -> 20
+    int c = lg >= 20 ? 20 : lg >= 18 ? 17 : lg >= 15 ? 16 : lg + 1;
     size_t W = (255 + c - 1) / c;
     if (n * W * point_bytes > ((size_t)24 << 30)) return 0;     // keep one query's table under 24 GiB
     return c;
