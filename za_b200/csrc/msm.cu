@@ -25,6 +25,13 @@
 #include <string.h>
 #include <stdlib.h>
 
+#ifndef ZA_ACC_G1_BLOCKS
+#define ZA_ACC_G1_BLOCKS 4
+#endif
+#ifndef ZA_ACC_G2_BLOCKS
+#define ZA_ACC_G2_BLOCKS 2
+#endif
+
 namespace za {
 
 // ------------------------------------------------------------------------------ device helpers
@@ -188,7 +195,7 @@ __global__ void __launch_bounds__(1024) msm_scan_apply_kernel(const uint32_t* co
 
 // K5: chunked segmented accumulation.  Thread `chunk` owns entries [chunk*Lc, (chunk+1)*Lc).
 template <class F>
-__global__ void __launch_bounds__(128, (sizeof(F) == sizeof(Fq) ? 4 : 2)) msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ entries,
+__global__ void __launch_bounds__(128, (sizeof(F) == sizeof(Fq) ? ZA_ACC_G1_BLOCKS : ZA_ACC_G2_BLOCKS)) msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ entries,
                                                              const uint32_t* __restrict__ offsets, uint32_t nkeys, uint32_t Lc,
                                                              XYZZ<F>* bucket_sums, XYZZ<F>* part_head, XYZZ<F>* part_tail,
                                                              uint32_t* tail_owner_key) {
@@ -665,7 +672,11 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
     uint32_t* d_long_list = d_owner + nchunks;
     uint32_t* d_long_count = d_long_list + nchunks;
     // weighted bucket reduction: levels of segment size 16 (B is a power of two)
-    const uint32_t SEG = 16;
+    // segment size 2^SEG_LOG: the reduction is latency bound (each level is a chain of 2(s-1) dependent group
+    // additions per thread), so small segments and more levels win: 4 measured best of 4/8/16
+    int SEG_LOG = 2;
+    if (const char* e = getenv("ZA_MSM_SEG_LOG")) { int v = atoi(e); if (v >= 1 && v <= 5) SEG_LOG = v; }
+    const uint32_t SEG = 1u << SEG_LOG;
     struct Level { uint32_t n_in, s, n_out, pool_off; };
     std::vector<Level> levels;
     uint32_t pool_len = 0;
@@ -719,9 +730,9 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
         int li = 0;
         for (const Level& lv : levels) {
             XYZZ<F>* dst = d_lvl[li & 1];
-            // acc of level l carries weight SEG^l: every earlier level had the full segment size SEG = 2^4
+            // acc of level l carries weight SEG^l: every earlier level had the full segment size SEG
             const uint32_t total = (uint32_t)Wr * lv.n_out;
-            msm_weighted_level_kernel<F><<<nblk(total, 128), 128, 0, side>>>(src, lv.n_in, lv.s, lv.n_out, total, 4 * li, dst, d_pool, pool_stride,
+            msm_weighted_level_kernel<F><<<nblk(total, 128), 128, 0, side>>>(src, lv.n_in, lv.s, lv.n_out, total, SEG_LOG * li, dst, d_pool, pool_stride,
                                                                              lv.pool_off);
             ctx->launches++;
             src = dst;
