@@ -268,35 +268,63 @@ def run_gpu(args):
                 "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 256 + 16 * 128 * 5 + 16 * 256},
                 "gpu_launches": int(launches), "clocks": clocks, "imad_peak_timads": imad_peak / 1e12}
 
-    # ---- sub-metrics (rank-local, N = 1 only): 2^log_msm-point G1 MSM and 2^log_ntt Fr NTT, inputs resident
-    if world == 1 and not args.no_sub:
+    # ---- sub-metrics: 2^log_msm-point G1 MSM (point range sharded over the ranks, fixed-base table per shard,
+    #      partial sums combined on the host) and, at N = 1, the 2^log_ntt Fr NTT; inputs resident
+    if not args.no_sub:
         sub = {}
         n_msm = 1 << args.log_msm
-        bases = za_b200.Bases.generate(ctx, 1, n_msm, 1)
-        sc = torch.from_numpy(synthetic.random_scalars(n_msm, 0x5A410005)).to(dev)
+        lo, hi = za_b200.share(n_msm, rank, world)
+        n_loc = hi - lo
+        bases = za_b200.Bases.generate(ctx, 1, n_loc, 1 + lo)
+        tab_c = bases.precompute()
+        sc_all = synthetic.random_scalars(n_msm, 0x5A410005)
+        sc = torch.from_numpy(sc_all[lo:hi].copy()).to(dev)
+        rec = torch.zeros(128, dtype=torch.uint8, device=dev)
+        recs = [torch.zeros_like(rec) for _ in range(world)] if world > 1 else None
         torch.cuda.synchronize()
+
+        def msm_step(d_scalars):
+            if world == 1:
+                return za_b200.multiexp_device(ctx, bases, d_scalars, n_loc)
+            part = za_b200.multiexp_device(ctx, bases, d_scalars, n_loc, partial=True)
+            rec.copy_(torch.from_numpy(np.frombuffer(part, np.uint8).copy()))
+            dist.all_gather(recs, rec)
+            return za_b200.point_sum(1, [r.cpu().numpy().tobytes() for r in recs]) if rank == 0 else None
+
         ctx.profile(True)
         ctx.profile_read()
-        msm_ms, _ = timed(lambda: za_b200.multiexp_device(ctx, bases, sc.data_ptr(), n_msm), max(2, min(K, 5)), 3)
+        msm_ms, msm_pt = timed(lambda: msm_step(sc.data_ptr()), max(2, min(K, 5)), 3)
         p2 = ctx.profile_read()
         ctx.profile(False)
         a = p2["msm_accumulate_g1"]
-        sub["g1_msm"] = {"log_n": args.log_msm, "ms": msm_ms, "mpts_s": n_msm / msm_ms / 1e3, "scalars": "uniform 253-bit",
-                         "accumulate_ms": a["ms"] / max(a["spans"], 1), "sort_ms": p2["msm_sort"]["ms"] / max(a["spans"], 1),
-                         "reduce_ms": p2["msm_reduce"]["ms"] / max(a["spans"], 1),
-                         "imad_frac": (a["work"] * MODMUL_PER_MADD_G1 * IMAD_PER_MODMUL / (a["ms"] * 1e-3)) / za_b200.imad_peak(ctx) if a["ms"] else None}
-        scw = torch.from_numpy(synthetic.witness_like_scalars(n_msm, 0x5A410006)).to(dev)
-        msm_w_ms, _ = timed(lambda: za_b200.multiexp_device(ctx, bases, scw.data_ptr(), n_msm), 2, 3)
-        sub["g1_msm_witness_like"] = {"log_n": args.log_msm, "ms": msm_w_ms, "mpts_s": n_msm / msm_w_ms / 1e3, "scalars": "40% 0, 30% 1, 30% uniform"}
+        ipk = za_b200.imad_peak(ctx)
+        sub["g1_msm"] = {"log_n": args.log_msm, "n_gpus": world, "ms": msm_ms, "mpts_s": n_msm / msm_ms / 1e3, "scalars": "uniform 253-bit",
+                         "fixed_base_table_c": tab_c, "accumulate_ms": a["ms"] / max(a["spans"], 1),
+                         "sort_ms": p2["msm_sort"]["ms"] / max(a["spans"], 1),
+                         "imad_frac": (a["work"] * MODMUL_PER_MADD_G1 * IMAD_PER_MODMUL / (a["ms"] * 1e-3)) / ipk if a["ms"] else None}
+        if rank == 0 and args.log_msm <= 20:
+            # linearity check of the full-size result: bases are (1+i) G, so the sum is (sum s_i (1+i) mod r) G
+            from tests import oracle as O
+            from tests import pyref as P
+            v = sc_all.view(np.uint64).reshape(n_msm, 4)
+            tot = sum(sum(int(x) * (i + 1) for i, x in enumerate(v[:, limb])) << (64 * limb) for limb in range(4)) % P.R_MOD
+            sub["g1_msm"]["matches_closed_form"] = bool(O.g1_tuple(msm_pt) == O.g1_mul(P.G1_GEN, tot))
+        scw = torch.from_numpy(synthetic.witness_like_scalars(n_msm, 0x5A410006)[lo:hi].copy()).to(dev)
+        msm_w_ms, _ = timed(lambda: msm_step(scw.data_ptr()), 2, 3)
+        sub["g1_msm_witness_like"] = {"log_n": args.log_msm, "n_gpus": world, "ms": msm_w_ms, "mpts_s": n_msm / msm_w_ms / 1e3,
+                                      "scalars": "40% 0, 30% 1, 30% uniform"}
         del bases, sc, scw
-        n_ntt = 1 << args.log_ntt
-        v = torch.from_numpy(synthetic.random_scalars(n_ntt, 0x5A410007)).to(dev)
-        torch.cuda.synchronize()
-        ntt_ms, _ = timed(lambda: ctx.ntt_device(v.data_ptr(), args.log_ntt, za_b200.FFT), max(2, min(K, 5)), 3)
-        hbm_peak, _ = peaks()
-        sub["fr_ntt"] = {"log_n": args.log_ntt, "ms": ntt_ms, "gelem_s": n_ntt / ntt_ms / 1e6, "hbm_frac": 64.0 * n_ntt / (ntt_ms * 1e-3) / 1e9 / hbm_peak,
-                         "order": "natural in, natural out, forward"}
-        del v
+        if world == 1:
+            n_ntt = 1 << args.log_ntt
+            v = torch.from_numpy(synthetic.random_scalars(n_ntt, 0x5A410007)).to(dev)
+            torch.cuda.synchronize()
+            ntt_ms, _ = timed(lambda: ctx.ntt_device(v.data_ptr(), args.log_ntt, za_b200.FFT), max(2, min(K, 5)), 3)
+            hbm_peak, _ = peaks()
+            sub["fr_ntt"] = {"log_n": args.log_ntt, "ms": ntt_ms, "gelem_s": n_ntt / ntt_ms / 1e6,
+                             "hbm_frac": 64.0 * n_ntt / (ntt_ms * 1e-3) / 1e9 / hbm_peak,
+                             "imad_frac": IMAD_PER_MODMUL * (n_ntt / 2) * args.log_ntt / (ntt_ms * 1e-3) / ipk,
+                             "order": "natural in, natural out, forward"}
+            del v
         if line is not None:
             line["submetrics"] = sub
 
