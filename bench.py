@@ -149,6 +149,8 @@ def run_gpu(args):
     ni, na, ptr, var, coeff, inputs, aux = cs
     circ = za_b200.Circuit(ctx, ni, na, ptr, var, coeff)
     pk = za_b200.Parameters.synthetic(ctx, counts["ic"], counts["h"], counts["l"], counts["a"], counts["b_g1"], counts["b_g2"])
+    if world > 1:
+        pk.partition(circ, rank, world)
     m = 1 << log_m
     wit_host = torch.from_numpy(np.concatenate([inputs, aux])).pin_memory()
     inputs_pin = torch.from_numpy(inputs.copy()).pin_memory()

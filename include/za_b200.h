@@ -171,6 +171,9 @@ int za_circuit_info(const za_circuit *circuit, uint32_t *info);
  *   partials_out: ZA_PARTIALS_BYTES (6 G1 + 2 G2 XYZZ sums, canonical coordinates).
  * Stage 3, host: add the `world` partial records and assemble the proof (a few group operations). */
 #define ZA_PARTIALS_BYTES 1280
+/* Optional, once per (pk, circuit, rank): rebuild the proving key's fixed-base tables for exactly the point range
+ * this rank owns in every query, with the window size chosen for the share (smaller shares want fewer buckets). */
+int za_pk_partition(za_ctx *ctx, za_pk *pk, const za_circuit *circuit, int rank, int world);
 int za_prove_h_device(za_ctx *ctx, const za_circuit *circuit, const void *d_witness, void *d_h);
 int za_prove_msm_partials(za_ctx *ctx, const za_pk *pk, const za_circuit *circuit, const void *d_witness,
                           const void *d_h, int rank, int world, uint8_t *partials_out);

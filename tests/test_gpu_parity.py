@@ -320,7 +320,7 @@ def test_staged_prove_equals_single_call(ctx):
     """The one-process-per-GPU stages run on one device with world = 1, 2, 3: same proof."""
     import torch
     import za_b200
-    ni, na, ptr, var, coeff, inputs, aux = circuits.mul_chain(700, x0=13)
+    ni, na, ptr, var, coeff, inputs, aux = circuits.mul_chain_fast(9000, x0=13)
     ocs = O.CS(ni, na, ptr, var, coeff)
     prm = O.Params.generate(ocs, [31, 32, 33, 34, 35], threads=8)
     pk = za_b200.Parameters.read(ctx, prm.write())
@@ -337,6 +337,10 @@ def test_staged_prove_equals_single_call(ctx):
     for world in (1, 2, 3):
         parts = [za_b200.prove_msm_partials(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), k, world) for k in range(world)]
         assert za_b200.prove_assemble(pk, np.stack(parts), 5, 6) == ref
+    # per-rank fixed-base tables (za_pk_partition): rank 1 of 2 has tables for its range only; every rank still works
+    pk.partition(circ, 1, 2)
+    parts = [za_b200.prove_msm_partials(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), k, 2) for k in range(2)]
+    assert za_b200.prove_assemble(pk, np.stack(parts), 5, 6) == ref
 
 
 @pytest.mark.parametrize("group,n", [(1, 5000), (1, 1 << 16), (2, 4096), (2, 20000)])

@@ -74,6 +74,7 @@ SYMBOLS = {
     "za_create_proof": (ci, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "za_create_proof_device": (ci, [vp, vp, vp, vp, vp, vp, vp]),
     "za_circuit_info": (ci, [vp, vp]),
+    "za_pk_partition": (ci, [vp, vp, vp, ci, ci]),
     "za_prove_h_device": (ci, [vp, vp, vp, vp]),
     "za_prove_msm_partials": (ci, [vp, vp, vp, vp, vp, ci, ci, vp]),
     "za_prove_assemble": (ci, [vp, vp, ci, vp, vp, vp]),

@@ -273,6 +273,28 @@ ZA_HD void fp_mad_redc(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi)
         O[7] = p_addc(O[7], 0u);
     }
     uint32_t q = p_mul_lo(E[0], P::inv);
+#if defined(ZA_FF_REDC_WIDE)
+    // variant: the m*q products as plain IMAD.WIDE, carries in the ALU.  Measured slower on B200 (11.5 vs
+    // 15.0 T IMAD-class/s in scratch/mb/modmul_bench: the ALU pipe becomes the limit); kept for reference.
+    uint32_t ql[8], qh[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) p_mul_wide(ql[j], qh[j], P::mod(j), q);
+    O[0] = p_add_cc(O[0], ql[1]);
+    O[1] = p_addc_cc(O[1], qh[1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+        O[j] = p_addc_cc(O[j], ql[j + 1]);
+        O[j + 1] = (j == 6) ? p_addc(O[j + 1], qh[j + 1]) : p_addc_cc(O[j + 1], qh[j + 1]);
+    }
+    E[0] = p_add_cc(E[0], ql[0]);
+    E[1] = p_addc_cc(E[1], qh[0]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+        E[j] = p_addc_cc(E[j], ql[j]);
+        E[j + 1] = p_addc_cc(E[j + 1], qh[j]);
+    }
+    O[7] = p_addc(O[7], 0u);
+#else
     O[0] = p_mad_lo_cc(P::mod(1), q, O[0]);
     O[1] = p_madc_hi_cc(P::mod(1), q, O[1]);
 #pragma unroll
@@ -288,6 +310,7 @@ ZA_HD void fp_mad_redc(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi)
         E[j + 1] = p_madc_hi_cc(P::mod(j), q, E[j + 1]);
     }
     O[7] = p_addc(O[7], 0u);
+#endif
 }
 
 template <class P>

@@ -60,6 +60,7 @@ struct Bases {
     // optional fixed-base table: table[i*W + w] = 2^(c w) * pts[i]  (see bases_table_kernel)
     DevBuf table;
     int tab_c = 0, tab_W = 0;
+    size_t tab_lo = 0, tab_n = 0;     // the table covers bases [tab_lo, tab_lo + tab_n)
 };
 
 // Window size of the fixed-base table: with one bucket space for all windows the bucket count is 2^(c-1)
@@ -74,15 +75,23 @@ static int table_window_bits(size_t n, size_t point_bytes) {
     if (n * W * point_bytes > ((size_t)24 << 30)) return 0;     // keep one query's table under 24 GiB
     return c;
 }
-static void bases_build_table(Ctx* ctx, Bases* b) {
+// Build the table for bases [lo, lo + n) (default: the whole array); the window size follows n.
+static void bases_build_table(Ctx* ctx, Bases* b, size_t lo = 0, size_t n = (size_t)-1) {
+    if (n == (size_t)-1) n = b->n - lo;
     const size_t pb = b->group == 1 ? sizeof(G1Affine) : sizeof(G2Affine);
-    const int c = table_window_bits(b->n, pb);
+    b->table.release(); b->tab_c = 0; b->tab_W = 0; b->tab_lo = 0; b->tab_n = 0;
+    const int c = table_window_bits(n, pb);
     if (!c || b->has_infinity) return;
     const int W = (255 + c - 1) / c;
-    b->table.alloc(b->n * (size_t)W * pb);
-    if (b->group == 1) bases_table_build<Fq>(ctx, b->pts.as<G1Affine>(), b->n, c, W, b->table.as<G1Affine>());
-    else bases_table_build<Fq2>(ctx, b->pts.as<G2Affine>(), b->n, c, W, b->table.as<G2Affine>());
-    b->tab_c = c; b->tab_W = W;
+    b->table.alloc(n * (size_t)W * pb);
+    if (b->group == 1) bases_table_build<Fq>(ctx, b->pts.as<G1Affine>() + lo, n, c, W, b->table.as<G1Affine>());
+    else bases_table_build<Fq2>(ctx, b->pts.as<G2Affine>() + lo, n, c, W, b->table.as<G2Affine>());
+    b->tab_c = c; b->tab_W = W; b->tab_lo = lo; b->tab_n = n;
+}
+template <class F>
+static const Affine<F>* table_for(const Bases* b, size_t offset, size_t n) {
+    if (!b->tab_c || n <= 64 || offset < b->tab_lo || offset + n > b->tab_lo + b->tab_n) return nullptr;
+    return b->table.as<Affine<F>>() + (offset - b->tab_lo) * (size_t)b->tab_W;
 }
 
 static std::unique_ptr<Bases> bases_from_le(Ctx* ctx, int group, const uint8_t* le, size_t n, bool allow_infinity, const char* what) {
@@ -128,8 +137,7 @@ template <class F>
 static XYZZ<F> multiexp_dev(Ctx* ctx, const Bases* b, size_t offset, const uint32_t* d_scalars, size_t n) {
     if (offset > b->n || n > b->n - offset)
         throw ZaError(ZA_ERR_IO, "multiexp: the base query is shorter than the exponent vector (bellman: unexpected EOF)");
-    const Affine<F>* table = b->tab_c && n > 64 ? b->table.as<Affine<F>>() + offset * (size_t)b->tab_W : nullptr;
-    msm_enqueue<F>(ctx, 0, b->pts.as<Affine<F>>() + offset, d_scalars, n, b->has_infinity, -1, table, b->tab_c, b->tab_W);
+    msm_enqueue<F>(ctx, 0, b->pts.as<Affine<F>>() + offset, d_scalars, n, b->has_infinity, -1, table_for<F>(b, offset, n), b->tab_c, b->tab_W);
     return msm_finish<F>(ctx, 0);
 }
 
@@ -484,8 +492,7 @@ template <class F>
 static void multiexp_enqueue(Ctx* ctx, int slot, const Bases* b, size_t offset, const uint32_t* d_scalars, size_t n, int share_sort = -1) {
     if (offset > b->n || n > b->n - offset)
         throw ZaError(ZA_ERR_IO, "multiexp: the base query is shorter than the exponent vector (bellman: unexpected EOF)");
-    const Affine<F>* table = b->tab_c && n > 64 ? b->table.as<Affine<F>>() + offset * (size_t)b->tab_W : nullptr;
-    msm_enqueue<F>(ctx, slot, b->pts.as<Affine<F>>() + offset, d_scalars, n, b->has_infinity, share_sort, table, b->tab_c, b->tab_W);
+    msm_enqueue<F>(ctx, slot, b->pts.as<Affine<F>>() + offset, d_scalars, n, b->has_infinity, share_sort, table_for<F>(b, offset, n), b->tab_c, b->tab_W);
 }
 
 static void check_query_lengths(const Pk* pk, const Circuit* c, size_t m) {
@@ -894,6 +901,28 @@ int za_pk_synthetic(za_ctx* ctx, const uint32_t* counts, za_pk** out) {
         for (Bases* q : {pk->h.get(), pk->l.get(), pk->a.get(), pk->b_g1.get(), pk->b_g2.get()}) bases_build_table(c, q);
     } catch (...) { delete h; throw; }
     *out = h;
+    return ZA_OK;
+    ZA_CATCH
+}
+
+// One process per GPU: rebuild the fixed-base tables of `pk` for the point range rank `rank` of `world` owns in
+// every query (the shares za_prove_msm_partials uses), with the window size chosen for the share.
+int za_pk_partition(za_ctx* ctx, za_pk* pk, const za_circuit* circuit, int rank, int world) {
+    if (!ctx || !pk || !circuit) return fail(ZA_ERR_INVALID, "NULL argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(ZA_ERR_INVALID, "bad rank/world");
+    ZA_TRY
+    ZA_CUDA(cudaSetDevice(ctx->c.device));
+    Pk* p = pk->p.get();
+    const Circuit* c = circuit->c.get();
+    const size_t m = domain_size(c, nullptr);
+    check_query_lengths(p, c, m);
+    size_t lo, hi;
+    share(m - 1, rank, world, lo, hi); bases_build_table(&ctx->c, p->h.get(), lo, hi - lo);
+    share(c->na, rank, world, lo, hi); bases_build_table(&ctx->c, p->l.get(), lo, hi - lo);
+    share(c->a_cat_total, rank, world, lo, hi); bases_build_table(&ctx->c, p->a.get(), lo, hi - lo);
+    share(c->b_cat_total, rank, world, lo, hi);
+    bases_build_table(&ctx->c, p->b_g1.get(), lo, hi - lo);
+    bases_build_table(&ctx->c, p->b_g2.get(), lo, hi - lo);
     return ZA_OK;
     ZA_CATCH
 }

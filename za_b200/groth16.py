@@ -212,6 +212,10 @@ class Parameters:
         check(lib().za_pk_synthetic(ctx.h, c, ctypes.byref(hd)))
         return cls(ctx, hd)
 
+    def partition(self, circuit, rank, world):
+        """One process per GPU: keep fixed-base tables only for the point range this rank owns (za_pk_partition)."""
+        check(lib().za_pk_partition(self.ctx.h, self.h, circuit.h, rank, world))
+
     def counts(self):
         c = (ctypes.c_uint32 * 6)()
         check(lib().za_pk_counts(self.h, c))
