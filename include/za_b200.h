@@ -160,6 +160,10 @@ int za_create_proof(za_ctx *ctx, const za_pk *pk, const za_circuit *circuit, con
 /* Same with the witness [inputs | aux] (canonical, (num_inputs+num_aux)*32 bytes) already in device memory. */
 int za_create_proof_device(za_ctx *ctx, const za_pk *pk, const za_circuit *circuit, const void *d_witness,
                            const uint8_t *r, const uint8_t *s, uint8_t *proof_out);
+/* constraints.satisfies_with_signals (constraint.rs:29-67; called before proving at prover.rs:155), on the GPU:
+ * *first_bad = -1 if every row satisfies A(w) * B(w) == C(w), else the smallest failing row. */
+int za_circuit_satisfied(za_ctx *ctx, const za_circuit *circuit, const uint8_t *inputs, const uint8_t *aux,
+                         int64_t *first_bad);
 /* info[7] = num_inputs, num_aux, num_constraints, |a_aux_density|, |b_input_density|, |b_aux_density|, log2(m) */
 int za_circuit_info(const za_circuit *circuit, uint32_t *info);
 
@@ -209,6 +213,26 @@ int za_vk_to_json(const uint8_t *vk, size_t n_ic, const char *const *input_names
                   size_t size);
 /* helper::verify (helper.rs:149-158): vk JSON + proof-with-inputs JSON -> *valid */
 int za_verify_json(const char *vk_json, const char *proof_json, int *valid);
+
+/* ---- proving.key container and circuit synthesis (host side) ---------------------------------------------
+ * read_pk / write_pk of format.rs:223-293: AST blob (opaque), constraints (bincode QEQ), ignored signals,
+ * then bellman's Parameters.  Constraints cross the ABI as three CSR matrices over SIGNAL ids, 32-byte LE
+ * coefficients, za's convention a*b + c = 0.  Two passes: za_pkfile_scan sizes the buffers
+ * (info[6] = num_constraints, num_ignore, nnz_a, nnz_b, nnz_c, max signal id + 1), za_pkfile_read fills them. */
+int za_pkfile_scan(const uint8_t *file, size_t len, uint64_t *info, size_t *params_offset, size_t *ast_offset,
+                   size_t *ast_len);
+int za_pkfile_read(const uint8_t *file, size_t len, uint32_t *const *ptr, uint32_t *const *sig,
+                   uint8_t *const *coeff, uint32_t *ignore);
+int za_pkfile_write(const uint8_t *ast, size_t ast_len, uint32_t num_constraints, const uint32_t *const *ptr,
+                    const uint32_t *const *sig, const uint8_t *const *coeff, const uint32_t *ignore,
+                    uint32_t num_ignore, const uint8_t *params, size_t params_len, uint8_t *out, size_t size,
+                    size_t *out_len);
+/* CircomCircuit::synthesize (prover.rs:45-103) as data: signal -> bellman variable (input if is_public, else aux,
+ * none if ignored; signal 0 = input 0 = one), per-term variables for za_r1cs, and C = -c (prover.rs:98). */
+int za_synthesize(uint32_t n_signals, const uint8_t *is_public, const uint32_t *ignore, uint32_t num_ignore,
+                  uint32_t num_constraints, const uint32_t *const *ptr, const uint32_t *const *sig,
+                  const uint8_t *c_coeff, uint32_t *var_of_signal, uint32_t *const *out_var, uint8_t *out_c_coeff,
+                  uint32_t *num_inputs, uint32_t *num_aux);
 
 /* JsonProofAndInput (format.rs:80-128): compact JSON, "0x"+64 hex coordinates, decimal public inputs.
  * public_inputs: n canonical scalars. Returns ZA_ERR_BUFFER_TOO_SMALL if len >= size (binding/c lib.rs:23). */

@@ -363,3 +363,40 @@ def test_multiexp_with_fixed_base_table(ctx, group, n):
     w = circuits.witness_like(n, 9)
     rc, exp3 = O.multiexp("g1" if group == 1 else "g2", pts, w, threads=8)
     assert za_b200.multiexp(ctx, tab, w) == exp3
+
+
+def test_helper_prove_from_a_proving_key_file(ctx):
+    """helper::prove / generate_verified_proof flow (helper.rs:91-147, prover.rs:139-208) from a proving.key
+    container: read_pk -> synthesize -> constraint check -> proof -> self-verify -> proof.json."""
+    import json, struct
+    import za_b200
+    from za_b200 import format as F, helper
+    from tests.test_format_host import container
+    # za-side circuit: signals one, main.out (public), x0 (private), x1 .. ; constraints x_k * x_k + (-x_{k+1}) = 0
+    nc = 300
+    R = P.R_MOD
+    qeqs = [([(2 + k, 1)], [(2 + k, 1)], [((3 + k) if k + 1 < nc else 1, R - 1)]) for k in range(nc)]
+    n_signals = 2 + nc
+    is_public = [0, 1] + [0] * nc
+    vals = [1, 0] + [0] * nc
+    x = 5
+    for k in range(nc):
+        vals[2 + k] = x; x = x * x % R
+    vals[1] = x
+    values = O.frs_to_np(vals).reshape(n_signals, 32)
+    # proving key made by the oracle's generate_parameters over the synthesized circuit
+    tmp = F.read_pk(container(F.EMPTY_AST, qeqs, [], b""))
+    syn = F.synthesize(n_signals, is_public, [], tmp.ptr, tmp.sig, tmp.coeff, values)
+    ocs = O.CS(syn["num_inputs"], syn["num_aux"], syn["ptr"], syn["var"], syn["coeff"])
+    prm = O.Params.generate(ocs, [41, 42, 43, 44, 45], threads=8)
+    pk_bytes = container(F.EMPTY_AST, qeqs, [], prm.write())
+    key = helper.LoadedKey(ctx, pk_bytes, is_public)
+    js, public = helper.prove(key, values, r=77, s=88)
+    rc, exp = prm.create_proof(ocs, syn["inputs"], syn["aux"], 77, 88, threads=8)
+    assert rc == 0 and js == za_b200.proof_to_json(exp, [x]) and public == [x]
+    assert za_b200.verify(za_b200.vk_to_json(key.params.vk(), ["main.out"]), js) is True
+    js2, _ = helper.prove(key, values)                       # random r, s: different proof, still valid
+    assert js2 != js and za_b200.verify(za_b200.vk_to_json(key.params.vk()), js2) is True
+    bad = values.copy(); bad[5, 0] ^= 1
+    with pytest.raises(ValueError):                          # "check_constrains_eval_zero failed"
+        helper.prove(key, bad)

@@ -73,6 +73,7 @@ SYMBOLS = {
     "za_circuit_free": (None, [vp]),
     "za_create_proof": (ci, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "za_create_proof_device": (ci, [vp, vp, vp, vp, vp, vp, vp]),
+    "za_circuit_satisfied": (ci, [vp, vp, vp, vp, ctypes.POINTER(ctypes.c_int64)]),
     "za_circuit_info": (ci, [vp, vp]),
     "za_pk_partition": (ci, [vp, vp, vp, ci, ci]),
     "za_prove_h_device": (ci, [vp, vp, vp, vp]),
@@ -86,6 +87,10 @@ SYMBOLS = {
     "za_verify_proof": (ci, [vp, sz, vp, vp, sz, ctypes.POINTER(ci)]),
     "za_vk_to_json": (ci, [vp, sz, ctypes.POINTER(ctypes.c_char_p), sz, ctypes.c_char_p, sz]),
     "za_verify_json": (ci, [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ci)]),
+    "za_pkfile_scan": (ci, [vp, sz, vp, vp, vp, vp]),
+    "za_pkfile_read": (ci, [vp, sz, vp, vp, vp, vp]),
+    "za_pkfile_write": (ci, [vp, sz, ctypes.c_uint32, vp, vp, vp, vp, ctypes.c_uint32, vp, sz, vp, sz, vp]),
+    "za_synthesize": (ci, [ctypes.c_uint32, vp, vp, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "za_proof_to_json": (ci, [vp, vp, sz, ctypes.c_char_p, sz]),
 }
 

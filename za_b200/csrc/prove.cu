@@ -324,6 +324,22 @@ __global__ void r1cs_eval_kernel(const uint32_t* __restrict__ ptr, const uint32_
     d[1] = make_uint4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
 }
 
+// constraints.satisfies_with_signals (compiler/src/types/constraint.rs:29-67, called at prover.rs:155): row k holds
+// iff A_k(w) * B_k(w) == C_k(w).  first_bad receives the smallest failing row (atomicMin).
+__global__ void r1cs_check_kernel(const Fr* __restrict__ a, const Fr* __restrict__ b, const Fr* __restrict__ c, uint32_t nrows, uint32_t* first_bad) {
+    uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    Fr x, y, z;
+    const uint4* pa = reinterpret_cast<const uint4*>(a + row);
+    const uint4* pb = reinterpret_cast<const uint4*>(b + row);
+    const uint4* pc = reinterpret_cast<const uint4*>(c + row);
+    uint4 a0 = pa[0], a1 = pa[1], b0 = pb[0], b1 = pb[1], c0 = pc[0], c1 = pc[1];
+    x.v[0] = a0.x; x.v[1] = a0.y; x.v[2] = a0.z; x.v[3] = a0.w; x.v[4] = a1.x; x.v[5] = a1.y; x.v[6] = a1.z; x.v[7] = a1.w;
+    y.v[0] = b0.x; y.v[1] = b0.y; y.v[2] = b0.z; y.v[3] = b0.w; y.v[4] = b1.x; y.v[5] = b1.y; y.v[6] = b1.z; y.v[7] = b1.w;
+    z.v[0] = c0.x; z.v[1] = c0.y; z.v[2] = c0.z; z.v[3] = c0.w; z.v[4] = c1.x; z.v[5] = c1.y; z.v[6] = c1.z; z.v[7] = c1.w;
+    if (x * y != z) atomicMin(first_bad, row);
+}
+
 static std::unique_ptr<Circuit> circuit_upload(Ctx* ctx, const za_r1cs* cs) {
     std::unique_ptr<Circuit> c(new Circuit());
     c->ctx = ctx; c->ni = cs->num_inputs; c->na = cs->num_aux; c->nc = cs->num_constraints;
@@ -923,6 +939,36 @@ int za_pk_partition(za_ctx* ctx, za_pk* pk, const za_circuit* circuit, int rank,
     share(c->b_cat_total, rank, world, lo, hi);
     bases_build_table(&ctx->c, p->b_g1.get(), lo, hi - lo);
     bases_build_table(&ctx->c, p->b_g2.get(), lo, hi - lo);
+    return ZA_OK;
+    ZA_CATCH
+}
+
+int za_circuit_satisfied(za_ctx* ctx, const za_circuit* circuit, const uint8_t* inputs, const uint8_t* aux, int64_t* first_bad) {
+    if (!ctx || !circuit || !inputs || !first_bad) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    Ctx* cx = &ctx->c;
+    const Circuit* c = circuit->c.get();
+    ZA_CUDA(cudaSetDevice(cx->device));
+    cudaStream_t st = cx->stream;
+    const uint32_t ni = c->ni, na = c->na, nc = c->nc;
+    check_scalars_canonical(inputs, ni, "inputs"); check_scalars_canonical(aux, na, "aux");
+    *first_bad = -1;
+    if (!nc) return ZA_OK;
+    DevBuf w(((size_t)ni + na) * 32), abc(3 * (size_t)nc * 32), flag(4);
+    ZA_CUDA(cudaMemcpyAsync(w.p, inputs, (size_t)ni * 32, cudaMemcpyHostToDevice, st));
+    if (na) ZA_CUDA(cudaMemcpyAsync((uint8_t*)w.p + (size_t)ni * 32, aux, (size_t)na * 32, cudaMemcpyHostToDevice, st));
+    fr_convert(cx, w.as<Fr>(), (size_t)ni + na, 0);
+    Fr* outs[3] = {abc.as<Fr>(), abc.as<Fr>() + nc, abc.as<Fr>() + 2 * (size_t)nc};
+    for (int k = 0; k < 3; k++)
+        r1cs_eval_kernel<<<nblk(nc, 128), 128, 0, st>>>(c->ptr[k].as<uint32_t>(), c->col[k].as<uint32_t>(), c->coeff[k].as<Fr>(), w.as<Fr>(), nc, outs[k]);
+    ZA_CUDA(cudaMemsetAsync(flag.p, 0xff, 4, st));
+    r1cs_check_kernel<<<nblk(nc, 128), 128, 0, st>>>(outs[0], outs[1], outs[2], nc, flag.as<uint32_t>());
+    cx->launches += 4;
+    ZA_CUDA(cudaGetLastError());
+    uint32_t h = 0;
+    ZA_CUDA(cudaMemcpyAsync(&h, flag.p, 4, cudaMemcpyDeviceToHost, st));
+    ZA_CUDA(cudaStreamSynchronize(st));
+    if (h != 0xffffffffu) *first_bad = (int64_t)h;
     return ZA_OK;
     ZA_CATCH
 }

@@ -264,6 +264,13 @@ class Circuit:
         check(lib().za_circuit_upload(ctx.h, ctypes.byref(s), ctypes.byref(h)))
         self.h = h
 
+    def first_unsatisfied(self, inputs, aux):
+        """constraints.satisfies_with_signals on the GPU: None if all rows hold, else the first failing row."""
+        inputs, aux = _u8(inputs, 32), _u8(aux, 32)
+        bad = ctypes.c_int64(-1)
+        check(lib().za_circuit_satisfied(self.ctx.h, self.h, _p(inputs), _p(aux), ctypes.byref(bad)))
+        return None if bad.value < 0 else int(bad.value)
+
     def info(self):
         c = (ctypes.c_uint32 * 7)()
         check(lib().za_circuit_info(self.h, c))
