@@ -44,7 +44,8 @@ enum {
     ZA_ERR_NOT_IN_SUBGROUP = -7,
     ZA_ERR_BAD_ENCODING = -8,
     ZA_ERR_BUFFER_TOO_SMALL = -9,
-    ZA_ERR_NOT_CANONICAL = -10        /* a scalar >= r was passed */
+    ZA_ERR_NOT_CANONICAL = -10,       /* a scalar >= r was passed */
+    ZA_ERR_UNCONSTRAINED_VARIABLE = -11 /* SynthesisError::UnconstrainedVariable (setup) */
 };
 
 #define ZA_VAR_AUX 0x80000000u /* constraint term variable: bit 31 set = aux index, else input index */
@@ -233,6 +234,17 @@ int za_synthesize(uint32_t n_signals, const uint8_t *is_public, const uint32_t *
                   uint32_t num_constraints, const uint32_t *const *ptr, const uint32_t *const *sig,
                   const uint8_t *c_coeff, uint32_t *var_of_signal, uint32_t *const *out_var, uint8_t *out_c_coeff,
                   uint32_t *num_inputs, uint32_t *num_aux);
+
+/* ---- trusted setup --------------------------------------------------------------------------------------
+ * Replaces bellman generate_parameters(circuit, g1, g2, alpha, beta, gamma, delta, tau): what
+ * generate_random_parameters (prover.rs:122) computes after drawing those seven values from the RNG.
+ * Scalars: 32-byte LE canonical; g1 / g2: affine interchange encoding.  out receives the byte stream of
+ * bellman's Parameters::write; size it with za_parameters_max_size (the A / B queries shrink when points at
+ * infinity are filtered out; *out_len is the actual length). */
+size_t za_parameters_max_size(const za_circuit *circuit);
+int za_generate_parameters(za_ctx *ctx, const za_circuit *circuit, const uint8_t *alpha, const uint8_t *beta,
+                           const uint8_t *gamma, const uint8_t *delta, const uint8_t *tau, const uint8_t *g1,
+                           const uint8_t *g2, uint8_t *out, size_t size, size_t *out_len);
 
 /* JsonProofAndInput (format.rs:80-128): compact JSON, "0x"+64 hex coordinates, decimal public inputs.
  * public_inputs: n canonical scalars. Returns ZA_ERR_BUFFER_TOO_SMALL if len >= size (binding/c lib.rs:23). */

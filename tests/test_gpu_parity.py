@@ -400,3 +400,78 @@ def test_helper_prove_from_a_proving_key_file(ctx):
     bad = values.copy(); bad[5, 0] ^= 1
     with pytest.raises(ValueError):                          # "check_constrains_eval_zero failed"
         helper.prove(key, bad)
+
+
+# ---------------------------------------------------------------- trusted setup (N2): generate_parameters on the GPU
+def _setup_case(ctx, cs_tuple, toxic, g1=None, g2=None):
+    import za_b200
+    ni, na, ptr, var, coeff = cs_tuple[:5]
+    ocs = O.CS(ni, na, ptr, var, coeff)
+    exp = O.Params.generate(ocs, toxic, g1=g1, g2=g2, threads=8).write()
+    circ = za_b200.Circuit(ctx, ni, na, ptr, var, coeff)
+    kw = {}
+    if g1 is not None: kw["g1"] = g1
+    if g2 is not None: kw["g2"] = g2
+    got = za_b200.generate_parameters(ctx, circ, *toxic, **kw)
+    assert len(got) == len(exp)
+    assert got == exp
+    return got
+
+
+def test_generate_parameters_example_circuit(ctx):
+    """Config 1's setup: the proving key of example/circuit.za, byte for byte bellman's Parameters::write stream."""
+    cs = P.example_factor_circuit()
+    ocs = O.CS.from_rows(cs.num_inputs, cs.num_aux, cs.rows)
+    _setup_case(ctx, (2, 2, ocs.ptr, ocs.var, ocs.coeff), [2, 3, 4, 5, 6])
+
+
+@pytest.mark.parametrize("nc", [1, 6, 100, 1022, (1 << 13) - 2])
+def test_generate_parameters_mul_chain(ctx, nc):
+    _setup_case(ctx, circuits.mul_chain(nc, x0=3), [0x1234567 + nc, 2 ** 200 + 9, 77, P.R_MOD - 2, 2 ** 253 + nc])
+
+
+def test_generate_parameters_random_generators(ctx):
+    """generate_random_parameters (prover.rs:122) draws g1 and g2 as random group elements, not the generators."""
+    g1 = O.g1_bytes(O.g1_mul(P.G1_GEN, 0xDEADBEEF12345))
+    g2 = O.g2_bytes(O.g2_mul(P.G2_GEN, 0xFEEDFACE98765))
+    _setup_case(ctx, circuits.mul_chain(50, x0=11), [9, 8, 7, 6, 5], g1=g1, g2=g2)
+
+
+def test_generate_parameters_filters_infinity_and_flags_unconstrained(ctx):
+    """Variables absent from A (or B) give points at infinity that bellman filters out of a / b_g1 / b_g2; an aux
+    variable absent from all three matrices is SynthesisError::UnconstrainedVariable."""
+    import za_b200
+    A = circuits.AUX
+    # inputs: one, out; aux: x, y, z.   rows: x * y = z ; z * one = out     (y never in A, x never in B, out only in C)
+    rows = [([(1, A | 0)], [(1, A | 1)], [(1, A | 2)]), ([(1, A | 2)], [(1, 0)], [(1, 1)])]      # (coeff, var)
+    ocs = O.CS.from_rows(2, 3, rows)
+    blob = _setup_case(ctx, (2, 3, ocs.ptr, ocs.var, ocs.coeff), [3, 5, 7, 11, 13])
+    pk = za_b200.Parameters.read(ctx, blob, checked=True)
+    cnt = pk.counts()
+    assert cnt["a"] < 5 and cnt["b_g1"] < 5 and cnt["b_g1"] == cnt["b_g2"]
+    # and a proof made with the GPU-generated key verifies
+    inputs = O.frs_to_np([1, 12]).reshape(-1, 32); aux = O.frs_to_np([3, 4, 12]).reshape(-1, 32)
+    circ = za_b200.Circuit(ctx, 2, 3, ocs.ptr, ocs.var, ocs.coeff)
+    proof = za_b200.create_proof(ctx, pk, circ, inputs, aux, 5, 6)
+    assert za_b200.verify_proof(pk.vk(), proof, [12]) is True
+    assert za_b200.verify_proof(pk.vk(), proof, [13]) is False
+    # aux 3 is never used
+    rows2 = rows
+    ocs2 = O.CS.from_rows(2, 4, rows2)
+    circ2 = za_b200.Circuit(ctx, 2, 4, ocs2.ptr, ocs2.var, ocs2.coeff)
+    with pytest.raises(za_b200.ZaError) as e:
+        za_b200.generate_parameters(ctx, circ2, 3, 5, 7, 11, 13)
+    assert e.value.code == -11
+    with pytest.raises(RuntimeError):
+        O.Params.generate(ocs2, [3, 5, 7, 11, 13])
+
+
+def test_generate_parameters_rejects_bad_toxic_values(ctx):
+    import za_b200
+    ni, na, ptr, var, coeff = circuits.mul_chain(6)[:5]
+    circ = za_b200.Circuit(ctx, ni, na, ptr, var, coeff)
+    with pytest.raises(za_b200.ZaError):
+        za_b200.generate_parameters(ctx, circ, 1, 2, 0, 4, 5)          # gamma = 0 has no inverse
+    with pytest.raises(za_b200.ZaError) as e:
+        za_b200.generate_parameters(ctx, circ, P.R_MOD, 2, 3, 4, 5)    # not canonical
+    assert e.value.code == -10

@@ -13,7 +13,7 @@ ZA_OK = 0
 ERR_NAMES = {
     0: "ZA_OK", -1: "ZA_ERR_CUDA", -2: "ZA_ERR_INVALID", -3: "ZA_ERR_UNEXPECTED_IDENTITY",
     -4: "ZA_ERR_POLY_DEGREE_TOO_LARGE", -5: "ZA_ERR_IO", -6: "ZA_ERR_NOT_ON_CURVE", -7: "ZA_ERR_NOT_IN_SUBGROUP",
-    -8: "ZA_ERR_BAD_ENCODING", -9: "ZA_ERR_BUFFER_TOO_SMALL", -10: "ZA_ERR_NOT_CANONICAL",
+    -8: "ZA_ERR_BAD_ENCODING", -9: "ZA_ERR_BUFFER_TOO_SMALL", -10: "ZA_ERR_NOT_CANONICAL", -11: "ZA_ERR_UNCONSTRAINED_VARIABLE",
 }
 
 
@@ -91,6 +91,8 @@ SYMBOLS = {
     "za_pkfile_read": (ci, [vp, sz, vp, vp, vp, vp]),
     "za_pkfile_write": (ci, [vp, sz, ctypes.c_uint32, vp, vp, vp, vp, ctypes.c_uint32, vp, sz, vp, sz, vp]),
     "za_synthesize": (ci, [ctypes.c_uint32, vp, vp, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "za_parameters_max_size": (sz, [vp]),
+    "za_generate_parameters": (ci, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, ctypes.POINTER(sz)]),
     "za_proof_to_json": (ci, [vp, vp, sz, ctypes.c_char_p, sz]),
 }
 

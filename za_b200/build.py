@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libza_b200.so")
-SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "prove.cu", "format.cu", "verify.cu"]
+SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "prove.cu", "format.cu", "verify.cu", "setup.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-O2", "--expt-relaxed-constexpr", "-rdc=false"]
 

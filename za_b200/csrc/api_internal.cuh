@@ -6,6 +6,7 @@ namespace za {
 
 // ntt.cu
 Fr host_domain_omega(int log_n);
+void launch_powers_public(Ctx* ctx, Fr* out, size_t count, const Fr& base, const Fr& first);
 void fr_convert(Ctx* ctx, Fr* d, size_t n, int dir);
 void ntt_mode(Ctx* ctx, Fr* buf, int log_n, int mode, int batch);
 void h_poly_device(Ctx* ctx, Fr* a, Fr* b, Fr* c, int log_m);
@@ -21,6 +22,7 @@ template <class F> XYZZ<F> msm_finish(Ctx* ctx, int slot);
 int msm_window_bits(size_t n);
 template <class F> void bases_generate(Ctx* ctx, Affine<F>* d_out, size_t n, uint64_t first, const Affine<F>& G);
 double imad_peak(Ctx* ctx);
+template <class F> void xyzz_normalise(Ctx* ctx, const XYZZ<F>* d_in, Affine<F>* d_out, size_t n);
 Fq host_g1_b();
 Fq2 host_g2_b();
 

@@ -807,6 +807,18 @@ void bases_generate(Ctx* ctx, Affine<F>* d_out, size_t n, uint64_t first, const 
 template void bases_generate<Fq>(Ctx*, Affine<Fq>*, size_t, uint64_t, const Affine<Fq>&);
 template void bases_generate<Fq2>(Ctx*, Affine<Fq2>*, size_t, uint64_t, const Affine<Fq2>&);
 
+// XYZZ -> affine for n points with shared inversions (points at infinity become (0,0)).
+template <class F>
+void xyzz_normalise(Ctx* ctx, const XYZZ<F>* d_in, Affine<F>* d_out, size_t n) {
+    if (!n) return;
+    size_t threads = (n + GEN_CHUNK - 1) / GEN_CHUNK;
+    bases_gen_normalise_kernel<F><<<nblk(threads, 128), 128, 0, ctx->stream>>>(d_in, d_out, n);
+    ctx->launches++;
+    ZA_CUDA(cudaGetLastError());
+}
+template void xyzz_normalise<Fq>(Ctx*, const XYZZ<Fq>*, Affine<Fq>*, size_t);
+template void xyzz_normalise<Fq2>(Ctx*, const XYZZ<Fq2>*, Affine<Fq2>*, size_t);
+
 // Build the fixed-base table of `n` points: d_table[i*W + w] = 2^(c w) * P_i (affine).
 template <class F>
 void bases_table_build(Ctx* ctx, const Affine<F>* d_pts, size_t n, int c, int W, Affine<F>* d_table) {

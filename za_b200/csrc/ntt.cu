@@ -247,6 +247,8 @@ static void launch_powers(Ctx* ctx, Fr* out, size_t count, const Fr& base, const
     ZA_CUDA(cudaGetLastError());
 }
 
+void launch_powers_public(Ctx* ctx, Fr* out, size_t count, const Fr& base, const Fr& first) { launch_powers(ctx, out, count, base, first); }
+
 NttDomain* get_domain(Ctx* ctx, int log_n, bool need_coset) {
     NttDomain* d;
     auto it = ctx->domains.find(log_n);

@@ -6,6 +6,7 @@
 // (`Parameters::read(pk, true)`) call into.  Step numbers refer to SURVEY.md §3.2.
 #include "common.cuh"
 #include "api_internal.cuh"
+#include "objects.cuh"
 #include <string.h>
 #include <stdlib.h>
 #include <memory>
@@ -49,19 +50,6 @@ static G2XYZZ g2_xyzz_from_le(const uint8_t* p) {
     for (int i = 0; i < 8; i++) c[i] = fq_from_le(p + 32 * i);
     return a;
 }
-
-// ------------------------------------------------------------------ device-resident bases
-struct Bases {
-    Ctx* ctx;
-    int group;            // 1 = G1, 2 = G2
-    size_t n;
-    bool has_infinity;
-    DevBuf pts;           // Affine<Fq> or Affine<Fq2>, Montgomery form
-    // optional fixed-base table: table[i*W + w] = 2^(c w) * pts[i]  (see bases_table_kernel)
-    DevBuf table;
-    int tab_c = 0, tab_W = 0;
-    size_t tab_lo = 0, tab_n = 0;     // the table covers bases [tab_lo, tab_lo + tab_n)
-};
 
 // Window size of the fixed-base table: with one bucket space for all windows the bucket count is 2^(c-1)
 // regardless of W, so c grows with log2(n) up to 20 (13 windows).  0 = no table (small or too large).
@@ -142,15 +130,6 @@ static XYZZ<F> multiexp_dev(Ctx* ctx, const Bases* b, size_t offset, const uint3
 }
 
 // ------------------------------------------------------------------ proving key
-struct Pk {
-    Ctx* ctx;
-    // verifying key, host side, Montgomery form
-    G1Affine alpha_g1, beta_g1, delta_g1;
-    G2Affine beta_g2, gamma_g2, delta_g2;
-    std::vector<G1Affine> ic;
-    std::unique_ptr<Bases> h, l, a, b_g1, b_g2;
-};
-
 static uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 
 // pairing_ce G1Uncompressed/G2Uncompressed: 32-byte big-endian coordinates, bit 7 of byte 0 =
@@ -275,19 +254,6 @@ static std::unique_ptr<Pk> pk_load(Ctx* ctx, const uint8_t* data, size_t len, bo
 // Montgomery form, the three density maps of bellman's ProvingAssignment (they depend on which
 // variables occur in A / B rows, never on the witness: density.inc(i) fires for every term)
 // and the compacted index lists the density-filtered multiexps need (K10).
-struct Circuit {
-    Ctx* ctx;
-    uint32_t ni, na, nc;
-    DevBuf ptr[3], col[3], coeff[3];     // col = slot in the witness vector [inputs | aux]
-    std::vector<uint8_t> a_aux_density, b_in_density, b_aux_density;
-    DevBuf a_aux_idx, b_in_idx, b_aux_idx;
-    uint32_t a_aux_total = 0, b_in_total = 0, b_aux_total = 0;
-    // positions in the witness vector [inputs | aux] of the exponents of the whole A query (all inputs, then
-    // the aux with a_aux_density) and of the whole B query (inputs with b_input_density, then aux with b_aux_density)
-    DevBuf a_cat_idx, b_cat_idx;
-    uint32_t a_cat_total = 0, b_cat_total = 0;
-};
-
 __global__ void circuit_coeff_import_kernel(Fr* c, size_t n, uint32_t* flag) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -368,6 +334,8 @@ static std::unique_ptr<Circuit> circuit_upload(Ctx* ctx, const za_r1cs* cs) {
                 if (w == 1) c->b_in_density[v] = 1;
             }
         }
+        c->h_ptr[w].assign(ptr, ptr + c->nc + 1);
+        c->h_col[w].assign(col.begin(), col.begin() + nt);
         c->ptr[w].alloc(((size_t)c->nc + 1) * 4);
         c->col[w].alloc((size_t)nt * 4);
         c->coeff[w].alloc((size_t)nt * 32);
@@ -704,10 +672,6 @@ static Affine<F> host_multiple(const Affine<F>& g, uint64_t k) {
 }  // namespace za
 
 using namespace za;
-
-struct za_bases { std::unique_ptr<Bases> b; };
-struct za_pk { std::unique_ptr<Pk> p; };
-struct za_circuit { std::unique_ptr<Circuit> c; };
 
 #define ZA_TRY try {
 #define ZA_CATCH                                                                   \

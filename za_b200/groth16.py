@@ -423,6 +423,27 @@ def verify(vk_json, proof_json):
     return bool(ok.value)
 
 
+G1_GENERATOR = (1).to_bytes(32, "little") + (2).to_bytes(32, "little")
+G2_GENERATOR = b"".join(int(x).to_bytes(32, "little") for x in (
+    10857046999023057135944570762232829481370756359578518086990519993285655852781,
+    11559732032986387107991004021392285783925812861821192530917403151452391805634,
+    8495653923123431417604973247489272438418190587263600148770280649306958101930,
+    4082367875863433681332203403145435568316851327593401208105741076214120093531))   # ethereum.rs:28-31
+
+
+def generate_parameters(ctx, circuit, alpha, beta, gamma, delta, tau, g1=G1_GENERATOR, g2=G2_GENERATOR):
+    """bellman generate_parameters with explicit toxic values (generate_random_parameters, prover.rs:122, draws
+    them — and g1, g2 — from the RNG).  Returns the bytes bellman's Parameters::write produces."""
+    size = int(lib().za_parameters_max_size(circuit.h))
+    out = np.zeros(size, np.uint8)
+    n = ctypes.c_size_t(0)
+    sc = [_scalar(x) for x in (alpha, beta, gamma, delta, tau)]
+    b1 = np.frombuffer(bytes(g1), np.uint8)
+    b2 = np.frombuffer(bytes(g2), np.uint8)
+    check(lib().za_generate_parameters(ctx.h, circuit.h, *[_p(x) for x in sc], _p(b1), _p(b2), _p(out), size, ctypes.byref(n)))
+    return out[:n.value].tobytes()
+
+
 def proof_to_json(proof, public_inputs):
     """JsonProofAndInput (format.rs:80-128).  public_inputs: ints (decimal strings in the JSON)."""
     p = np.frombuffer(bytes(proof), np.uint8)
