@@ -21,4 +21,16 @@ if what in ("all", "g2"):
     bases = za_b200.Bases.generate(ctx, 2, n, 1)
     sc = torch.from_numpy(synthetic.random_scalars(n, 3)).cuda()
     for _ in range(2): za_b200.multiexp_device(ctx, bases, sc.data_ptr(), n)
+if what == "g1t":
+    n = 1 << 20
+    bases = za_b200.Bases.generate(ctx, 1, n, 1)
+    bases.precompute()
+    sc = torch.from_numpy(synthetic.random_scalars(n, 2)).cuda()
+    for _ in range(2): za_b200.multiexp_device(ctx, bases, sc.data_ptr(), n)
+if what == "g2t":
+    n = 1 << 20
+    bases = za_b200.Bases.generate(ctx, 2, n, 1)
+    bases.precompute()
+    sc = torch.from_numpy(synthetic.random_scalars(n, 3)).cuda()
+    for _ in range(2): za_b200.multiexp_device(ctx, bases, sc.data_ptr(), n)
 print("done")

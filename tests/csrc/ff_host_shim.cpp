@@ -26,6 +26,8 @@ UNOP(shim_fq_from_mont, Fq, fp_from_mont(x))
 BINOP(shim_fq2_mul, Fq2, x * y)
 UNOP(shim_fq2_sqr, Fq2, sqr(x))
 UNOP(shim_fq2_inv, Fq2, inv(x))
+UNOP(shim_fr_inv_kaliski, Fr, fp_inv_kaliski(x))
+UNOP(shim_fq_inv_kaliski, Fq, fp_inv_kaliski(x))
 }
 #include "../../za_b200/csrc/ec.cuh"
 extern "C" {

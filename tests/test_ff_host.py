@@ -69,6 +69,17 @@ def test_field_ops(shim, name, p):
     assert shim.shim_lost_carries() == 0, "a carry was dropped by an instruction that cannot report it"
 
 
+@pytest.mark.parametrize("name,p", [("fr", P.R_MOD), ("fq", P.Q_MOD)])
+def test_kaliski_inverse(shim, name, p):
+    """The binary-Euclid inverse the batched-affine bucket rounds use equals the a^(p-2) ladder / python pow."""
+    rng = random.Random(5)
+    edge = [0, 1, 2, 3, 4, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, R % p, 1 << 253, 1 << 200, (1 << 253) + 1, p - (1 << 200), 1 << 32, 1 << 64, 3 << 96]
+    for x in edge + [rng.randrange(p) for _ in range(400)] + [rng.randrange(1 << 40) for _ in range(50)]:
+        got = unop(shim, f"shim_{name}_inv_kaliski", x)
+        assert got == (pow(x, -1, p) * R * R % p if x else 0), hex(x)
+    assert shim.shim_lost_carries() == 0
+
+
 def test_fq2_ops(shim):
     rng = random.Random(2)
     q = P.Q_MOD

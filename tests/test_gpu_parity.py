@@ -475,3 +475,83 @@ def test_generate_parameters_rejects_bad_toxic_values(ctx):
     with pytest.raises(za_b200.ZaError) as e:
         za_b200.generate_parameters(ctx, circ, P.R_MOD, 2, 3, 4, 5)    # not canonical
     assert e.value.code == -10
+
+
+# ---------------------------------------------------------------- batched-affine pair rounds (msm.cu K5a)
+@pytest.fixture
+def force_rounds():
+    import os
+    old = {k: os.environ.get(k) for k in ("ZA_MSM_ROUNDS", "ZA_MSM_C")}
+    def set_(rounds, c=None):
+        os.environ["ZA_MSM_ROUNDS"] = str(rounds)
+        if c is None: os.environ.pop("ZA_MSM_C", None)
+        else: os.environ["ZA_MSM_C"] = str(c)
+    yield set_
+    for k, v in old.items():
+        if v is None: os.environ.pop(k, None)
+        else: os.environ[k] = v
+
+
+@pytest.mark.parametrize("group", [1, 2])
+@pytest.mark.parametrize("rounds,c", [(0, None), (1, None), (2, 4), (3, 5), (5, 3), (6, 2)])
+def test_pair_rounds_match_oracle(ctx, force_rounds, group, rounds, c):
+    """Every round count gives the same group element as bellman's multiexp (small windows -> deep buckets)."""
+    force_rounds(rounds, c)
+    for n in (65, 300, 4099):
+        if group == 2 and n > 2000: n = 1500
+        _msm_case(ctx, group, n, O.random_frs(n, 900 + n + rounds))
+    n = 3000 if group == 1 else 1200
+    _msm_case(ctx, group, n, circuits.witness_like(n, 50 + rounds))
+
+
+@pytest.mark.parametrize("group", [1, 2])
+@pytest.mark.parametrize("rounds", [1, 2, 4])
+def test_pair_rounds_exceptional_pairs(ctx, force_rounds, group, rounds):
+    """P + P (doubling), P + (-P) (infinity) and infinity + P inside the pair rounds: every point four times with
+    the same scalar, and blocks of opposite points, so whole buckets cancel and results at infinity feed later rounds."""
+    import za_b200
+    force_rounds(rounds, 4)
+    n = 512
+    pts = (O.g1_multiples(n) if group == 1 else O.g2_multiples(n)).copy()
+    half = pts.shape[1] // 2
+    for k in range(1, 4):
+        pts[k::4] = pts[0::4]                              # every point four times
+    def negated(p):
+        q = p.copy()
+        if group == 1:
+            y = int.from_bytes(q[32:].tobytes(), "little")
+            q[32:] = np.frombuffer(((P.Q_MOD - y) % P.Q_MOD).to_bytes(32, "little"), np.uint8)
+        else:
+            for o in (64, 96):
+                y = int.from_bytes(q[o:o + 32].tobytes(), "little")
+                q[o:o + 32] = np.frombuffer(((P.Q_MOD - y) % P.Q_MOD).to_bytes(32, "little"), np.uint8)
+        return q
+    for i in range(0, 128, 4):                             # groups of P, P, -P, -P: the whole group cancels
+        pts[i + 2] = negated(pts[i]); pts[i + 3] = negated(pts[i])
+    for i in range(128, 192, 4):                           # P, -P, P, P: infinity + P in the next round
+        pts[i + 1] = negated(pts[i])
+    s = O.random_frs(n, 1234 + rounds)
+    for k in range(1, 4):
+        s[k::4] = s[0::4]
+    bases = za_b200.Bases(ctx, group, pts)
+    got = za_b200.multiexp(ctx, bases, s)
+    rc, exp = O.multiexp("g1" if group == 1 else "g2", pts, s, threads=8)
+    assert rc == 0 and got == exp
+    ones = np.zeros((n, 32), np.uint8); ones[:, 0] = 1     # all scalars 1: a single bucket holds everything
+    got = za_b200.multiexp(ctx, bases, ones)
+    rc, exp = O.multiexp("g1" if group == 1 else "g2", pts, ones, threads=8)
+    assert rc == 0 and got == exp
+
+
+def test_pair_rounds_fixed_base_table(ctx, force_rounds):
+    """Table mode (one bucket space, 2^(cw) P_i entries) through the pair rounds, witness-like and uniform scalars."""
+    import za_b200
+    n = 1 << 15
+    pts = O.g1_multiples(n)
+    for rounds in (0, 3):
+        force_rounds(rounds)
+        tab = za_b200.Bases(ctx, 1, pts)
+        tab.precompute()
+        for s in (O.random_frs(n, 71), circuits.witness_like(n, 72)):
+            rc, exp = O.multiexp("g1", pts, s, threads=8)
+            assert rc == 0 and za_b200.multiexp(ctx, tab, s) == exp

@@ -2,6 +2,7 @@
 // Every entry point converts C++ exceptions into status codes; nothing crosses the ABI but plain
 // pointers and sizes.
 #include "common.cuh"
+#include <stdlib.h>
 #include "api_internal.cuh"
 #include <string.h>
 
@@ -75,6 +76,17 @@ int za_ctx_create(int device, za_ctx** out) {
     za_ctx* c = new za_ctx();
     c->c.device = device;
     c->c.sm_count = prop.multiProcessorCount;
+    {
+        // The multiexps gather 64-byte (G1) / 128-byte (G2) points at random from tables far larger than L2; the
+        // default L2 fill granularity fetches 128 bytes per miss.  ZA_L2_FETCH = 32 / 64 / 128 overrides.
+        size_t gran = 0;
+        if (const char* e = getenv("ZA_L2_FETCH")) gran = (size_t)atoi(e);
+        if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        if (getenv("ZA_DEBUG_TIMELINE")) fprintf(stderr, "[za] L2 fetch granularity %zu\n", got);
+        cudaGetLastError();
+    }
     ZA_CUDA(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
     ZA_CUDA(cudaStreamCreateWithFlags(&c->c.side, cudaStreamNonBlocking));
     c->c.stream = c->own;

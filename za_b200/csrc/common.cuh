@@ -77,6 +77,8 @@ struct NttDomain {
 // stream, bucket reduction on the side stream) and their window sums collected at the end.
 struct MsmSlot {
     DevBuf counts, entries, buckets, parts, segs;
+    DevBuf pair_pts[2], pair_offs;       // batched-affine pair rounds: ping-pong point buffers, per-round bucket offsets
+    int rounds = 0;
     void* host_win = nullptr;            // pinned: window sums (+ entry count when profiling)
     size_t host_win_bytes = 0;
     cudaEvent_t acc_done = nullptr, done = nullptr;

@@ -154,12 +154,17 @@ static __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint
     __syncthreads();
     return base + x - v;
 }
-__global__ void __launch_bounds__(1024) msm_scan_totals_kernel(const uint32_t* counts, uint32_t count, uint32_t* cta_totals) {
+// `halve`: the counters are not read from `counts` but derived from the previous pair round's offsets:
+// a bucket holding k points holds ceil(k / 2) after one round of pairwise additions.
+static __device__ __forceinline__ uint32_t scan_count_at(const uint32_t* counts, uint32_t i, int halve) {
+    return halve ? (counts[i + 1] - counts[i] + 1) >> 1 : counts[i];
+}
+__global__ void __launch_bounds__(1024) msm_scan_totals_kernel(const uint32_t* counts, uint32_t count, uint32_t* cta_totals, int halve) {
     __shared__ uint32_t sm[32];
     const uint32_t base = blockIdx.x * SCAN_PER_CTA + threadIdx.x * 4;
     uint32_t s = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) if (base + k < count) s += counts[base + k];
+    for (int k = 0; k < 4; k++) if (base + k < count) s += scan_count_at(counts, base + k, halve);
     uint32_t total;
     block_excl_scan_1024(s, sm, total);
     if (threadIdx.x == 0) cta_totals[blockIdx.x] = total;
@@ -178,23 +183,25 @@ __global__ void __launch_bounds__(1024) msm_scan_ctas_kernel(uint32_t* cta_total
     if (threadIdx.x == 0) *grand_total = run;
 }
 __global__ void __launch_bounds__(1024) msm_scan_apply_kernel(const uint32_t* counts, uint32_t count, const uint32_t* cta_offsets, uint32_t* offsets,
-                                                              uint32_t* cursors) {
+                                                              uint32_t* cursors, int halve) {
     __shared__ uint32_t sm[32];
     const uint32_t base = blockIdx.x * SCAN_PER_CTA + threadIdx.x * 4;
     uint32_t v[4], s = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) { v[k] = base + k < count ? counts[base + k] : 0; s += v[k]; }
+    for (int k = 0; k < 4; k++) { v[k] = base + k < count ? scan_count_at(counts, base + k, halve) : 0; s += v[k]; }
     uint32_t total;
     uint32_t run = cta_offsets[blockIdx.x] + block_excl_scan_1024(s, sm, total);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        if (base + k < count) { offsets[base + k] = run; cursors[base + k] = run; }
+        if (base + k < count) { offsets[base + k] = run; if (cursors) cursors[base + k] = run; }
         run += v[k];
     }
 }
 
 // K5: chunked segmented accumulation.  Thread `chunk` owns entries [chunk*Lc, (chunk+1)*Lc).
-template <class F>
+// DIRECT: the stream is the output of the pair rounds (K5a) — entry `pos` is the point bases[pos] itself, no sign,
+// and may be the point at infinity (P + (-P) in a round).
+template <class F, bool DIRECT>
 __global__ void __launch_bounds__(128, (sizeof(F) == sizeof(Fq) ? ZA_ACC_G1_BLOCKS : ZA_ACC_G2_BLOCKS)) msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ entries,
                                                              const uint32_t* __restrict__ offsets, uint32_t nkeys, uint32_t Lc,
                                                              XYZZ<F>* bucket_sums, XYZZ<F>* part_head, XYZZ<F>* part_tail,
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(128, (sizeof(F) == sizeof(Fq) ? ZA_ACC_G1_BLOC
     bool head_open = offsets[key] < start;
     uint32_t bend = offsets[key + 1];
     XYZZ<F> acc = XYZZ<F>::inf();
-    uint32_t e = entries[start];
+    uint32_t e = DIRECT ? start : entries[start];
     Affine<F> P = ldg_vec(bases + (e & 0x7fffffffu));
     // One flat loop: every lane performs one mixed addition per iteration (convergent); the bucket
     // bookkeeping at run boundaries is the only divergent part and is a few instructions plus one store.
@@ -223,10 +230,10 @@ __global__ void __launch_bounds__(128, (sizeof(F) == sizeof(Fq) ? ZA_ACC_G1_BLOC
         const uint32_t e_cur = e;
         const Affine<F> P_cur = P;
         if (pos + 1 < end) {                       // prefetch the next point while this one is added
-            e = entries[pos + 1];
+            e = DIRECT ? pos + 1 : entries[pos + 1];
             P = ldg_vec(bases + (e & 0x7fffffffu));
         }
-        xyzz_madd_hot(acc, P_cur.x, P_cur.y, (e_cur >> 31) != 0);
+        if (!DIRECT || !P_cur.is_inf()) xyzz_madd_hot(acc, P_cur.x, P_cur.y, !DIRECT && (e_cur >> 31) != 0);
         const uint32_t nxt = pos + 1;
         if (nxt == bend || nxt == end) {
             const bool closes = nxt == bend;
@@ -240,6 +247,220 @@ __global__ void __launch_bounds__(128, (sizeof(F) == sizeof(Fq) ? ZA_ACC_G1_BLOC
                 bend = offsets[key + 1];
             }
         }
+    }
+}
+
+
+// K5a: batched-affine pair rounds.  One round halves every bucket: the k points of a bucket become ceil(k/2)
+// by adding neighbours pairwise in AFFINE coordinates — lambda = (y1-y0)/(x1-x0), 6 field products per addition
+// instead of the 10 of the XYZZ mixed addition — with all the divisions of a WARP (32 x LP) sharing ONE field
+// inversion (Montgomery's simultaneous-inversion trick).  A thread owns LP consecutive output points:
+//   forward   d_j = x1 - x0 (or 2 y0 when the pair is a doubling), prefix products of the d_j in local memory
+//   warp      prefix / suffix product scans of the lane totals over the lanes (shuffles) + one fp_inv_kaliski,
+//             which runs on the ALU pipe; no block-level synchronisation
+//   backward  1/d_j = I * prefix_j,  I *= d_j,  lambda, x3 = lambda^2 - x0 - x1, y3 = lambda (x0 - x3) - y0
+// Exceptional pairs (P + P, P + (-P), infinity) are detected in the forward pass and keep the batch intact.
+// After a few rounds the remaining points go through the XYZZ accumulation (DIRECT) as before.
+#if !defined(__CUDA_ARCH__)
+static inline Fq fq_mul_call(const Fq& a, const Fq& b) { return a * b; }      // host pass only parses the kernels
+#endif
+static __device__ __forceinline__ Fq fmul(const Fq& a, const Fq& b) { return fq_mul_call(a, b); }
+static __device__ __forceinline__ Fq2 fmul(const Fq2& a, const Fq2& b) { return a * b; }
+static __device__ __forceinline__ Fq fsqr(const Fq& a) { return fq_mul_call(a, a); }
+static __device__ __forceinline__ Fq2 fsqr(const Fq2& a) { return sqr(a); }
+static __device__ __noinline__ Fq fq_inv_call(const Fq a) { return fp_inv_kaliski<FqParams>(a); }
+static __device__ __forceinline__ Fq finv(const Fq& a) { return fq_inv_call(a); }
+static __device__ __forceinline__ Fq2 finv(const Fq2& a) {
+    const Fq n = fq_inv_call(fsqr(a.c0) + fsqr(a.c1));
+    Fq2 r;
+    r.c0 = fmul(a.c0, n);
+    r.c1 = -fmul(a.c1, n);
+    return r;
+}
+template <class T>
+static __device__ __forceinline__ T shfl_up_vec(const T& v, int d) {
+    T r;
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(&v);
+    uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (unsigned k = 0; k < sizeof(T) / 4; k++) o[k] = __shfl_up_sync(0xffffffffu, a[k], d);
+    return r;
+}
+template <class T>
+static __device__ __forceinline__ T shfl_down_vec(const T& v, int d) {
+    T r;
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(&v);
+    uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (unsigned k = 0; k < sizeof(T) / 4; k++) o[k] = __shfl_down_sync(0xffffffffu, a[k], d);
+    return r;
+}
+template <class T>
+static __device__ __forceinline__ T shfl_idx_vec(const T& v, int src) {
+    T r;
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(&v);
+    uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (unsigned k = 0; k < sizeof(T) / 4; k++) o[k] = __shfl_sync(0xffffffffu, a[k], src);
+    return r;
+}
+
+enum { PR_COPY0 = 0, PR_COPY1 = 1, PR_INF = 2, PR_ADD = 3, PR_DBL = 4 };
+
+// resolved source of output j: point index (bit 31 = negate y) of the first operand; the second one (pairs only)
+// is the next entry / next point
+template <class F, bool FIRST>
+static __device__ __forceinline__ uint32_t pair_ref(const uint32_t* entries, uint32_t s) { return FIRST ? entries[s] : s; }
+template <class F>
+static __device__ __forceinline__ const Affine<F>* pair_ptr(const Affine<F>* pts, uint32_t ref) { return pts + (ref & 0x7fffffffu); }
+
+template <class F, bool FIRST, int NT, int LP>
+__global__ void __launch_bounds__(NT, (sizeof(F) == sizeof(Fq) ? 512 : 256) / NT) msm_pair_round_kernel(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
+                                                                  const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out,
+                                                                  uint32_t nkeys, Affine<F>* __restrict__ out) {
+    constexpr int FB = sizeof(F) == sizeof(Fq) ? 4 : 2;      // forward pass: loads of FB outputs in flight per thread
+    static_assert(LP % FB == 0, "LP must be a multiple of the forward batch");
+    const uint32_t n_out = off_out[nkeys];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t cta_first = (uint64_t)blockIdx.x * (NT * LP);
+    if (cta_first + (uint64_t)(tid & ~31u) * LP >= n_out) return;       // the whole warp is past the end
+    const uint64_t q0_64 = cta_first + (uint64_t)tid * LP;
+    const uint32_t q0 = (uint32_t)q0_64;
+    const uint32_t cnt = q0_64 < n_out ? (n_out - q0 < (uint32_t)LP ? n_out - q0 : (uint32_t)LP) : 0u;
+    uint32_t ref0[LP], ref1[LP];                     // operands of output j (ref1 = 0xffffffff: no second operand)
+    uint8_t flags[LP];
+    F pre[LP];
+    F run = F::one();
+    if (cnt) {
+        // ---- walk the buckets of this thread's outputs, resolve the operands
+        uint32_t lo = 0, hi = nkeys;                  // last key with off_out[key] <= q0: the bucket of output q0
+        while (lo + 1 < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (off_out[mid] <= q0) lo = mid; else hi = mid;
+        }
+        uint32_t key = lo;
+        uint32_t obase = off_out[key], oend = off_out[key + 1], ibase = off_in[key], icnt = off_in[key + 1] - ibase;
+#pragma unroll 4
+        for (uint32_t j = 0; j < (uint32_t)LP; j++) {
+            uint32_t r0 = 0, r1 = 0xffffffffu;
+            if (j < cnt) {
+                const uint32_t q = q0 + j;
+                if (q == oend) {
+                    do { key++; } while (off_out[key + 1] <= q);
+                    obase = off_out[key]; oend = off_out[key + 1]; ibase = off_in[key]; icnt = off_in[key + 1] - ibase;
+                }
+                const uint32_t k = q - obase;
+                const uint32_t s0 = ibase + 2 * k;
+                r0 = pair_ref<F, FIRST>(entries, s0);
+                if (2 * k + 1 < icnt) r1 = pair_ref<F, FIRST>(entries, s0 + 1);
+            }
+            ref0[j] = r0; ref1[j] = r1;
+        }
+        // ---- forward: x differences, FB outputs' loads in flight at a time
+#pragma unroll 1
+        for (uint32_t j0 = 0; j0 < cnt; j0 += FB) {
+            F x0[FB], x1[FB];
+#pragma unroll
+            for (int u = 0; u < FB; u++) {
+                const uint32_t j = j0 + u;
+                const uint32_t r0 = ref0[j], r1 = ref1[j];     // j < LP always; entries beyond cnt are (0, none)
+                x0[u] = ldg_vec(&pair_ptr<F>(pts, r0)->x);
+                x1[u] = ldg_vec(&pair_ptr<F>(pts, r1 == 0xffffffffu ? r0 : r1)->x);
+            }
+            if (j0 + FB < cnt) {                       // the next batch's points on their way into L1 meanwhile
+#pragma unroll
+                for (int u = 0; u < FB; u++) {
+                    const uint32_t r0 = ref0[j0 + FB + u], r1 = ref1[j0 + FB + u];
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pair_ptr<F>(pts, r0)));
+                    if (r1 != 0xffffffffu) asm volatile("prefetch.global.L1 [%0];" ::"l"(pair_ptr<F>(pts, r1)));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < FB; u++) {
+                const uint32_t j = j0 + u;
+                if (j >= cnt) break;
+                const uint32_t r0 = ref0[j], r1 = ref1[j];
+                uint32_t fl = PR_COPY0;
+                if (r1 != 0xffffffffu) {
+                    F d = x1[u] - x0[u];
+                    fl = PR_ADD;
+                    if (d.is_zero() || x0[u].is_zero() || x1[u].is_zero()) {          // rare: look at the y coordinates
+                        F y0 = ldg_vec(&pair_ptr<F>(pts, r0)->y), y1 = ldg_vec(&pair_ptr<F>(pts, r1)->y);
+                        if (r0 >> 31) y0 = -y0;
+                        if (r1 >> 31) y1 = -y1;
+                        if (x0[u].is_zero() && y0.is_zero()) fl = PR_COPY1;
+                        else if (x1[u].is_zero() && y1.is_zero()) fl = PR_COPY0;
+                        else if (d.is_zero()) {
+                            if (y0 == y1 && !y0.is_zero()) { fl = PR_DBL; d = dbl(y0); }
+                            else fl = PR_INF;
+                        }
+                    }
+                    if (fl >= PR_ADD) { pre[j] = run; run = fmul(run, d); }
+                }
+                flags[j] = (uint8_t)fl;
+            }
+        }
+    }
+    // ---- one inversion per warp: prefix and suffix products of the lane totals over the lanes, the warp product
+    // inverted once (same value in every lane, so the branchy binary-Euclid inverse stays convergent), and
+    // 1 / total_lane = ginv * (product of the lanes before) * (product of the lanes after).  No block-level
+    // synchronisation: the warps of a CTA drift freely and hide each other's memory latency.
+    F I;
+    {
+        const unsigned lane = tid & 31;
+        F pf = run, sf = run;
+#pragma unroll 1
+        for (int d = 1; d < 32; d <<= 1) {
+            F up = shfl_up_vec(pf, d), dn = shfl_down_vec(sf, d);
+            if (lane < (unsigned)d) up = F::one();
+            if (lane + d >= 32) dn = F::one();
+            pf = fmul(pf, up);
+            sf = fmul(sf, dn);
+        }
+        const F ginv = finv(shfl_idx_vec(pf, 31));
+        F e = shfl_up_vec(pf, 1), sfx = shfl_down_vec(sf, 1);
+        if (lane == 0) e = F::one();
+        if (lane == 31) sfx = F::one();
+        I = fmul(fmul(ginv, e), sfx);
+    }
+    // ---- backward, software pipelined by one output: the operand indices and the prefix product of output j-1
+    // are loaded (local memory) and its two points prefetched into L1 while output j is computed
+    if (!cnt) return;
+    uint32_t nr0 = ref0[cnt - 1], nr1 = ref1[cnt - 1], nfl = flags[cnt - 1];
+    F npre = pre[cnt - 1];
+#pragma unroll 1
+    for (uint32_t j = cnt; j-- > 0;) {
+        const uint32_t r0 = nr0, r1 = nr1, fl = nfl;
+        const F pj = npre;
+        if (j) {
+            nr0 = ref0[j - 1]; nr1 = ref1[j - 1]; nfl = flags[j - 1];
+            npre = pre[j - 1];
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pair_ptr<F>(pts, nr0)));
+            if (nr1 != 0xffffffffu) asm volatile("prefetch.global.L1 [%0];" ::"l"(pair_ptr<F>(pts, nr1)));
+        }
+        Affine<F> R;
+        if (fl >= PR_ADD) {
+            Affine<F> A = ldg_vec(pair_ptr<F>(pts, r0)), B = ldg_vec(pair_ptr<F>(pts, r1));
+            if (r0 >> 31) A.y = -A.y;
+            if (r1 >> 31) B.y = -B.y;
+            F d = B.x - A.x, num = B.y - A.y, xs = A.x + B.x;
+            if (fl == PR_DBL) {
+                const F xx = fsqr(A.x);
+                d = dbl(A.y); num = dbl(xx) + xx; xs = dbl(A.x);
+            }
+            const F id = fmul(I, pj);
+            I = fmul(I, d);
+            const F lam = fmul(num, id);
+            R.x = fsqr(lam) - xs;
+            R.y = fmul(lam, A.x - R.x) - A.y;
+        } else if (fl == PR_INF) {
+            R = Affine<F>::inf();
+        } else {
+            const uint32_t r = fl == PR_COPY1 ? r1 : r0;
+            R = ldg_vec(pair_ptr<F>(pts, r));
+            if (r >> 31) R.y = -R.y;
+        }
+        st_vec(out + q0 + j, R);
     }
 }
 
@@ -333,15 +554,20 @@ __global__ void __launch_bounds__(128) msm_weighted_level_kernel(const XYZZ<F>* 
     st_vec(pool + (size_t)w * pool_stride + pool_off + j, acc);
 }
 
-// K6b: warp per group of `per` consecutive points -> one sum
+// K6b: one level of the pool sum: warp g of window w adds the (up to) `per` points [g*per, (g+1)*per) of the
+// window's `count` points and writes out[w*groups + g]: per/32 sequential additions per lane, then a five-step
+// shuffle tree.
 template <class F>
-__global__ void __launch_bounds__(128) msm_group_reduce_kernel(const XYZZ<F>* __restrict__ in, uint32_t per, uint32_t groups, XYZZ<F>* out) {
+__global__ void __launch_bounds__(128) msm_group_reduce_kernel(const XYZZ<F>* __restrict__ in, uint32_t stride_in, uint32_t count, uint32_t per,
+                                                               uint32_t groups, uint32_t total_groups, XYZZ<F>* out) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned lane = threadIdx.x & 31;
-    if (warp >= groups) return;
+    if (warp >= total_groups) return;
+    const uint32_t w = warp / groups, g = warp % groups;
+    const uint32_t lo = g * per, hi = lo + per < count ? lo + per : count;
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t k = lane; k < per; k += 32) {
-        XYZZ<F> v = ld_vec(in + (size_t)warp * per + k);
+    for (uint32_t k = lo + lane; k < hi; k += 32) {
+        XYZZ<F> v = ld_vec(in + (size_t)w * stride_in + k);
         xyzz_add<F>(acc, v);
     }
     acc = warp_reduce_xyzz<F>(acc, lane);
@@ -634,14 +860,38 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
     const uint64_t Emax = (uint64_t)n * W;
     if (single) d_bases = d_table;
     if (Emax >= 0xffffffffull) throw ZaError(ZA_ERR_INVALID, "multiexp too large for 32-bit entry offsets");
+    // batched-affine pair rounds before the XYZZ accumulation: worth it while buckets hold several points
+    // (load = entries per bucket).  ZA_MSM_ROUNDS overrides (0 = XYZZ accumulation only).
+    constexpr int PAIR_NT = 128, PAIR_LP = 32, PAIR_MAX_ROUNDS = 6;
+    int rounds = 0;
+    {
+        // Measured on B200 (profiles/r01_pair_rounds.md): over Fq2 the rounds win (17 instead of 28 Fq products
+        // per addition, -19 % at 2^20 points); over Fq the first round has to gather every 64-byte point twice
+        // from a table far larger than L2 (the memory system fetches 128 bytes per miss) and is DRAM bound,
+        // so G1 keeps the single-pass XYZZ accumulation.
+        const double load = (double)Emax / (double)nkeys;
+        if (sizeof(F) == sizeof(Fq2)) rounds = load >= 12 ? 4 : load >= 6 ? 3 : load >= 3 ? 1 : 0;
+        if (Emax < (1u << 16)) rounds = 0;
+        if (const char* e = getenv("ZA_MSM_ROUNDS")) { int v = atoi(e); if (v >= 0 && v <= PAIR_MAX_ROUNDS) rounds = v; }
+    }
+    sl.rounds = rounds;
+    int pair_lp = PAIR_LP;
+    if (const char* e = getenv("ZA_MSM_PAIR_LP")) { if (atoi(e) == 16) pair_lp = 16; }
+    uint64_t pair_cap[PAIR_MAX_ROUNDS + 1];               // upper bounds of the point count after each round
+    {
+        uint64_t cap = Emax;
+        for (int r = 0; r < rounds; r++) { cap = (cap + (cap < nkeys ? cap : nkeys) + 1) / 2; pair_cap[r] = cap; }
+        pair_cap[rounds] = cap;
+    }
+    const uint64_t Efinal = rounds ? pair_cap[rounds - 1] : Emax;
     // chunk length: ~2 chunks per resident thread slot, between 16 and 2048 entries (measured best of 2/4/8 at 2^20)
     uint64_t per_slot = 2;
     if (const char* e = getenv("ZA_MSM_CHUNKS_PER_SLOT")) { int v = atoi(e); if (v >= 1 && v <= 64) per_slot = (uint64_t)v; }
     uint64_t tslots = (uint64_t)ctx->sm_count * 512 * per_slot;
-    uint32_t Lc = (uint32_t)((Emax + tslots - 1) / tslots);
+    uint32_t Lc = (uint32_t)((Efinal + tslots - 1) / tslots);
     if (Lc < 16) Lc = 16;
     if (Lc > 2048) Lc = 2048;
-    const uint32_t nchunks = (uint32_t)((Emax + Lc - 1) / Lc);
+    const uint32_t nchunks = (uint32_t)((Efinal + Lc - 1) / Lc);
     sl.kind = 2; sl.c = c; sl.W = Wr; sl.nkeys = nkeys; sl.Lc = Lc; sl.nchunks = nchunks;
     sl.acc_cat = sizeof(F) == sizeof(Fq) ? PROF_ACC_G1 : PROF_ACC_G2;
 
@@ -664,6 +914,15 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
         d_entries = sl.entries.as<uint32_t>();
     }
     sl.d_offsets = d_offsets; sl.d_entries = d_entries;
+    uint32_t *d_pair_off = nullptr, *d_pair_cta = nullptr;
+    const uint32_t* d_offsets_final = d_offsets;
+    if (rounds) {
+        sl.pair_offs.ensure(((size_t)rounds * (nkeys + 1) + nctas) * 4);
+        d_pair_off = sl.pair_offs.as<uint32_t>();
+        d_pair_cta = d_pair_off + (size_t)rounds * (nkeys + 1);
+        sl.pair_pts[0].ensure((size_t)pair_cap[0] * sizeof(Affine<F>));
+        if (rounds > 1) sl.pair_pts[1].ensure((size_t)pair_cap[1] * sizeof(Affine<F>));
+    }
     sl.buckets.ensure((size_t)nkeys * sizeof(XYZZ<F>));
     sl.parts.ensure((size_t)nchunks * (2 * sizeof(XYZZ<F>) + 8) + 16);   // part_head | part_tail | owner | long_list | long_count
     XYZZ<F>* d_head = sl.parts.as<XYZZ<F>>();
@@ -689,13 +948,19 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
     }
     const uint32_t pool_used = pool_len + 1;                         // + the final plain sum T
     const uint32_t pool_stride = (pool_used + 63) / 64 * 64;         // padded with points at infinity
-    const uint32_t pool_groups = pool_stride / 64;
+    // pool sum: a tree of warp reductions over GRP_PER points each (4 sequential additions per lane, then a
+    // five-step shuffle tree), sizes pool_stride -> /128 -> ... -> 1 per window
+    constexpr uint32_t GRP_PER = 128;
+    std::vector<uint32_t> grp_sizes;
+    size_t grp_total = 0;
+    for (uint32_t cnt = pool_stride; cnt > 1;) { cnt = (cnt + GRP_PER - 1) / GRP_PER; grp_sizes.push_back(cnt); grp_total += cnt; }
+    if (grp_sizes.empty()) { grp_sizes.push_back(1); grp_total = 1; }
     const size_t lvl_elems = (size_t)Wr * (B / (B < SEG ? B : SEG) + 1);
-    sl.segs.ensure(((size_t)Wr * pool_stride + 2 * lvl_elems + (size_t)Wr * pool_groups + Wr) * sizeof(XYZZ<F>));
+    sl.segs.ensure(((size_t)Wr * pool_stride + 2 * lvl_elems + (size_t)Wr * grp_total) * sizeof(XYZZ<F>));
     XYZZ<F>* d_pool = sl.segs.as<XYZZ<F>>();
     XYZZ<F>* d_lvl[2] = {d_pool + (size_t)Wr * pool_stride, d_pool + (size_t)Wr * pool_stride + lvl_elems};
     XYZZ<F>* d_grp = d_lvl[1] + lvl_elems;
-    XYZZ<F>* d_win = d_grp + (size_t)Wr * pool_groups;
+    XYZZ<F>* d_win = d_grp + (size_t)Wr * (grp_total - 1);          // the last level has one point per window
     XYZZ<F>* d_buckets = sl.buckets.as<XYZZ<F>>();
 
     ZA_CUDA(cudaMemsetAsync(d_buckets, 0, (size_t)nkeys * sizeof(XYZZ<F>), st));
@@ -706,25 +971,52 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
         ZA_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nkeys * 4, st));
         ProfScope prof(ctx, PROF_MSM_SORT, (double)n);
         msm_digits_hist_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_counts, single ? 1 : 0);
-        msm_scan_totals_kernel<<<nctas, 1024, 0, st>>>(d_counts, nkeys, d_cta);
+        msm_scan_totals_kernel<<<nctas, 1024, 0, st>>>(d_counts, nkeys, d_cta, 0);
         msm_scan_ctas_kernel<<<1, 1024, 0, st>>>(d_cta, nctas, d_offsets + nkeys);
-        msm_scan_apply_kernel<<<nctas, 1024, 0, st>>>(d_counts, nkeys, d_cta, d_offsets, d_cursors);
+        msm_scan_apply_kernel<<<nctas, 1024, 0, st>>>(d_counts, nkeys, d_cta, d_offsets, d_cursors, 0);
         msm_digits_scatter_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_cursors, d_entries, single ? 1 : 0);
         ctx->launches += 5;
     }
     {
         ProfScope prof(ctx, sl.acc_cat, 0);
-        msm_accumulate_kernel<F><<<nblk(nchunks, 128), 128, 0, st>>>(d_bases, d_entries, d_offsets, nkeys, Lc, d_buckets, d_head, d_tail, d_owner);
+        const Affine<F>* cur_pts = d_bases;
+        const uint32_t* cur_off = d_offsets;
+        uint64_t cap = Emax;
+        for (int r = 0; r < rounds; r++) {
+            uint32_t* nxt_off = d_pair_off + (size_t)r * (nkeys + 1);
+            Affine<F>* nxt_pts = sl.pair_pts[r & 1].as<Affine<F>>();
+            msm_scan_totals_kernel<<<nctas, 1024, 0, st>>>(cur_off, nkeys, d_pair_cta, 1);
+            msm_scan_ctas_kernel<<<1, 1024, 0, st>>>(d_pair_cta, nctas, nxt_off + nkeys);
+            msm_scan_apply_kernel<<<nctas, 1024, 0, st>>>(cur_off, nkeys, d_pair_cta, nxt_off, nullptr, 1);
+            cap = pair_cap[r];
+            // small rounds: shorter per-thread runs so that the grid still fills the SMs
+            if (pair_lp == 16 || cap < (uint64_t)ctx->sm_count * 4 * PAIR_NT * 32) {
+                const unsigned grid = nblk(cap, PAIR_NT * 16);
+                if (r == 0) msm_pair_round_kernel<F, true, PAIR_NT, 16><<<grid, PAIR_NT, 0, st>>>(cur_pts, d_entries, cur_off, nxt_off, nkeys, nxt_pts);
+                else msm_pair_round_kernel<F, false, PAIR_NT, 16><<<grid, PAIR_NT, 0, st>>>(cur_pts, nullptr, cur_off, nxt_off, nkeys, nxt_pts);
+            } else {
+                const unsigned grid = nblk(cap, PAIR_NT * PAIR_LP);
+                if (r == 0) msm_pair_round_kernel<F, true, PAIR_NT, PAIR_LP><<<grid, PAIR_NT, 0, st>>>(cur_pts, d_entries, cur_off, nxt_off, nkeys, nxt_pts);
+                else msm_pair_round_kernel<F, false, PAIR_NT, PAIR_LP><<<grid, PAIR_NT, 0, st>>>(cur_pts, nullptr, cur_off, nxt_off, nkeys, nxt_pts);
+            }
+            ctx->launches += 4;
+            if (ctx->profile) ZA_CUDA(cudaMemcpyAsync((uint32_t*)sl.host_win + 1 + r, nxt_off + nkeys, 4, cudaMemcpyDeviceToHost, st));
+            cur_pts = nxt_pts;
+            cur_off = nxt_off;
+        }
+        if (rounds) msm_accumulate_kernel<F, true><<<nblk(nchunks, 128), 128, 0, st>>>(cur_pts, nullptr, cur_off, nkeys, Lc, d_buckets, d_head, d_tail, d_owner);
+        else msm_accumulate_kernel<F, false><<<nblk(nchunks, 128), 128, 0, st>>>(d_bases, d_entries, d_offsets, nkeys, Lc, d_buckets, d_head, d_tail, d_owner);
         ctx->launches++;
+        d_offsets_final = cur_off;
     }
     ZA_CUDA(cudaEventRecord(sl.acc_done, st));
     if (timeline) cudaEventRecord(sl.dbg_acc, st);
     ZA_CUDA(cudaStreamWaitEvent(side, sl.acc_done, 0));
     {
         ProfScope prof(ctx, PROF_MSM_REDUCE, (double)nkeys, side, true);
-        msm_fixup_kernel<F><<<nblk(nchunks, 128), 128, 0, side>>>(d_offsets, nkeys, Lc, nchunks, d_head, d_tail, d_owner, d_buckets, d_long_list,
+        msm_fixup_kernel<F><<<nblk(nchunks, 128), 128, 0, side>>>(d_offsets_final, nkeys, Lc, nchunks, d_head, d_tail, d_owner, d_buckets, d_long_list,
                                                                   d_long_count);
-        msm_fixup_long_kernel<F><<<ctx->sm_count * 2, 128, 0, side>>>(d_offsets, Lc, d_head, d_tail, d_owner, d_buckets, d_long_list, d_long_count);
+        msm_fixup_long_kernel<F><<<ctx->sm_count * 2, 128, 0, side>>>(d_offsets_final, Lc, d_head, d_tail, d_owner, d_buckets, d_long_list, d_long_count);
         ctx->launches += 2;
         const XYZZ<F>* src = d_buckets;
         int li = 0;
@@ -741,9 +1033,17 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
         // the final T (one per window) is the plain sum of all buckets: pool slot pool_len
         ZA_CUDA(cudaMemcpy2DAsync(d_pool + pool_len, (size_t)pool_stride * sizeof(XYZZ<F>), src, sizeof(XYZZ<F>), sizeof(XYZZ<F>), Wr,
                                   cudaMemcpyDeviceToDevice, side));
-        msm_group_reduce_kernel<F><<<nblk((size_t)Wr * pool_groups * 32, 128), 128, 0, side>>>(d_pool, 64, (uint32_t)Wr * pool_groups, d_grp);
-        msm_group_reduce_kernel<F><<<nblk((size_t)Wr * 32, 128), 128, 0, side>>>(d_grp, pool_groups, (uint32_t)Wr, d_win);
-        ctx->launches += 2;
+        {
+            const XYZZ<F>* gin = d_pool;
+            uint32_t gstride = pool_stride, gcount = pool_stride;
+            XYZZ<F>* gout = d_grp;
+            for (uint32_t groups : grp_sizes) {
+                msm_group_reduce_kernel<F><<<nblk((size_t)Wr * groups * 32, 128), 128, 0, side>>>(gin, gstride, gcount, GRP_PER, groups, (uint32_t)Wr * groups, gout);
+                ctx->launches++;
+                gin = gout; gstride = groups; gcount = groups;
+                gout += (size_t)Wr * groups;
+            }
+        }
     }
     ZA_CUDA(cudaGetLastError());
     ZA_CUDA(cudaMemcpyAsync((uint8_t*)sl.host_win + 64, d_win, (size_t)Wr * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, side));
@@ -770,9 +1070,16 @@ XYZZ<F> msm_finish(Ctx* ctx, int slot_id) {
         return result;
     }
     if (ctx->profile) {
-        uint32_t E;
-        memcpy(&E, sl.host_win, 4);
-        ctx->prof_work[sl.acc_cat] += (double)E;      // mixed additions actually performed
+        // algorithmic work of the accumulation in Fq products: a batched-affine addition is 5M + 1S (G2: 5 Fq2
+        // products of 3 and one squaring of 2 = 17), an XYZZ mixed addition 8M + 2S (G2: 28); the point count
+        // after every round came back with the window sums
+        uint32_t E[8];
+        memcpy(E, sl.host_win, 4 * (1 + sl.rounds));
+        const bool g1 = sizeof(F) == sizeof(Fq);
+        double work = 0;
+        for (int r = 0; r < sl.rounds; r++) work += (double)(E[r] - E[r + 1]) * (g1 ? 6.0 : 17.0);
+        work += (double)E[sl.rounds] * (g1 ? 10.0 : 28.0);
+        ctx->prof_work[sl.acc_cat] += work;
     }
     // window combination on the host: result = sum_w 2^(c w) S_w   (bellman: `higher.double()` x c, then add)
     for (int w = sl.W - 1; w >= 0; w--) {
