@@ -31,6 +31,9 @@
 #ifndef ZA_ACC_G2_BLOCKS
 #define ZA_ACC_G2_BLOCKS 2
 #endif
+#ifndef ZA_PAIR_G2_BLOCKS
+#define ZA_PAIR_G2_BLOCKS 2
+#endif
 
 namespace za {
 
@@ -315,7 +318,7 @@ template <class F>
 static __device__ __forceinline__ const Affine<F>* pair_ptr(const Affine<F>* pts, uint32_t ref) { return pts + (ref & 0x7fffffffu); }
 
 template <class F, bool FIRST, int NT, int LP>
-__global__ void __launch_bounds__(NT, (sizeof(F) == sizeof(Fq) ? 512 : 256) / NT) msm_pair_round_kernel(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
+__global__ void __launch_bounds__(NT, (sizeof(F) == sizeof(Fq) ? 512 : ZA_PAIR_G2_BLOCKS * 128) / NT) msm_pair_round_kernel(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
                                                                   const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out,
                                                                   uint32_t nkeys, Affine<F>* __restrict__ out) {
     constexpr int FB = sizeof(F) == sizeof(Fq) ? 4 : 2;      // forward pass: loads of FB outputs in flight per thread
