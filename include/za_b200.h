@@ -179,7 +179,21 @@ int za_circuit_info(const za_circuit *circuit, uint32_t *info);
 /* Optional, once per (pk, circuit, rank): rebuild the proving key's fixed-base tables for exactly the point range
  * this rank owns in every query, with the window size chosen for the share (smaller shares want fewer buckets). */
 int za_pk_partition(za_ctx *ctx, za_pk *pk, const za_circuit *circuit, int rank, int world);
+/* The same with rank 0 taking only rank0_weight_permille / 1000 of an ordinary rank's share of the witness
+ * multiexps (L, A, B): rank 0 also runs the H-polynomial pipeline of stage 1 while the others already work. */
+/* The point-range rule itself (host only): [lo, hi) of `count` items for `rank`; 1000 = equal shares. */
+int za_share_weighted(uint64_t count, int rank, int world, uint32_t rank0_weight_permille, uint64_t *lo, uint64_t *hi);
+int za_pk_partition_weighted(za_ctx *ctx, za_pk *pk, const za_circuit *circuit, int rank, int world,
+                             uint32_t rank0_weight_permille);
 int za_prove_h_device(za_ctx *ctx, const za_circuit *circuit, const void *d_witness, void *d_h);
+/* Stage 2 in two asynchronous halves, so that the multiexps that do not depend on the H polynomial (ZA_MSM_WITNESS:
+ * L, A, B-G1, B-G2) run on every GPU while rank 0 still computes it; ZA_MSM_H (needs d_h on the rank's share)
+ * follows once the h scalars have arrived.  za_prove_msm_collect waits for all of them -> partials record. */
+#define ZA_MSM_WITNESS 1
+#define ZA_MSM_H 2
+int za_prove_msm_enqueue(za_ctx *ctx, const za_pk *pk, const za_circuit *circuit, const void *d_witness,
+                         const void *d_h, int rank, int world, int which);
+int za_prove_msm_collect(za_ctx *ctx, uint8_t *partials_out);
 int za_prove_msm_partials(za_ctx *ctx, const za_pk *pk, const za_circuit *circuit, const void *d_witness,
                           const void *d_h, int rank, int world, uint8_t *partials_out);
 int za_prove_assemble(const za_pk *pk, const uint8_t *partials, int world, const uint8_t *r, const uint8_t *s,

@@ -30,6 +30,26 @@ def test_share_rule_partitions_every_count():
             assert prev == count
 
 
+def test_weighted_share_rule():
+    """Rank 0 also runs the H pipeline, so it may take a smaller part of the witness multiexps: the ranges still
+    partition every count, equal weights reproduce the plain rule, and rank 0's share shrinks with its weight."""
+    import za_b200
+    for count in (0, 1, 5, 1000, (1 << 20) + 3):
+        for world in (1, 2, 4, 8):
+            for w in (1.0, 0.5, 0.106, 0.001):
+                prev = 0
+                for rank in range(world):
+                    lo, hi = za_b200.share_weighted(count, rank, world, w)
+                    assert lo == prev and hi >= lo
+                    if w == 1.0:
+                        assert (lo, hi) == za_b200.share(count, rank, world)
+                    prev = hi
+                assert prev == count
+    lo, hi = za_b200.share_weighted(8000, 0, 8, 0.106)
+    assert hi - lo == 8000 * 106 // 7106
+    assert za_b200.share_weighted(8000, 0, 8, 1.0) == (0, 1000)
+
+
 def _worker(rank, world, port, n, q):
     import za_b200
     os.environ["MASTER_ADDR"] = "127.0.0.1"

@@ -76,6 +76,10 @@ SYMBOLS = {
     "za_circuit_satisfied": (ci, [vp, vp, vp, vp, ctypes.POINTER(ctypes.c_int64)]),
     "za_circuit_info": (ci, [vp, vp]),
     "za_pk_partition": (ci, [vp, vp, vp, ci, ci]),
+    "za_pk_partition_weighted": (ci, [vp, vp, vp, ci, ci, ctypes.c_uint32]),
+    "za_share_weighted": (ci, [ctypes.c_uint64, ci, ci, ctypes.c_uint32, vp, vp]),
+    "za_prove_msm_enqueue": (ci, [vp, vp, vp, vp, vp, ci, ci, ci]),
+    "za_prove_msm_collect": (ci, [vp, vp]),
     "za_prove_h_device": (ci, [vp, vp, vp, vp]),
     "za_prove_msm_partials": (ci, [vp, vp, vp, vp, vp, ci, ci, vp]),
     "za_prove_assemble": (ci, [vp, vp, ci, vp, vp, vp]),

@@ -28,6 +28,7 @@ struct Pk {
     G2Affine beta_g2, gamma_g2, delta_g2;
     std::vector<G1Affine> ic;
     std::unique_ptr<Bases> h, l, a, b_g1, b_g2;
+    uint32_t rank0_weight = 1000;   // per mille: rank 0's share of the witness multiexps relative to the other ranks
 };
 
 

@@ -471,6 +471,19 @@ static inline void share(size_t cnt, int rank, int world, size_t& lo, size_t& hi
     lo = (size_t)(((unsigned __int128)cnt * (unsigned)rank) / (unsigned)world);
     hi = (size_t)(((unsigned __int128)cnt * (unsigned)(rank + 1)) / (unsigned)world);
 }
+// the same with rank 0 weighted w0 (per mille of an ordinary rank's share): rank 0 also runs the H-polynomial
+// pipeline, so it takes a smaller part of the witness multiexps (za_pk_partition_weighted)
+static inline void share_weighted(size_t cnt, int rank, int world, uint32_t w0, size_t& lo, size_t& hi) {
+    if (world == 1 || w0 == 1000) { share(cnt, rank, world, lo, hi); return; }
+    const unsigned __int128 total = (unsigned __int128)w0 + 1000u * (unsigned)(world - 1);
+    auto bound = [&](int k) -> size_t {
+        if (k <= 0) return 0;
+        if (k >= world) return cnt;
+        return (size_t)(((unsigned __int128)cnt * ((unsigned __int128)w0 + 1000u * (unsigned)(k - 1))) / total);
+    };
+    lo = bound(rank);
+    hi = bound(rank + 1);
+}
 
 template <class F>
 static void multiexp_enqueue(Ctx* ctx, int slot, const Bases* b, size_t offset, const uint32_t* d_scalars, size_t n, int share_sort = -1) {
@@ -492,24 +505,37 @@ static void check_query_lengths(const Pk* pk, const Circuit* c, size_t m) {
 // is ONE multiexp over the concatenated exponent vector (the sums a_inputs + a_aux etc. are all create_proof
 // uses).  Five multiexps are in flight: H, L, A, B(G1), B(G2) — the last two share one digit sort.  Each query
 // is cut by point range across ranks.
-static void prove_msms_enqueue(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* d_wit, const Fr* d_h, int rank, int world) {
+enum { MSM_WITNESS = 1, MSM_H = 2 };     // za_prove_msm_enqueue `which`
+static void prove_msms_enqueue(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* d_wit, const Fr* d_h, int rank, int world,
+                               int which = MSM_WITNESS | MSM_H) {
     const uint32_t ni = c->ni, na = c->na;
     const size_t m = domain_size(c, nullptr);
     check_query_lengths(pk, c, m);
     const uint8_t* d_aux = d_wit + (size_t)ni * 32;
+    const uint32_t w0 = world > 1 ? pk->rank0_weight : 1000u;
     size_t lo, hi;
-    // G2 first: its (longest) bucket reduction then overlaps the G1 accumulations on the side stream
-    const uint32_t* sb = gather(ctx, d_wit, c->b_cat_idx, c->b_cat_total, ctx->scratch[13]);
-    share(c->b_cat_total, rank, world, lo, hi);
-    multiexp_enqueue<Fq>(ctx, 3, pk->b_g1.get(), lo, sb + lo * 8, hi - lo);
-    multiexp_enqueue<Fq2>(ctx, 4, pk->b_g2.get(), lo, sb + lo * 8, hi - lo, hi - lo > 64 ? 3 : -1);
-    share(m - 1, rank, world, lo, hi);
-    multiexp_enqueue<Fq>(ctx, 0, pk->h.get(), lo, (const uint32_t*)(d_h + lo), hi - lo);
-    share(na, rank, world, lo, hi);
-    multiexp_enqueue<Fq>(ctx, 1, pk->l.get(), lo, (const uint32_t*)(d_aux + lo * 32), hi - lo);
-    const uint32_t* sa = gather(ctx, d_wit, c->a_cat_idx, c->a_cat_total, ctx->scratch[12]);
-    share(c->a_cat_total, rank, world, lo, hi);
-    multiexp_enqueue<Fq>(ctx, 2, pk->a.get(), lo, sa + lo * 8, hi - lo);
+    if (which & MSM_WITNESS) {
+        // G2 first: its (longest) bucket reduction then overlaps the G1 accumulations on the side stream
+        const uint32_t* sb = gather(ctx, d_wit, c->b_cat_idx, c->b_cat_total, ctx->scratch[13]);
+        share_weighted(c->b_cat_total, rank, world, w0, lo, hi);
+        multiexp_enqueue<Fq>(ctx, 3, pk->b_g1.get(), lo, sb + lo * 8, hi - lo);
+        multiexp_enqueue<Fq2>(ctx, 4, pk->b_g2.get(), lo, sb + lo * 8, hi - lo, hi - lo > 64 ? 3 : -1);
+    }
+    if ((which & MSM_H) && (which & MSM_WITNESS)) {
+        share(m - 1, rank, world, lo, hi);
+        multiexp_enqueue<Fq>(ctx, 0, pk->h.get(), lo, (const uint32_t*)(d_h + lo), hi - lo);
+    }
+    if (which & MSM_WITNESS) {
+        share_weighted(na, rank, world, w0, lo, hi);
+        multiexp_enqueue<Fq>(ctx, 1, pk->l.get(), lo, (const uint32_t*)(d_aux + lo * 32), hi - lo);
+        const uint32_t* sa = gather(ctx, d_wit, c->a_cat_idx, c->a_cat_total, ctx->scratch[12]);
+        share_weighted(c->a_cat_total, rank, world, w0, lo, hi);
+        multiexp_enqueue<Fq>(ctx, 2, pk->a.get(), lo, sa + lo * 8, hi - lo);
+    }
+    if ((which & MSM_H) && !(which & MSM_WITNESS)) {
+        share(m - 1, rank, world, lo, hi);
+        multiexp_enqueue<Fq>(ctx, 0, pk->h.get(), lo, (const uint32_t*)(d_h + lo), hi - lo);
+    }
 }
 // second half of prove_msms: wait for the five multiexps in completion order and combine their windows
 static void prove_msms_collect(Ctx* ctx, Partials& out) {
@@ -887,24 +913,39 @@ int za_pk_synthetic(za_ctx* ctx, const uint32_t* counts, za_pk** out) {
 
 // One process per GPU: rebuild the fixed-base tables of `pk` for the point range rank `rank` of `world` owns in
 // every query (the shares za_prove_msm_partials uses), with the window size chosen for the share.
-int za_pk_partition(za_ctx* ctx, za_pk* pk, const za_circuit* circuit, int rank, int world) {
+int za_share_weighted(uint64_t count, int rank, int world, uint32_t rank0_weight_permille, uint64_t* lo, uint64_t* hi) {
+    if (!lo || !hi || world < 1 || rank < 0 || rank >= world || rank0_weight_permille < 1 || rank0_weight_permille > 1000)
+        return fail(ZA_ERR_INVALID, "bad argument");
+    size_t a, b;
+    share_weighted((size_t)count, rank, world, rank0_weight_permille, a, b);
+    *lo = a; *hi = b;
+    return ZA_OK;
+}
+
+int za_pk_partition_weighted(za_ctx* ctx, za_pk* pk, const za_circuit* circuit, int rank, int world, uint32_t rank0_weight_permille) {
     if (!ctx || !pk || !circuit) return fail(ZA_ERR_INVALID, "NULL argument");
     if (world < 1 || rank < 0 || rank >= world) return fail(ZA_ERR_INVALID, "bad rank/world");
+    if (rank0_weight_permille < 1 || rank0_weight_permille > 1000) return fail(ZA_ERR_INVALID, "rank-0 weight must be in [1, 1000] per mille");
     ZA_TRY
     ZA_CUDA(cudaSetDevice(ctx->c.device));
     Pk* p = pk->p.get();
     const Circuit* c = circuit->c.get();
     const size_t m = domain_size(c, nullptr);
     check_query_lengths(p, c, m);
+    p->rank0_weight = rank0_weight_permille;
+    const uint32_t w0 = world > 1 ? rank0_weight_permille : 1000u;
     size_t lo, hi;
     share(m - 1, rank, world, lo, hi); bases_build_table(&ctx->c, p->h.get(), lo, hi - lo);
-    share(c->na, rank, world, lo, hi); bases_build_table(&ctx->c, p->l.get(), lo, hi - lo);
-    share(c->a_cat_total, rank, world, lo, hi); bases_build_table(&ctx->c, p->a.get(), lo, hi - lo);
-    share(c->b_cat_total, rank, world, lo, hi);
+    share_weighted(c->na, rank, world, w0, lo, hi); bases_build_table(&ctx->c, p->l.get(), lo, hi - lo);
+    share_weighted(c->a_cat_total, rank, world, w0, lo, hi); bases_build_table(&ctx->c, p->a.get(), lo, hi - lo);
+    share_weighted(c->b_cat_total, rank, world, w0, lo, hi);
     bases_build_table(&ctx->c, p->b_g1.get(), lo, hi - lo);
     bases_build_table(&ctx->c, p->b_g2.get(), lo, hi - lo);
     return ZA_OK;
     ZA_CATCH
+}
+int za_pk_partition(za_ctx* ctx, za_pk* pk, const za_circuit* circuit, int rank, int world) {
+    return za_pk_partition_weighted(ctx, pk, circuit, rank, world, 1000);
 }
 
 int za_circuit_satisfied(za_ctx* ctx, const za_circuit* circuit, const uint8_t* inputs, const uint8_t* aux, int64_t* first_bad) {
@@ -975,6 +1016,31 @@ int za_prove_msm_partials(za_ctx* ctx, const za_pk* pk, const za_circuit* circui
     ZA_CUDA(cudaSetDevice(ctx->c.device));
     Partials P;
     prove_msms(&ctx->c, pk->p.get(), circuit->c.get(), (const uint8_t*)d_witness, (const Fr*)d_h, rank, world, P);
+    partials_to_le(P, partials_out);
+    return ZA_OK;
+    ZA_CATCH
+}
+
+int za_prove_msm_enqueue(za_ctx* ctx, const za_pk* pk, const za_circuit* circuit, const void* d_witness, const void* d_h, int rank, int world,
+                         int which) {
+    if (!ctx || !pk || !circuit || !d_witness) return fail(ZA_ERR_INVALID, "NULL argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(ZA_ERR_INVALID, "bad rank/world");
+    if (!(which & (MSM_WITNESS | MSM_H)) || ((which & MSM_H) && !d_h)) return fail(ZA_ERR_INVALID, "bad multiexp selection");
+    ZA_TRY
+    ZA_CUDA(cudaSetDevice(ctx->c.device));
+    prove_msms_enqueue(&ctx->c, pk->p.get(), circuit->c.get(), (const uint8_t*)d_witness, (const Fr*)d_h, rank, world, which);
+    return ZA_OK;
+    ZA_CATCH
+}
+
+int za_prove_msm_collect(za_ctx* ctx, uint8_t* partials_out) {
+    if (!ctx || !partials_out) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    ZA_CUDA(cudaSetDevice(ctx->c.device));
+    for (int s : {0, 1, 2, 3, 4})
+        if (!ctx->c.slots[s].busy) return fail(ZA_ERR_INVALID, "za_prove_msm_collect: multiexp %d was not enqueued", s);
+    Partials P;
+    prove_msms_collect(&ctx->c, P);
     partials_to_le(P, partials_out);
     return ZA_OK;
     ZA_CATCH

@@ -212,9 +212,12 @@ class Parameters:
         check(lib().za_pk_synthetic(ctx.h, c, ctypes.byref(hd)))
         return cls(ctx, hd)
 
-    def partition(self, circuit, rank, world):
-        """One process per GPU: keep fixed-base tables only for the point range this rank owns (za_pk_partition)."""
-        check(lib().za_pk_partition(self.ctx.h, self.h, circuit.h, rank, world))
+    def partition(self, circuit, rank, world, rank0_weight=1.0):
+        """One process per GPU: keep fixed-base tables only for the point range this rank owns (za_pk_partition).
+        rank0_weight < 1: rank 0 (which also runs the H-polynomial pipeline) takes that fraction of an ordinary
+        rank's share of the witness multiexps (za_pk_partition_weighted)."""
+        w = max(1, min(1000, int(round(rank0_weight * 1000))))
+        check(lib().za_pk_partition_weighted(self.ctx.h, self.h, circuit.h, rank, world, w))
 
     def counts(self):
         c = (ctypes.c_uint32 * 6)()
@@ -365,6 +368,21 @@ def prove_msm_partials(ctx, params, circuit, d_witness, d_h, rank, world):
     return out
 
 
+MSM_WITNESS, MSM_H = 1, 2
+
+
+def prove_msm_enqueue(ctx, params, circuit, d_witness, d_h, rank, world, which=MSM_WITNESS | MSM_H):
+    """Stage 2, asynchronous: enqueue the witness multiexps (L, A, B) and / or the H multiexp of this rank's range."""
+    check(lib().za_prove_msm_enqueue(ctx.h, params.h, circuit.h, ctypes.c_void_p(d_witness), ctypes.c_void_p(d_h), rank, world, which))
+
+
+def prove_msm_collect(ctx):
+    """Wait for the five enqueued multiexps -> PARTIALS_BYTES record."""
+    out = np.zeros(PARTIALS_BYTES, np.uint8)
+    check(lib().za_prove_msm_collect(ctx.h, _p(out)))
+    return out
+
+
 def prove_assemble(params, partials, r, s):
     """Stage 3 (host): add the per-rank partial records and assemble the proof."""
     partials = np.ascontiguousarray(partials, dtype=np.uint8).reshape(-1, PARTIALS_BYTES)
@@ -376,6 +394,14 @@ def prove_assemble(params, partials, r, s):
 def share(count, rank, world):
     """The contiguous [lo, hi) share of `count` items that rank owns (same rule as the library)."""
     return count * rank // world, count * (rank + 1) // world
+
+
+def share_weighted(count, rank, world, rank0_weight=1.0):
+    """[lo, hi) of `count` items for `rank` when rank 0 takes rank0_weight of an ordinary share (za_share_weighted)."""
+    w = max(1, min(1000, int(round(rank0_weight * 1000))))
+    lo, hi = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    check(lib().za_share_weighted(count, rank, world, w, ctypes.byref(lo), ctypes.byref(hi)))
+    return lo.value, hi.value
 
 
 def imad_peak(ctx):
