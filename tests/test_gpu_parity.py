@@ -341,6 +341,21 @@ def test_staged_prove_equals_single_call(ctx):
     pk.partition(circ, 1, 2)
     parts = [za_b200.prove_msm_partials(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), k, 2) for k in range(2)]
     assert za_b200.prove_assemble(pk, np.stack(parts), 5, 6) == ref
+    # weighted ranges (rank 0 also runs the H pipeline) and the two-phase enqueue: the witness multiexps first,
+    # the H multiexp once the h scalars are there, one collect
+    for world, w0 in ((2, 0.776), (4, 0.55), (8, 0.106), (3, 0.001)):
+        parts = []
+        for k in range(world):
+            pk.partition(circ, k, world, w0)
+            za_b200.prove_msm_enqueue(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), k, world, za_b200.MSM_WITNESS)
+            za_b200.prove_msm_enqueue(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), k, world, za_b200.MSM_H)
+            parts.append(za_b200.prove_msm_collect(ctx))
+        assert za_b200.prove_assemble(pk, np.stack(parts), 5, 6) == ref, (world, w0)
+    with pytest.raises(za_b200.ZaError):                     # collect without the H multiexp enqueued
+        za_b200.prove_msm_enqueue(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), 0, 2, za_b200.MSM_WITNESS)
+        za_b200.prove_msm_collect(ctx)
+    za_b200.prove_msm_enqueue(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), 0, 2, za_b200.MSM_H)
+    za_b200.prove_msm_collect(ctx)                           # drains the slots again
 
 
 @pytest.mark.parametrize("group,n", [(1, 5000), (1, 1 << 16), (2, 4096), (2, 20000)])
