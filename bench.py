@@ -207,10 +207,12 @@ def run_gpu(args):
         wit_dev.copy_(wit_host, non_blocking=True)
         return prove_device_step()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, after_warmup=None):
         for _ in range(warmup):
             fn()
         barrier()
+        if after_warmup:
+            after_warmup()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         out = None
@@ -231,14 +233,17 @@ def run_gpu(args):
     if sampler:
         sampler.start()
     # ---- headline: prove ms, witness resident
-    ctx.profile(True)
-    ctx.profile_read()
-    l0 = ctx.launch_count()
-    prove_ms, proof = timed(prove_device_step, K, W)
-    launches = (ctx.launch_count() - l0) // (K + W) * K
+    # per-kernel-class CUDA-event timing covers the K timed steps only (the warm-up steps allocate and page in code)
+    l0 = [0]
+    def start_profile():
+        ctx.profile(True)
+        ctx.profile_read()
+        l0[0] = ctx.launch_count()
+    prove_ms, proof = timed(prove_device_step, K, W, start_profile)
+    launches = ctx.launch_count() - l0[0]
     prof = ctx.profile_read()
     ctx.profile(False)
-    steps_profiled = K + W
+    steps_profiled = K
     # ---- e2e: host buffers
     e2e_ms, proof_e2e = timed(prove_e2e_step, K, W)
     if rank == 0:

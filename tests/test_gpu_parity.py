@@ -233,6 +233,30 @@ def test_create_proof_config2_2pow16(ctx):
     _prove_case(ctx, circuits.mul_chain_fast(nc, x0=0x5A410002), toxic, r=2 ** 200 + 17, s=2 ** 100 + 3)
 
 
+def test_create_proof_rejects_non_canonical_witness(ctx):
+    """A witness element >= r is refused (ZA_ERR_NOT_CANONICAL, first offending index named) — the range check runs on
+    the uploaded copy on the GPU — and the same call with the value reduced still proves."""
+    import za_b200
+    ni, na, ptr, var, coeff, inputs, aux = circuits.mul_chain(100, x0=7)
+    ocs = O.CS(ni, na, ptr, var, coeff)
+    prm = O.Params.generate(ocs, [3, 5, 7, 11, 13], threads=4)
+    pk = za_b200.Parameters.read(ctx, prm.write(), checked=True)
+    circ = za_b200.Circuit(ctx, ni, na, ptr, var, coeff)
+    bad_aux = aux.copy()
+    bad_aux[17] = np.frombuffer(P.R_MOD.to_bytes(32, "little"), np.uint8)          # == r
+    bad_aux[60] = 0xFF
+    with pytest.raises(za_b200.ZaError) as e:
+        za_b200.create_proof(ctx, pk, circ, inputs, bad_aux, 5, 6)
+    assert e.value.code == -10 and "aux[17]" in str(e.value)
+    bad_in = inputs.copy()
+    bad_in[1] = 0xFF
+    with pytest.raises(za_b200.ZaError) as e:
+        za_b200.create_proof(ctx, pk, circ, bad_in, aux, 5, 6)
+    assert e.value.code == -10 and "inputs[1]" in str(e.value)
+    rc, exp = prm.create_proof(ocs, inputs, aux, 5, 6, threads=4)
+    assert rc == 0 and za_b200.create_proof(ctx, pk, circ, inputs, aux, 5, 6) == exp
+
+
 def test_pk_load_rejects_bad_streams(ctx):
     import za_b200
     cs = P.example_factor_circuit()

@@ -30,6 +30,7 @@ Ctx::~Ctx() {
         if (sl.side) cudaStreamDestroy(sl.side);
     }
     if (side) cudaStreamDestroy(side);
+    if (host_flag) cudaFreeHost(host_flag);
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 

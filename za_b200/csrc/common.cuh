@@ -108,6 +108,7 @@ struct Ctx {
     DevBuf scratch[16];
     MsmSlot slots[8];
     cudaStream_t side = nullptr;        // bucket reductions overlap the next multiexp's accumulation here
+    unsigned long long* host_flag = nullptr;   // pinned: verdict of the witness range check of create_proof
     uint64_t launches = 0;              // kernels launched through this context (bench: gpu_launches)
     // optional per-kernel-class timing with CUDA events on `stream` (bench.py roofline numbers)
     bool profile = false;

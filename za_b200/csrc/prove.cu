@@ -656,16 +656,49 @@ static void create_proof_device(Ctx* ctx, const Pk* pk, const Circuit* c, const 
     if (timeline) { t4 = now(); fprintf(stderr, "[za timeline] after H: enqueue %.3f ms, host pre %.3f, wait+combine %.3f, host post %.3f\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3); }
 }
 
+// index of the first element >= r in a vector of canonical-form candidates (atomicMin; ~0 if all are canonical)
+__global__ void fr_canonical_check_kernel(const uint32_t* __restrict__ v, size_t n, unsigned long long* first_bad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* p = reinterpret_cast<const uint4*>(v + 8 * i);
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (!fp_is_canonical<FrParams>(w)) atomicMin(first_bad, (unsigned long long)i);
+}
+
 static void create_proof(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* inputs, const uint8_t* aux, const uint8_t* r_le,
                          const uint8_t* s_le, uint8_t* proof_out, za_trace* tr) {
     cudaStream_t st = ctx->stream;
     const uint32_t ni = c->ni, na = c->na;
-    check_scalars_canonical(inputs, ni, "inputs"); check_scalars_canonical(aux, na, "aux");
     DevBuf& wit = ctx->scratch[10];
     wit.ensure(((size_t)ni + na) * 32);
     ZA_CUDA(cudaMemcpyAsync(wit.p, inputs, (size_t)ni * 32, cudaMemcpyHostToDevice, st));
     if (na) ZA_CUDA(cudaMemcpyAsync((uint8_t*)wit.p + (size_t)ni * 32, aux, (size_t)na * 32, cudaMemcpyHostToDevice, st));
-    create_proof_device(ctx, pk, c, (const uint8_t*)wit.p, r_le, s_le, proof_out, tr);
+    // "is every witness element < r" is checked on the uploaded copy (a pass over 32 MB on the host would sit in
+    // front of every proof); the verdict travels back behind the upload and is read once the proof is done
+    DevBuf& bad = ctx->scratch[14];
+    bad.ensure(64);
+    if (!ctx->host_flag) ZA_CUDA(cudaHostAlloc((void**)&ctx->host_flag, 64, cudaHostAllocDefault));
+    ZA_CUDA(cudaMemsetAsync(bad.p, 0xff, 8, st));
+    fr_canonical_check_kernel<<<nblk((size_t)ni + na, 256), 256, 0, st>>>((const uint32_t*)wit.p, (size_t)ni + na, bad.as<unsigned long long>());
+    ctx->launches++;
+    ZA_CUDA(cudaGetLastError());
+    ZA_CUDA(cudaMemcpyAsync(ctx->host_flag, bad.p, 8, cudaMemcpyDeviceToHost, st));
+    try {
+        create_proof_device(ctx, pk, c, (const uint8_t*)wit.p, r_le, s_le, proof_out, tr);
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        if (*ctx->host_flag == ~0ull) throw;      // otherwise the non-canonical element below is the root cause
+    }
+    ZA_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long first_bad = *ctx->host_flag;
+    if (first_bad != ~0ull) {
+        memset(proof_out, 0, 256);
+        char b[128];
+        if (first_bad < ni) snprintf(b, sizeof b, "inputs[%llu] is not a canonical Fr element (>= r)", first_bad);
+        else snprintf(b, sizeof b, "aux[%llu] is not a canonical Fr element (>= r)", first_bad - ni);
+        throw ZaError(ZA_ERR_NOT_CANONICAL, b);
+    }
 }
 
 // synthetic proving key: every base is a known multiple of the generator (bench + full-size property tests)
