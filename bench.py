@@ -257,11 +257,18 @@ def run_gpu(args):
         acc1, acc2, nttp = prof["msm_accumulate_g1"], prof["msm_accumulate_g2"], prof["ntt"]
         # dominant kernel of the step: the G1/G2 bucket-accumulation kernels (integer-pipe bound)
         dom = acc1 if acc1["ms"] >= acc2["ms"] else acc2
-        dom_name = "msm_accumulate_kernel<Fq>" if dom is acc1 else "msm_pair_round_kernel<Fq2> x4 + msm_accumulate_kernel<Fq2>"
+        dom_name = "msm_accumulate_g1_sm_kernel (G1 bucket accumulation, XYZZ mixed additions)" if dom is acc1 else "msm_pair_round_kernel<Fq2> x4 + msm_accumulate_kernel<Fq2>"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if dom is acc1 and log_m == 20 and world == 1 and os.path.exists(tpath):
+            t = json.load(open(tpath)).get("msm_accumulate_g1_sm_kernel")
+            if t:
+                traffic = int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
         imads = dom["work"] * IMAD_PER_MODMUL
         achieved = imads / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else 0.0
         roofline = {"bound": "imad", "kernel": dom_name, "achieved": achieved, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
-                    "frac": achieved / (imad_peak / 1e12) if imad_peak else None, "traffic": None,
+                    "frac": achieved / (imad_peak / 1e12) if imad_peak else None, "traffic": traffic,
+                    "traffic_note": "DRAM read+write bytes per launch from the ncu --set full capture of the same 2^20 workload (profiles/r01_traffic.json); null for other sizes",
                     "peak_source": "measured in this run (za_imad_peak: dependency-free mad.lo.u32 on all SMs)",
                     "algorithmic": f"{int(dom['work'] / max(dom['spans'], 1))} Fq products (10 per XYZZ mixed addition) x {IMAD_PER_MODMUL} IMAD per launch",
                     "launch_ms": dom["ms"] / max(dom["spans"], 1), "share_of_step": dom["ms"] / steps_profiled / prove_ms,

@@ -254,6 +254,146 @@ __global__ void __launch_bounds__(128, (sizeof(F) == sizeof(Fq) ? ZA_ACC_G1_BLOC
 }
 
 
+// K5 (G1): the same chunked accumulation with the thread's working set — the XYZZ accumulator, the two point
+// buffers and five temporaries — kept in SHARED memory, and a field product that takes three shared-memory
+// addresses.  Measured reason (profiles/r01_session3.md): with the product as a by-value call, every call costs
+// ~32 IMAD.MOV register moves (16 argument words in, 8 result words out, plus rotation), ptxas issues those moves on
+// the integer-multiply pipe (fmaheavy, 2 cycles each), and that pipe is the kernel's bound: 82 % busy for 70 % of
+// algorithmic IMAD.  Operands that live in shared memory are loaded straight into the registers the product reads
+// (LDS.128 on the otherwise idle LSU pipe) and the result is stored from the registers it is produced in.
+// Variable v of thread t: chunk c (16 bytes) at ((2 v + c) * 128 + t) * 16 — a warp's access is 512 contiguous bytes.
+// The next point travels into the other point buffer with cp.async while the current one is added.
+#define ACC_SM_NT 128
+enum { AV_X = 0, AV_Y, AV_ZZ, AV_ZZZ, AV_PX0, AV_PY0, AV_PX1, AV_PY1, AV_P, AV_R, AV_PP, AV_PPP, AV_Q, AV_COUNT };
+#define ACC_SM_BYTES (AV_COUNT * 32 * ACC_SM_NT)
+static __device__ __forceinline__ Fq sm_ld(uint32_t a) {
+    Fq r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]) : "r"(a) : "memory");
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "r"(a + ACC_SM_NT * 16) : "memory");
+    return r;
+}
+static __device__ __forceinline__ void sm_st(uint32_t a, const Fq& r) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a + ACC_SM_NT * 16), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7]) : "memory");
+}
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ void fq_mul_sm(uint32_t d, uint32_t a, uint32_t b) { sm_st(d, fp_mul<FqParams>(sm_ld(a), sm_ld(b))); }
+#else
+static inline void fq_mul_sm(uint32_t, uint32_t, uint32_t) {}
+#endif
+static __device__ __forceinline__ void cp_async16_sm(uint32_t smem_addr, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+static __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool DIRECT>
+__global__ void __launch_bounds__(ACC_SM_NT, 4) msm_accumulate_g1_sm_kernel(const Affine<Fq>* __restrict__ bases, const uint32_t* __restrict__ entries,
+                                                                             const uint32_t* __restrict__ offsets, uint32_t nkeys, uint32_t Lc,
+                                                                             XYZZ<Fq>* bucket_sums, XYZZ<Fq>* part_head, XYZZ<Fq>* part_tail,
+                                                                             uint32_t* tail_owner_key) {
+    extern __shared__ uint4 acc_sm[];
+    const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t E = offsets[nkeys];
+    const uint64_t start64 = (uint64_t)chunk * Lc;
+    if (start64 >= E) return;
+    const uint32_t start = (uint32_t)start64;
+    const uint32_t end = (uint64_t)start + Lc < E ? start + Lc : E;
+    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(acc_sm) + threadIdx.x * 16;
+    auto var = [&](int v) { return sm0 + (uint32_t)v * (2 * ACC_SM_NT * 16); };
+    uint32_t lo = 0, hi = nkeys;                    // last key with offsets[key] <= start (non-empty by construction)
+    while (lo + 1 < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= start) lo = mid; else hi = mid;
+    }
+    uint32_t key = lo;
+    bool head_open = offsets[key] < start;
+    uint32_t bend = offsets[key + 1];
+    bool acc_inf = true;
+    auto fetch = [&](uint32_t e, uint32_t buf) {     // point e -> point buffer `buf` (x: 2 chunks, y: 2 chunks)
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(bases + (e & 0x7fffffffu));
+        const uint32_t px = var(AV_PX0 + 2 * (int)buf), py = var(AV_PY0 + 2 * (int)buf);
+        cp_async16_sm(px, src); cp_async16_sm(px + ACC_SM_NT * 16, src + 16);
+        cp_async16_sm(py, src + 32); cp_async16_sm(py + ACC_SM_NT * 16, src + 48);
+    };
+    uint32_t e = DIRECT ? start : entries[start];
+    fetch(e, start & 1u);
+    cp_async_commit();
+    for (uint32_t pos = start; pos < end; pos++) {
+        const uint32_t e_cur = e;
+        const uint32_t buf = pos & 1u;
+        if (pos + 1 < end) {                         // the next point travels while this one is added
+            e = DIRECT ? pos + 1 : entries[pos + 1];
+            fetch(e, buf ^ 1u);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        const uint32_t vx = var(AV_PX0 + 2 * (int)buf), vy = var(AV_PY0 + 2 * (int)buf);
+        const bool negate = !DIRECT && (e_cur >> 31) != 0;
+        bool skip = false;
+        if (DIRECT) { const Fq x = sm_ld(vx), y = sm_ld(vy); skip = x.is_zero() && y.is_zero(); }
+        if (!skip) {
+            if (acc_inf) {
+                Fq y = sm_ld(vy);
+                if (negate) y = -y;
+                sm_st(var(AV_X), sm_ld(vx)); sm_st(var(AV_Y), y);
+                sm_st(var(AV_ZZ), Fq::one()); sm_st(var(AV_ZZZ), Fq::one());
+                acc_inf = false;
+            } else {
+                fq_mul_sm(var(AV_P), vx, var(AV_ZZ));                 // U2
+                fq_mul_sm(var(AV_R), vy, var(AV_ZZZ));                // S2
+                const Fq P = sm_ld(var(AV_P)) - sm_ld(var(AV_X));
+                Fq S2 = sm_ld(var(AV_R));
+                if (negate) S2 = -S2;
+                const Fq R = S2 - sm_ld(var(AV_Y));
+                if (P.is_zero()) {                                     // rare: the same point again, or its negative
+                    if (R.is_zero()) {
+                        Fq y = sm_ld(vy);
+                        if (negate) y = -y;
+                        const XYZZ<Fq> d = xyzz_dbl_affine<Fq>(sm_ld(vx), y);
+                        sm_st(var(AV_X), d.X); sm_st(var(AV_Y), d.Y); sm_st(var(AV_ZZ), d.ZZ); sm_st(var(AV_ZZZ), d.ZZZ);
+                    } else {
+                        acc_inf = true;
+                    }
+                } else {
+                    sm_st(var(AV_P), P); sm_st(var(AV_R), R);
+                    fq_mul_sm(var(AV_PP), var(AV_P), var(AV_P));
+                    fq_mul_sm(var(AV_PPP), var(AV_P), var(AV_PP));
+                    fq_mul_sm(var(AV_Q), var(AV_X), var(AV_PP));
+                    fq_mul_sm(var(AV_P), var(AV_R), var(AV_R));       // R^2 (P is dead)
+                    const Fq Q = sm_ld(var(AV_Q));
+                    const Fq X3 = sm_ld(var(AV_P)) - sm_ld(var(AV_PPP)) - dbl(Q);
+                    sm_st(var(AV_X), X3);
+                    sm_st(var(AV_P), Q - X3);
+                    fq_mul_sm(var(AV_P), var(AV_R), var(AV_P));       // R (Q - X3)
+                    fq_mul_sm(var(AV_Q), var(AV_Y), var(AV_PPP));     // Y1 PPP
+                    sm_st(var(AV_Y), sm_ld(var(AV_P)) - sm_ld(var(AV_Q)));
+                    fq_mul_sm(var(AV_ZZ), var(AV_ZZ), var(AV_PP));
+                    fq_mul_sm(var(AV_ZZZ), var(AV_ZZZ), var(AV_PPP));
+                }
+            }
+        }
+        const uint32_t nxt = pos + 1;
+        if (nxt == bend || nxt == end) {
+            const bool closes = nxt == bend;
+            XYZZ<Fq> acc = XYZZ<Fq>::inf();
+            if (!acc_inf) { acc.X = sm_ld(var(AV_X)); acc.Y = sm_ld(var(AV_Y)); acc.ZZ = sm_ld(var(AV_ZZ)); acc.ZZZ = sm_ld(var(AV_ZZZ)); }
+            if (!head_open && closes) st_vec(bucket_sums + key, acc);
+            else if (head_open) st_vec(part_head + chunk, acc);
+            else { st_vec(part_tail + chunk, acc); tail_owner_key[chunk] = key; }
+            head_open = false;
+            acc_inf = true;
+            if (nxt < end) {
+                do { key++; } while (offsets[key + 1] <= nxt);
+                bend = offsets[key + 1];
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+
 // K5a: batched-affine pair rounds.  One round halves every bucket: the k points of a bucket become ceil(k/2)
 // by adding neighbours pairwise in AFFINE coordinates — lambda = (y1-y0)/(x1-x0), 6 field products per addition
 // instead of the 10 of the XYZZ mixed addition — with all the divisions of a WARP (32 x LP) sharing ONE field
@@ -584,6 +724,7 @@ __global__ void __launch_bounds__(128) msm_naive_kernel(const Affine<F>* __restr
                                                         XYZZ<F>* out) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned lane = threadIdx.x & 31;
+    if (warp * 32 >= n) return;                      // whole warps past the end (the CTA has four): `out` has ceil(n/32) slots
     const uint32_t i = warp * 32 + lane;
     XYZZ<F> acc = XYZZ<F>::inf();
     if (i < n) {
@@ -1007,8 +1148,25 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
             cur_pts = nxt_pts;
             cur_off = nxt_off;
         }
-        if (rounds) msm_accumulate_kernel<F, true><<<nblk(nchunks, 128), 128, 0, st>>>(cur_pts, nullptr, cur_off, nkeys, Lc, d_buckets, d_head, d_tail, d_owner);
-        else msm_accumulate_kernel<F, false><<<nblk(nchunks, 128), 128, 0, st>>>(d_bases, d_entries, d_offsets, nkeys, Lc, d_buckets, d_head, d_tail, d_owner);
+        // G1: working set in shared memory (msm_accumulate_g1_sm_kernel); ZA_MSM_ACC_SM=0 selects the register version
+        static const bool acc_sm = !(getenv("ZA_MSM_ACC_SM") && atoi(getenv("ZA_MSM_ACC_SM")) == 0);
+        bool launched = false;
+        if constexpr (sizeof(F) == sizeof(Fq)) {
+            if (acc_sm) {
+                if (rounds) {
+                    ZA_CUDA(cudaFuncSetAttribute(msm_accumulate_g1_sm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACC_SM_BYTES));
+                    msm_accumulate_g1_sm_kernel<true><<<nblk(nchunks, ACC_SM_NT), ACC_SM_NT, ACC_SM_BYTES, st>>>(cur_pts, nullptr, cur_off, nkeys, Lc, d_buckets, d_head, d_tail, d_owner);
+                } else {
+                    ZA_CUDA(cudaFuncSetAttribute(msm_accumulate_g1_sm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACC_SM_BYTES));
+                    msm_accumulate_g1_sm_kernel<false><<<nblk(nchunks, ACC_SM_NT), ACC_SM_NT, ACC_SM_BYTES, st>>>(d_bases, d_entries, d_offsets, nkeys, Lc, d_buckets, d_head, d_tail, d_owner);
+                }
+                launched = true;
+            }
+        }
+        if (!launched) {
+            if (rounds) msm_accumulate_kernel<F, true><<<nblk(nchunks, 128), 128, 0, st>>>(cur_pts, nullptr, cur_off, nkeys, Lc, d_buckets, d_head, d_tail, d_owner);
+            else msm_accumulate_kernel<F, false><<<nblk(nchunks, 128), 128, 0, st>>>(d_bases, d_entries, d_offsets, nkeys, Lc, d_buckets, d_head, d_tail, d_owner);
+        }
         ctx->launches++;
         d_offsets_final = cur_off;
     }
