@@ -31,6 +31,7 @@ IMAD_PER_MODMUL = 264          # 8x32-bit-limb Montgomery product, 
 # The accumulation kernels report their algorithmic work in Fq products (za_ctx_profile_read): an XYZZ mixed
 # addition is 8M + 2S = 10 (over Fq2: 8 x 3 + 2 x 2 = 28), a batched-affine addition of the G2 pair rounds
 # 5M + 1S over Fq2 = 17.
+R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617   # compiler/src/algebra/fs.rs:15-16
 R_FIXED = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF1234567890AB
 S_FIXED = 0x0FEDCBA9876543210FEDCBA9876543210FEDCBA9876543210FEDCBA98765
 
@@ -354,6 +355,31 @@ def run_gpu(args):
                              "imad_frac": IMAD_PER_MODMUL * (n_ntt / 2) * args.log_ntt / (ntt_ms * 1e-3) / ipk,
                              "order": "natural in, natural out, forward"}
             del v
+        if world == 1 and args.log_setup > 0:
+            # the rows either side of create_proof on a REAL key: generate_parameters on the
+            # GPU -> Parameters::write stream -> Parameters::read(checked) -> create_proof (host buffers) -> verify_proof
+            log_s = min(log_m, args.log_setup)
+            nc_s = (1 << log_s) - 2
+            ni2, na2, ptr2, var2, coeff2, in2, aux2 = synthetic.mul_chain(nc_s, x0=0x5A410002)
+            circ2 = za_b200.Circuit(ctx, ni2, na2, ptr2, var2, coeff2)
+            t0 = time.perf_counter()
+            blob = za_b200.generate_parameters(ctx, circ2, 0x5A410011, 0x5A410012, 0x5A410013, 0x5A410014, 0x5A410015)
+            t1 = time.perf_counter()
+            pk2 = za_b200.Parameters.read(ctx, blob, checked=True)
+            t2 = time.perf_counter()
+            pr2 = za_b200.create_proof(ctx, pk2, circ2, in2, aux2, R_FIXED, S_FIXED)      # first call: buffers are allocated
+            t3 = time.perf_counter()
+            pr2 = za_b200.create_proof(ctx, pk2, circ2, in2, aux2, R_FIXED, S_FIXED)
+            t4 = time.perf_counter()
+            pub = [int.from_bytes(in2[i].tobytes(), "little") for i in range(1, ni2)]
+            ok = za_b200.verify_proof(pk2.vk(), pr2, pub)
+            t5 = time.perf_counter()
+            bad = za_b200.verify_proof(pk2.vk(), pr2, [(pub[0] + 1) % R_MOD] + pub[1:])
+            sub["real_key_pipeline"] = {"log_m": log_s, "parameters_bytes": len(blob), "generate_parameters_ms": (t1 - t0) * 1e3,
+                                        "parameters_read_checked_ms": (t2 - t1) * 1e3, "create_proof_host_buffers_ms": (t4 - t3) * 1e3,
+                                        "verify_proof_host_ms": (t5 - t4) * 1e3, "proof_verifies": bool(ok),
+                                        "wrong_public_input_rejected": bool(not bad), "timing": "host wall clock, one call each"}
+            del pk2, circ2, blob
         if line is not None:
             line["submetrics"] = sub
 
@@ -416,6 +442,7 @@ def main():
     ap.add_argument("--log-m", dest="log_m", type=int, default=20, help="log2 of the evaluation domain of the prove workload")
     ap.add_argument("--log-msm", dest="log_msm", type=int, default=24)
     ap.add_argument("--log-ntt", dest="log_ntt", type=int, default=24)
+    ap.add_argument("--log-setup", dest="log_setup", type=int, default=18, help="domain of the real-key pipeline sub-metric (0 = skip)")
     ap.add_argument("--cpu-log-m", dest="cpu_log_m", type=int, default=20, help="domain of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the MSM / NTT sub-metrics")
