@@ -77,6 +77,9 @@ struct NttDomain {
 // stream, bucket reduction on the side stream) and their window sums collected at the end.
 struct MsmSlot {
     DevBuf counts, entries, buckets, parts, segs;
+    DevBuf red;                          // row / column bucket reduction: stage buffers, row sums, six results per bucket space
+    int red_mode = 0, red_k = 0;         // 1: row / column reduction (K6'), host_win holds 6 points per bucket space
+    uint32_t red_H = 0, red_Lw = 0;
     DevBuf pair_pts[2], pair_offs;       // batched-affine pair rounds: ping-pong point buffers, per-round bucket offsets
     int rounds = 0;
     void* host_win = nullptr;            // pinned: window sums (+ entry count when profiling)

@@ -717,6 +717,120 @@ __global__ void __launch_bounds__(128) msm_group_reduce_kernel(const XYZZ<F>* __
     if (lane == 0) st_vec(out + warp, acc);
 }
 
+// K6' — row / column bucket reduction.  The hierarchical running-sum reduction above is a chain of ~100 dependent
+// group additions and ~90 doublings (1.4 ms for 2^19 buckets with the GPU otherwise idle behind the last multiexp, and
+// the dominant cost of a multi-GPU proof, where every rank still reduces all its buckets).  With the bucket index
+// split as i = hi * 2^k + lo,
+//     sum_i (i + 1) S_i = 2^k * sum_hi hi R_hi + sum_lo (lo + 1) C_lo,   R_hi = sum_lo S_i (row sums), C_lo = sum_hi S_i (column sums):
+// two PLAIN sums over all buckets (trees of eight-way stages: the same ~2 additions per bucket, every lane busy,
+// depth ~22) and two weighted sums over at most 1024 points each, which one CTA computes with a suffix scan
+// (sum_i i X_i = sum_{j>=1} suffix_j).  Measured at 2^19 buckets: 1.37 -> 0.90 ms (G1), 3.71 -> 2.61 ms (G2).
+// K6'a: one stage of a strided sum: out[w][g][lo] = sum_{t<f} in[w][g*f + t][lo].  Column sums: w = bucket space,
+// rows of `width` = 2^k points.  Row sums: w = row, width = 1.
+template <class F>
+__global__ void __launch_bounds__(128) msm_colsum_kernel(const XYZZ<F>* __restrict__ in, uint32_t rows_in, uint32_t width, uint32_t f, uint32_t rows_out,
+                                                         uint32_t total, XYZZ<F>* out) {
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    const uint32_t per_w = rows_out * width;
+    const uint32_t w = id / per_w, rem = id % per_w, g = rem / width, lo = rem % width;
+    const XYZZ<F>* base = in + ((size_t)w * rows_in + (size_t)g * f) * width + lo;
+    XYZZ<F> acc = ld_vec(base);
+    for (uint32_t t = 1; t < f; t++) {
+        XYZZ<F> v = ld_vec(base + (size_t)t * width);
+        xyzz_add<F>(acc, v);
+    }
+    st_vec(out + ((size_t)w * rows_out + g) * width + lo, acc);
+}
+
+template <class F>
+static __device__ __forceinline__ XYZZ<F> shfl_down_xyzz(const XYZZ<F>& v, int d, unsigned lane, unsigned width) {
+    XYZZ<F> o;
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(&v);
+    uint32_t* b = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (unsigned k = 0; k < sizeof(XYZZ<F>) / 4; k++) b[k] = __shfl_down_sync(0xffffffffu, a[k], d);
+    if (lane + d >= width) o = XYZZ<F>::inf();
+    return o;
+}
+// sum over the 256 threads of a CTA (result in thread 0); sm: 8 slots
+template <class F>
+static __device__ __forceinline__ XYZZ<F> block_sum_xyzz_256(XYZZ<F> v, XYZZ<F>* sm, unsigned lane, unsigned warp) {
+    v = warp_reduce_xyzz<F>(v, lane);
+    __syncthreads();
+    if (lane == 0) st_vec(sm + warp, v);
+    __syncthreads();
+    XYZZ<F> r = XYZZ<F>::inf();
+    if (warp == 0) {
+        if (lane < 8) r = ld_vec(sm + lane);
+        r = warp_reduce_xyzz<F>(r, lane);
+    }
+    return r;
+}
+// K6'b: weighted sums of short arrays.  CTA a < Wr handles the row sums of bucket space a (n = nR points, may be 0),
+// CTA Wr + w the column sums of space w (nC points); n is a power of two <= 1024.  Thread t owns ipt = max(1, n / 256)
+// consecutive points.  With L_t = the thread's own sum_j j X_j and S_t = the sum of all points of the threads >= t
+// (suffix scan), sum_i i X_i = sum_t (L_t + ipt [t >= 1] S_t) = out[0]; out[1] = U = the sum of all points, so that
+// sum_i (i + 1) X_i = out[0] + out[1] (host); out[2] is unused (infinity).
+template <class F>
+__global__ void __launch_bounds__(256, 1) msm_small_weighted_kernel(const XYZZ<F>* __restrict__ inR, uint32_t nR, const XYZZ<F>* __restrict__ inC, uint32_t nC,
+                                                                     uint32_t Wr, XYZZ<F>* out3) {
+    __shared__ XYZZ<F> sm[8];
+    const uint32_t a = blockIdx.x;
+    const bool is_c = a >= Wr;
+    const uint32_t w = is_c ? a - Wr : a;
+    const uint32_t n = is_c ? nC : nR;
+    const XYZZ<F>* in = is_c ? inC + (size_t)w * nC : inR + (size_t)w * nR;
+    const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t ipt = n > 256 ? n / 256 : 1;
+    XYZZ<F> T = XYZZ<F>::inf(), L = XYZZ<F>::inf();
+    for (uint32_t j = ipt; j-- > 0;) {
+        const uint32_t idx = t * ipt + j;
+        if (idx < n) {
+            XYZZ<F> x = ld_vec(in + idx);
+            xyzz_add<F>(T, x);
+        }
+        if (j > 0) xyzz_add<F>(L, T);
+    }
+    // suffix sums of the T_t over the CTA: inside the warp by shuffles, across the warps through shared memory
+    XYZZ<F> S = T;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        XYZZ<F> o = shfl_down_xyzz<F>(S, d, lane, 32);
+        xyzz_add<F>(S, o);
+    }
+    if (lane == 0) st_vec(sm + warp, S);
+    __syncthreads();
+    if (warp == 0) {
+        XYZZ<F> v = lane < 8 ? ld_vec(sm + lane) : XYZZ<F>::inf();
+#pragma unroll 1
+        for (int d = 1; d < 8; d <<= 1) {
+            XYZZ<F> o = shfl_down_xyzz<F>(v, d, lane, 8);
+            xyzz_add<F>(v, o);
+        }
+        XYZZ<F> ex = shfl_down_xyzz<F>(v, 1, lane, 8);      // sum of the warps after this one
+        __syncwarp();
+        if (lane < 8) st_vec(sm + lane, ex);
+    }
+    __syncthreads();
+    {
+        XYZZ<F> after = ld_vec(sm + warp);
+        xyzz_add<F>(S, after);                              // S = sum_{t' >= t} T_t'
+    }
+    const XYZZ<F> U = S;                                    // thread 0: the sum of all points
+    // sum_i i X_i = sum_t (L_t + ipt * [t >= 1] S_t): one block sum
+    if (t != 0) {
+        for (uint32_t m = ipt; m > 1; m >>= 1) S = xyzz_dbl<F>(S);
+        xyzz_add<F>(L, S);
+    }
+    const XYZZ<F> Wsum = block_sum_xyzz_256<F>(L, sm, lane, warp);
+    if (t == 0) {
+        st_vec(out3 + (size_t)a * 3 + 0, Wsum);
+        st_vec(out3 + (size_t)a * 3 + 1, U);
+        st_vec(out3 + (size_t)a * 3 + 2, XYZZ<F>::inf());
+    }
+}
+
 // Small inputs (public-input queries have a handful of points): thread per point, double-and-add,
 // then a single-warp tree.  Also an independent on-device check of the bucket pipeline (tests).
 template <class F>
@@ -964,7 +1078,7 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
         if (!sl.dbg_start) { cudaEventCreate(&sl.dbg_start); cudaEventCreate(&sl.dbg_acc); cudaEventCreate(&sl.dbg_done); }
         cudaEventRecord(sl.dbg_start, st);
     }
-    const size_t want_host = 64 + 128 * sizeof(XYZZ<Fq2>);     // header (entry count) + up to 128 windows
+    const size_t want_host = 64 + 6 * 128 * sizeof(XYZZ<Fq2>); // header (entry count) + up to 128 bucket spaces x 6 partial results
     if (sl.host_win_bytes < want_host) {
         if (sl.host_win) cudaFreeHost(sl.host_win);
         ZA_CUDA(cudaHostAlloc(&sl.host_win, want_host, cudaHostAllocDefault));
@@ -1105,12 +1219,18 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
     XYZZ<F>* d_lvl[2] = {d_pool + (size_t)Wr * pool_stride, d_pool + (size_t)Wr * pool_stride + lvl_elems};
     XYZZ<F>* d_grp = d_lvl[1] + lvl_elems;
     XYZZ<F>* d_win = d_grp + (size_t)Wr * (grp_total - 1);          // the last level has one point per window
+    size_t win_points = (size_t)Wr;
     XYZZ<F>* d_buckets = sl.buckets.as<XYZZ<F>>();
 
     ZA_CUDA(cudaMemsetAsync(d_buckets, 0, (size_t)nkeys * sizeof(XYZZ<F>), st));
     ZA_CUDA(cudaMemsetAsync(d_owner, 0xff, (size_t)nchunks * 4, st));
     ZA_CUDA(cudaMemsetAsync(d_long_count, 0, 4, st));
-    ZA_CUDA(cudaMemsetAsync(d_pool, 0, (size_t)Wr * pool_stride * sizeof(XYZZ<F>), st));
+    // bucket reduction: row / column scheme (K6') unless the bucket space is larger than 2^20 or ZA_MSM_REDUCE_OLD is set
+    static const bool reduce_old = getenv("ZA_MSM_REDUCE_OLD") != nullptr;
+    const int nb = c - 1;
+    const bool use_rc = !reduce_old && nb <= 20;
+    sl.red_mode = use_rc ? 1 : 0;
+    if (!use_rc) ZA_CUDA(cudaMemsetAsync(d_pool, 0, (size_t)Wr * pool_stride * sizeof(XYZZ<F>), st));
     if (share_sort < 0) {
         ZA_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nkeys * 4, st));
         ProfScope prof(ctx, PROF_MSM_SORT, (double)n);
@@ -1179,35 +1299,83 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
                                                                   d_long_count);
         msm_fixup_long_kernel<F><<<ctx->sm_count * 2, 128, 0, side>>>(d_offsets_final, Lc, d_head, d_tail, d_owner, d_buckets, d_long_list, d_long_count);
         ctx->launches += 2;
-        const XYZZ<F>* src = d_buckets;
-        int li = 0;
-        for (const Level& lv : levels) {
-            XYZZ<F>* dst = d_lvl[li & 1];
-            // acc of level l carries weight SEG^l: every earlier level had the full segment size SEG
-            const uint32_t total = (uint32_t)Wr * lv.n_out;
-            msm_weighted_level_kernel<F><<<nblk(total, 128), 128, 0, side>>>(src, lv.n_in, lv.s, lv.n_out, total, SEG_LOG * li, dst, d_pool, pool_stride,
-                                                                             lv.pool_off);
+        if (use_rc) {
+            const uint32_t k = nb < 10 ? (uint32_t)nb : 10u, Lw = 1u << k, H = B >> k;      // B = H rows x Lw columns
+            const size_t stage_elems = (size_t)Wr * (B / 8 > Lw ? B / 8 : Lw);
+            const size_t r_elems = H > 1 ? (size_t)Wr * H : 0;
+            sl.red.ensure((4 * stage_elems + r_elems + (size_t)6 * Wr) * sizeof(XYZZ<F>));
+            XYZZ<F>* d_stage[2] = {sl.red.as<XYZZ<F>>(), sl.red.as<XYZZ<F>>() + stage_elems};
+            XYZZ<F>* d_rstage[2] = {d_stage[1] + stage_elems, d_stage[1] + 2 * stage_elems};
+            XYZZ<F>* d_r = d_rstage[1] + stage_elems;
+            XYZZ<F>* d_out3 = d_r + r_elems;
+            const XYZZ<F>* d_c = d_buckets;
+            if (H > 1) {
+                // row sums: every row (Lw contiguous buckets) is a batch of Lw one-point "rows" for the same kernel
+                {
+                    const uint32_t rows = (uint32_t)Wr * H;
+                    const XYZZ<F>* cur = d_buckets;
+                    int pp = 0;
+                    for (uint32_t cnt = Lw; cnt > 1;) {
+                        const uint32_t f = cnt >= 8 ? 8 : cnt, cnt_out = cnt / f;
+                        const uint32_t total = rows * cnt_out;
+                        XYZZ<F>* dst = cnt_out == 1 ? d_r : d_rstage[pp];
+                        msm_colsum_kernel<F><<<nblk(total, 128), 128, 0, side>>>(cur, cnt, 1, f, cnt_out, total, dst);
+                        ctx->launches++;
+                        cur = dst;
+                        pp ^= 1;
+                        cnt = cnt_out;
+                    }
+                }
+                // column sums: H rows of Lw points, eight rows per thread and stage
+                const XYZZ<F>* cur = d_buckets;
+                int pp = 0;
+                for (uint32_t rows_in = H; rows_in > 1;) {
+                    const uint32_t f = rows_in >= 8 ? 8 : rows_in, rows_out = rows_in / f;
+                    const uint32_t total = (uint32_t)Wr * rows_out * Lw;
+                    msm_colsum_kernel<F><<<nblk(total, 128), 128, 0, side>>>(cur, rows_in, Lw, f, rows_out, total, d_stage[pp]);
+                    ctx->launches++;
+                    cur = d_stage[pp];
+                    pp ^= 1;
+                    rows_in = rows_out;
+                }
+                d_c = cur;
+            }
+            msm_small_weighted_kernel<F><<<2 * Wr, 256, 0, side>>>(d_r, H > 1 ? H : 0, d_c, Lw, (uint32_t)Wr, d_out3);
             ctx->launches++;
-            src = dst;
-            li++;
-        }
-        // the final T (one per window) is the plain sum of all buckets: pool slot pool_len
-        ZA_CUDA(cudaMemcpy2DAsync(d_pool + pool_len, (size_t)pool_stride * sizeof(XYZZ<F>), src, sizeof(XYZZ<F>), sizeof(XYZZ<F>), Wr,
-                                  cudaMemcpyDeviceToDevice, side));
-        {
-            const XYZZ<F>* gin = d_pool;
-            uint32_t gstride = pool_stride, gcount = pool_stride;
-            XYZZ<F>* gout = d_grp;
-            for (uint32_t groups : grp_sizes) {
-                msm_group_reduce_kernel<F><<<nblk((size_t)Wr * groups * 32, 128), 128, 0, side>>>(gin, gstride, gcount, GRP_PER, groups, (uint32_t)Wr * groups, gout);
+            sl.red_k = (int)k; sl.red_H = H; sl.red_Lw = Lw;
+            d_win = d_out3;
+            win_points = 6 * (size_t)Wr;
+        } else {
+            const XYZZ<F>* src = d_buckets;
+            int li = 0;
+            for (const Level& lv : levels) {
+                XYZZ<F>* dst = d_lvl[li & 1];
+                // acc of level l carries weight SEG^l: every earlier level had the full segment size SEG
+                const uint32_t total = (uint32_t)Wr * lv.n_out;
+                msm_weighted_level_kernel<F><<<nblk(total, 128), 128, 0, side>>>(src, lv.n_in, lv.s, lv.n_out, total, SEG_LOG * li, dst, d_pool, pool_stride,
+                                                                                 lv.pool_off);
                 ctx->launches++;
-                gin = gout; gstride = groups; gcount = groups;
-                gout += (size_t)Wr * groups;
+                src = dst;
+                li++;
+            }
+            // the final T (one per window) is the plain sum of all buckets: pool slot pool_len
+            ZA_CUDA(cudaMemcpy2DAsync(d_pool + pool_len, (size_t)pool_stride * sizeof(XYZZ<F>), src, sizeof(XYZZ<F>), sizeof(XYZZ<F>), Wr,
+                                      cudaMemcpyDeviceToDevice, side));
+            {
+                const XYZZ<F>* gin = d_pool;
+                uint32_t gstride = pool_stride, gcount = pool_stride;
+                XYZZ<F>* gout = d_grp;
+                for (uint32_t groups : grp_sizes) {
+                    msm_group_reduce_kernel<F><<<nblk((size_t)Wr * groups * 32, 128), 128, 0, side>>>(gin, gstride, gcount, GRP_PER, groups, (uint32_t)Wr * groups, gout);
+                    ctx->launches++;
+                    gin = gout; gstride = groups; gcount = groups;
+                    gout += (size_t)Wr * groups;
+                }
             }
         }
     }
     ZA_CUDA(cudaGetLastError());
-    ZA_CUDA(cudaMemcpyAsync((uint8_t*)sl.host_win + 64, d_win, (size_t)Wr * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, side));
+    ZA_CUDA(cudaMemcpyAsync((uint8_t*)sl.host_win + 64, d_win, win_points * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, side));
     if (ctx->profile) ZA_CUDA(cudaMemcpyAsync(sl.host_win, d_offsets + nkeys, 4, cudaMemcpyDeviceToHost, side));
     ZA_CUDA(cudaEventRecord(sl.done, side));
     if (timeline) cudaEventRecord(sl.dbg_done, side);
@@ -1241,6 +1409,26 @@ XYZZ<F> msm_finish(Ctx* ctx, int slot_id) {
         for (int r = 0; r < sl.rounds; r++) work += (double)(E[r] - E[r + 1]) * (g1 ? 6.0 : 17.0);
         work += (double)E[sl.rounds] * (g1 ? 10.0 : 28.0);
         ctx->prof_work[sl.acc_cat] += work;
+    }
+    // row / column reduction: the six partial results of bucket space w -> sum_b (b + 1) S_b  (K6')
+    std::vector<XYZZ<F>> spaces;
+    if (sl.red_mode == 1) {
+        auto weighted = [](const XYZZ<F>* o, uint32_t, bool plus_one) {          // sum_i i X_i (+ sum_i X_i)
+            XYZZ<F> r = o[0];
+            if (plus_one) xyzz_add<F>(r, o[1]);
+            return r;
+        };
+        spaces.resize(sl.W);
+        for (int w = 0; w < sl.W; w++) {
+            XYZZ<F> t = weighted(win + 3 * (size_t)(sl.W + w), sl.red_Lw, true);
+            if (sl.red_H > 1) {
+                XYZZ<F> hi = weighted(win + 3 * (size_t)w, sl.red_H, false);
+                for (int k = 0; k < sl.red_k; k++) hi = xyzz_dbl<F>(hi);
+                xyzz_add<F>(t, hi);
+            }
+            spaces[w] = t;
+        }
+        win = spaces.data();
     }
     // window combination on the host: result = sum_w 2^(c w) S_w   (bellman: `higher.double()` x c, then add)
     for (int w = sl.W - 1; w >= 0; w--) {
