@@ -271,7 +271,7 @@ def run_gpu(args):
                     "frac": achieved / (imad_peak / 1e12) if imad_peak else None, "traffic": traffic,
                     "traffic_note": "DRAM read+write bytes per launch from the ncu --set full capture of the same 2^20 workload (profiles/r01_traffic.json); null for other sizes",
                     "peak_source": "measured in this run (za_imad_peak: dependency-free mad.lo.u32 on all SMs)",
-                    "algorithmic": f"{int(dom['work'] / max(dom['spans'], 1))} Fq products (10 per XYZZ mixed addition) x {IMAD_PER_MODMUL} IMAD per launch",
+                    "algorithmic": f"{int(dom['work'] / max(dom['spans'], 1))} Fq products (" + ("10 per XYZZ mixed addition" if dom is acc1 else "17 per batched-affine addition, 28 per XYZZ mixed addition over Fq2") + f") x {IMAD_PER_MODMUL} IMAD per launch (rank 0's share)",
                     "launch_ms": dom["ms"] / max(dom["spans"], 1), "share_of_step": dom["ms"] / steps_profiled / prove_ms,
                     "note": "tensor cores not applicable (multiprecision integer); HBM needs 96 B/point, two orders below compute"}
         g2_t = acc2["work"] * IMAD_PER_MODMUL / (acc2["ms"] * 1e-3) / 1e12 if acc2["ms"] > 0 else 0.0
