@@ -251,13 +251,42 @@ def run_gpu(args):
         assert proof == proof_e2e, "device-resident and host-buffer proofs differ"
     clocks = sampler.summary() if sampler else None
 
+    # The G2 multiexp runs on its own stream NEXT TO the G1 multiexps (they share the SMs by design), so the per-class
+    # event times of the step overlap and are not per-kernel durations.  For the roofline objects the two accumulation
+    # kernels are therefore also timed ALONE, in this process, on the same workload size (2^log_m points, fixed-base
+    # table, uniform scalars): that duration is what `achieved` uses; the in-step figure is reported beside it.
+    def isolated_accumulation(group):
+        n_iso = 1 << log_m
+        bases_iso = za_b200.Bases.generate(ctx, group, n_iso, 1)
+        bases_iso.precompute()
+        sc_iso = torch.from_numpy(synthetic.random_scalars(n_iso, 0x5A410008 + group)).to(dev)
+        for _ in range(3):
+            za_b200.multiexp_device(ctx, bases_iso, sc_iso.data_ptr(), n_iso)
+        ctx.profile(True)
+        ctx.profile_read()
+        for _ in range(5):
+            za_b200.multiexp_device(ctx, bases_iso, sc_iso.data_ptr(), n_iso)
+        p_iso = ctx.profile_read()
+        ctx.profile(False)
+        del bases_iso, sc_iso
+        return p_iso["msm_accumulate_g1" if group == 1 else "msm_accumulate_g2"]
+
+    iso1 = iso2 = None
+    if rank == 0 and world == 1 and log_m <= 22:
+        iso1, iso2 = isolated_accumulation(1), isolated_accumulation(2)
+
     line = None
     if rank == 0:
         hbm_peak, peak_src = peaks()
         imad_peak = za_b200.imad_peak(ctx)
         acc1, acc2, nttp = prof["msm_accumulate_g1"], prof["msm_accumulate_g2"], prof["ntt"]
+        in_step = {"g1": acc1["ms"] / max(acc1["spans"], 1), "g2": acc2["ms"] / max(acc2["spans"], 1)}
+        n_g1_launches = acc1["spans"] / max(steps_profiled, 1)
+        if iso1 is not None:
+            acc1, acc2 = iso1, iso2
         # dominant kernel of the step: the G1/G2 bucket-accumulation kernels (integer-pipe bound)
-        dom = acc1 if acc1["ms"] >= acc2["ms"] else acc2
+        per1, per2 = acc1["ms"] / max(acc1["spans"], 1), acc2["ms"] / max(acc2["spans"], 1)
+        dom = acc1 if per1 * max(n_g1_launches, 1.0) >= per2 else acc2        # by time per step: 4 G1 launches against 1 G2
         dom_name = "msm_accumulate_g1_sm_kernel (G1 bucket accumulation, XYZZ mixed additions)" if dom is acc1 else "msm_pair_round_kernel<Fq2> x4 + msm_accumulate_kernel<Fq2>"
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
@@ -272,13 +301,17 @@ def run_gpu(args):
                     "traffic_note": "DRAM read+write bytes per launch from the ncu --set full capture of the same 2^20 workload (profiles/r01_traffic.json); null for other sizes",
                     "peak_source": "measured in this run (za_imad_peak: dependency-free mad.lo.u32 on all SMs)",
                     "algorithmic": f"{int(dom['work'] / max(dom['spans'], 1))} Fq products (" + ("10 per XYZZ mixed addition" if dom is acc1 else "17 per batched-affine addition, 28 per XYZZ mixed addition over Fq2") + f") x {IMAD_PER_MODMUL} IMAD per launch (rank 0's share)",
-                    "launch_ms": dom["ms"] / max(dom["spans"], 1), "share_of_step": dom["ms"] / steps_profiled / prove_ms,
+                    "launch_ms": dom["ms"] / max(dom["spans"], 1),
+                    "timing": ("kernel timed alone in this process (CUDA events), same size and table as in the proof; in the proof it shares the SMs with the G2 multiexp's kernels by design" if iso1 is not None else "in-step CUDA events"),
+                    "in_step_launch_ms": in_step["g1" if dom is acc1 else "g2"],
+                    "share_of_step": (dom["ms"] / max(dom["spans"], 1)) * (n_g1_launches if dom is acc1 else 1.0) / prove_ms,
                     "note": "tensor cores not applicable (multiprecision integer); HBM needs 96 B/point, two orders below compute"}
         g2_t = acc2["work"] * IMAD_PER_MODMUL / (acc2["ms"] * 1e-3) / 1e12 if acc2["ms"] > 0 else 0.0
         roofline_g2 = {"bound": "imad", "kernel": "G2 bucket accumulation: msm_pair_round_kernel<Fq2> (batched-affine rounds) + msm_accumulate_kernel<Fq2>",
                        "achieved": g2_t, "peak": imad_peak / 1e12, "unit": "TIMAD/s", "frac": g2_t / (imad_peak / 1e12) if imad_peak else None,
                        "algorithmic": f"{int(acc2['work'] / max(acc2['spans'], 1))} Fq products (17 per batched-affine addition, 28 per XYZZ mixed addition over Fq2) x {IMAD_PER_MODMUL} IMAD per multiexp",
-                       "launch_ms": acc2["ms"] / max(acc2["spans"], 1), "share_of_step": acc2["ms"] / steps_profiled / prove_ms}
+                       "launch_ms": acc2["ms"] / max(acc2["spans"], 1), "in_step_launch_ms": in_step["g2"],
+                       "share_of_step": acc2["ms"] / max(acc2["spans"], 1) / prove_ms}
         ntt_bytes = 64.0 * nttp["work"]
         ntt_gbs = ntt_bytes / (nttp["ms"] * 1e-3) / 1e9 if nttp["ms"] > 0 else 0.0
         roofline_ntt = {"bound": "hbm", "kernel": "ntt_pass_kernel (one transform = 3 passes at 2^20)", "achieved": ntt_gbs, "peak": hbm_peak, "unit": "GB/s",
@@ -286,6 +319,7 @@ def run_gpu(args):
                         "algorithmic": "64 B per element per transform (one 32 B read + one 32 B write)",
                         "imad_frac": (IMAD_PER_MODMUL * (nttp["work"] / 2) * log_m / (nttp["ms"] * 1e-3)) / imad_peak if nttp["ms"] > 0 else None}
         breakdown = {k: round(v["ms"] / steps_profiled, 4) for k, v in prof.items() if v["ms"] > 0}
+        breakdown["note"] = "event time per kernel class per step; the classes run on concurrent streams, so the sum exceeds the step"
         h2d = int(wit_host.numel())
         line = {"metric": METRIC, "value": prove_ms, "unit": "ms", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": prove_ms,
                 "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",

@@ -27,9 +27,12 @@ Ctx::~Ctx() {
         if (sl.host_win) cudaFreeHost(sl.host_win);
         if (sl.acc_done) cudaEventDestroy(sl.acc_done);
         if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.sort_ev) cudaEventDestroy(sl.sort_ev);
         if (sl.side) cudaStreamDestroy(sl.side);
     }
     if (side) cudaStreamDestroy(side);
+    if (g2_stream) cudaStreamDestroy(g2_stream);
+    if (g2_fork) cudaEventDestroy(g2_fork);
     if (host_flag) cudaFreeHost(host_flag);
     if (own_stream && stream) cudaStreamDestroy(stream);
 }

@@ -85,6 +85,7 @@ struct MsmSlot {
     void* host_win = nullptr;            // pinned: window sums (+ entry count when profiling)
     size_t host_win_bytes = 0;
     cudaEvent_t acc_done = nullptr, done = nullptr;
+    cudaEvent_t sort_ev = nullptr;        // recorded behind this slot's digit sort
     cudaStream_t side = nullptr;         // this slot's reduction stream (high priority, so it is not starved by accumulations)
     cudaEvent_t dbg_start = nullptr, dbg_acc = nullptr, dbg_done = nullptr;   // ZA_DEBUG_TIMELINE only
     bool busy = false;                   // enqueued, not yet finished
@@ -111,6 +112,8 @@ struct Ctx {
     DevBuf scratch[16];
     MsmSlot slots[8];
     cudaStream_t side = nullptr;        // bucket reductions overlap the next multiexp's accumulation here
+    cudaStream_t g2_stream = nullptr;   // the G2 multiexp of a proof runs here, next to the G1 multiexps (prove_msms_enqueue)
+    cudaEvent_t g2_fork = nullptr;
     unsigned long long* host_flag = nullptr;   // pinned: verdict of the witness range check of create_proof
     uint64_t launches = 0;              // kernels launched through this context (bench: gpu_launches)
     // optional per-kernel-class timing with CUDA events on `stream` (bench.py roofline numbers)

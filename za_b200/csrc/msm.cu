@@ -1240,6 +1240,10 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
         msm_scan_apply_kernel<<<nctas, 1024, 0, st>>>(d_counts, nkeys, d_cta, d_offsets, d_cursors, 0);
         msm_digits_scatter_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_cursors, d_entries, single ? 1 : 0);
         ctx->launches += 5;
+        if (!sl.sort_ev) ZA_CUDA(cudaEventCreateWithFlags(&sl.sort_ev, cudaEventDisableTiming));
+        ZA_CUDA(cudaEventRecord(sl.sort_ev, st));          // a multiexp that shares this sort from another stream waits for it
+    } else if (ctx->slots[share_sort].sort_ev) {
+        ZA_CUDA(cudaStreamWaitEvent(st, ctx->slots[share_sort].sort_ev, 0));
     }
     {
         ProfScope prof(ctx, sl.acc_cat, 0);

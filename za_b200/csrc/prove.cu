@@ -518,8 +518,28 @@ static void prove_msms_enqueue(Ctx* ctx, const Pk* pk, const Circuit* c, const u
         // G2 first: its (longest) bucket reduction then overlaps the G1 accumulations on the side stream
         const uint32_t* sb = gather(ctx, d_wit, c->b_cat_idx, c->b_cat_total, ctx->scratch[13]);
         share_weighted(c->b_cat_total, rank, world, w0, lo, hi);
+        // The G2 multiexp goes to its own (high-priority) stream.  Its kernels hold 2 CTAs of 190+ registers per SM and
+        // are latency bound (8 warps/SM, multiply pipe ~60 % busy); the registers they leave fit exactly one CTA of the
+        // G1 accumulation, so the G1 multiexps on the main stream run next to it and fill the pipe
+        // (profiles/r01_session3.md).  It starts as soon as the shared digit sort of the B (G1) multiexp is done.
+        // ZA_G2_INLINE=1: everything on the main stream, one after the other.
+        static const bool g2_inline = getenv("ZA_G2_INLINE") != nullptr;
+        cudaStream_t main_st = ctx->stream;
+        if (!g2_inline) {
+            if (!ctx->g2_stream) {
+                int lo_prio = 0, hi_prio = 0;
+                ZA_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+                ZA_CUDA(cudaStreamCreateWithPriority(&ctx->g2_stream, cudaStreamNonBlocking, hi_prio));
+                ZA_CUDA(cudaEventCreateWithFlags(&ctx->g2_fork, cudaEventDisableTiming));
+            }
+            ZA_CUDA(cudaEventRecord(ctx->g2_fork, main_st));            // the B scalars are gathered
+            ZA_CUDA(cudaStreamWaitEvent(ctx->g2_stream, ctx->g2_fork, 0));
+        }
         multiexp_enqueue<Fq>(ctx, 3, pk->b_g1.get(), lo, sb + lo * 8, hi - lo);
-        multiexp_enqueue<Fq2>(ctx, 4, pk->b_g2.get(), lo, sb + lo * 8, hi - lo, hi - lo > 64 ? 3 : -1);
+        if (!g2_inline) ctx->stream = ctx->g2_stream;
+        try { multiexp_enqueue<Fq2>(ctx, 4, pk->b_g2.get(), lo, sb + lo * 8, hi - lo, hi - lo > 64 ? 3 : -1); }
+        catch (...) { ctx->stream = main_st; throw; }
+        ctx->stream = main_st;
     }
     if ((which & MSM_H) && (which & MSM_WITNESS)) {
         share(m - 1, rank, world, lo, hi);
