@@ -271,9 +271,22 @@ def run_gpu(args):
         del bases_iso, sc_iso
         return p_iso["msm_accumulate_g1" if group == 1 else "msm_accumulate_g2"]
 
-    iso1 = iso2 = None
+    def isolated_ntt():
+        v_iso = torch.from_numpy(synthetic.random_scalars(1 << log_m, 0x5A41000B)).to(dev)
+        for _ in range(3):
+            ctx.ntt_device(v_iso.data_ptr(), log_m, za_b200.FFT)
+        ctx.profile(True)
+        ctx.profile_read()
+        for _ in range(7):
+            ctx.ntt_device(v_iso.data_ptr(), log_m, za_b200.FFT)
+        p_iso = ctx.profile_read()
+        ctx.profile(False)
+        del v_iso
+        return p_iso["ntt"]
+
+    iso1 = iso2 = iso_ntt = None
     if rank == 0 and world == 1 and log_m <= 22:
-        iso1, iso2 = isolated_accumulation(1), isolated_accumulation(2)
+        iso1, iso2, iso_ntt = isolated_accumulation(1), isolated_accumulation(2), isolated_ntt()
 
     line = None
     if rank == 0:
@@ -282,8 +295,9 @@ def run_gpu(args):
         acc1, acc2, nttp = prof["msm_accumulate_g1"], prof["msm_accumulate_g2"], prof["ntt"]
         in_step = {"g1": acc1["ms"] / max(acc1["spans"], 1), "g2": acc2["ms"] / max(acc2["spans"], 1)}
         n_g1_launches = acc1["spans"] / max(steps_profiled, 1)
+        ntt_in_step_ms = nttp["ms"] / max(steps_profiled, 1)
         if iso1 is not None:
-            acc1, acc2 = iso1, iso2
+            acc1, acc2, nttp = iso1, iso2, iso_ntt
         # dominant kernel of the step: the G1/G2 bucket-accumulation kernels (integer-pipe bound)
         per1, per2 = acc1["ms"] / max(acc1["spans"], 1), acc2["ms"] / max(acc2["spans"], 1)
         dom = acc1 if per1 * max(n_g1_launches, 1.0) >= per2 else acc2        # by time per step: 4 G1 launches against 1 G2
@@ -317,6 +331,8 @@ def run_gpu(args):
         roofline_ntt = {"bound": "hbm", "kernel": "ntt_pass_kernel (one transform = 3 passes at 2^20)", "achieved": ntt_gbs, "peak": hbm_peak, "unit": "GB/s",
                         "frac": ntt_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                         "algorithmic": "64 B per element per transform (one 32 B read + one 32 B write)",
+                        "timing": ("seven forward transforms timed alone in this process; in the proof the H pipeline runs next to the witness multiexps and stretches" if iso_ntt is not None else "in-step CUDA events"),
+                        "in_step_ms_per_proof": ntt_in_step_ms,
                         "imad_frac": (IMAD_PER_MODMUL * (nttp["work"] / 2) * log_m / (nttp["ms"] * 1e-3)) / imad_peak if nttp["ms"] > 0 else None}
         breakdown = {k: round(v["ms"] / steps_profiled, 4) for k, v in prof.items() if v["ms"] > 0}
         breakdown["note"] = "event time per kernel class per step; the classes run on concurrent streams, so the sum exceeds the step"

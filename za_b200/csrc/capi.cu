@@ -32,6 +32,9 @@ Ctx::~Ctx() {
     }
     if (side) cudaStreamDestroy(side);
     if (g2_stream) cudaStreamDestroy(g2_stream);
+    if (h_stream) cudaStreamDestroy(h_stream);
+    if (h_fork) cudaEventDestroy(h_fork);
+    if (h_join) cudaEventDestroy(h_join);
     if (g2_fork) cudaEventDestroy(g2_fork);
     if (host_flag) cudaFreeHost(host_flag);
     if (own_stream && stream) cudaStreamDestroy(stream);

@@ -114,6 +114,8 @@ struct Ctx {
     cudaStream_t side = nullptr;        // bucket reductions overlap the next multiexp's accumulation here
     cudaStream_t g2_stream = nullptr;   // the G2 multiexp of a proof runs here, next to the G1 multiexps (prove_msms_enqueue)
     cudaEvent_t g2_fork = nullptr;
+    cudaStream_t h_stream = nullptr;    // the H pipeline runs here, next to the witness multiexps (create_proof_device)
+    cudaEvent_t h_fork = nullptr, h_join = nullptr;
     unsigned long long* host_flag = nullptr;   // pinned: verdict of the witness range check of create_proof
     uint64_t launches = 0;              // kernels launched through this context (bench: gpu_launches)
     // optional per-kernel-class timing with CUDA events on `stream` (bench.py roofline numbers)

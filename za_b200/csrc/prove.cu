@@ -637,6 +637,36 @@ static void create_proof_device(Ctx* ctx, const Pk* pk, const Circuit* c, const 
     const size_t m = domain_size(c, nullptr);
     DevBuf& h = ctx->scratch[9];
     h.ensure(m * sizeof(Fr));
+    // The H pipeline (r1cs evaluation, seven NTTs) runs on its own high-priority stream NEXT TO the witness multiexps:
+    // B, L and A do not depend on it, its short kernels leave the SMs half empty at every launch boundary and wave
+    // tail, and the accumulation CTAs fill those holes.  The NTTs stretch (2.2 -> ~13 ms, in the shadow), the proof
+    // gets 0.8 ms shorter (profiles/r01_session3.md); the H multiexp is enqueued behind the pipeline.
+    // ZA_H_INLINE=1: H pipeline first, on the main stream.
+    static const bool h_overlap = getenv("ZA_H_INLINE") == nullptr;
+    if (h_overlap && !tr) {
+        cudaStream_t main_st = ctx->stream;
+        if (!ctx->h_stream) {
+            int lo_prio = 0, hi_prio = 0;
+            ZA_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+            ZA_CUDA(cudaStreamCreateWithPriority(&ctx->h_stream, cudaStreamNonBlocking, hi_prio));
+            ZA_CUDA(cudaEventCreateWithFlags(&ctx->h_fork, cudaEventDisableTiming));
+            ZA_CUDA(cudaEventCreateWithFlags(&ctx->h_join, cudaEventDisableTiming));
+        }
+        ZA_CUDA(cudaEventRecord(ctx->h_fork, main_st));
+        ZA_CUDA(cudaStreamWaitEvent(ctx->h_stream, ctx->h_fork, 0));
+        ctx->stream = ctx->h_stream;
+        try { prove_h(ctx, c, d_wit, h.as<Fr>(), nullptr); } catch (...) { ctx->stream = main_st; throw; }
+        ZA_CUDA(cudaEventRecord(ctx->h_join, ctx->h_stream));
+        ctx->stream = main_st;
+        prove_msms_enqueue(ctx, pk, c, d_wit, h.as<Fr>(), 0, 1, MSM_WITNESS);
+        ZA_CUDA(cudaStreamWaitEvent(main_st, ctx->h_join, 0));
+        prove_msms_enqueue(ctx, pk, c, d_wit, h.as<Fr>(), 0, 1, MSM_H);
+        AssemblePre pre = prove_assemble_pre(pk, r_le, s_le);
+        Partials Q;
+        prove_msms_collect(ctx, Q);
+        prove_assemble_post(pre, Q, proof_out);
+        return;
+    }
     prove_h(ctx, c, d_wit, h.as<Fr>(), tr);
     Partials P;
     if (tr && (tr->msm_g1 || tr->msm_g2)) {
