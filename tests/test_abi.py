@@ -66,3 +66,56 @@ def test_proof_json_format():
     p = np.frombuffer(proof, np.uint8); pi = np.zeros(64, np.uint8); pi[0] = 21
     rc = _lib.lib().za_proof_to_json(p.ctypes.data_as(ctypes.c_void_p), pi.ctypes.data_as(ctypes.c_void_p), 2, buf, len(js))
     assert rc == -9
+
+
+# ---------------------------------------------------------------- libza2c: the outer C ABI of za's bindings (include/za2c.h)
+def _za2c():
+    from za_b200 import build as zb
+    L = ctypes.CDLL(zb.OUT_ZA2C)
+    L.verify.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+    L.verify.restype = ctypes.c_int
+    L.prove.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+    L.prove.restype = ctypes.c_int
+    L.setup.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+    L.setup.restype = ctypes.c_int
+    L.verbose.argtypes = [ctypes.c_int]
+    L.verbose.restype = None
+    return L
+
+
+def test_za2c_exports_the_reference_symbols():
+    """binding/go/lib.go:6-9 links `verbose`, `setup`, `prove`, `verify` from -lza2c."""
+    text = open(os.path.join(ROOT, "include", "za2c.h")).read()
+    L = _za2c()
+    for name in ("verbose", "setup", "prove", "verify"):
+        assert re.search(r"\b%s\s*\(" % name, text) and hasattr(L, name)
+
+
+def test_za2c_verify_like_the_bindings_use_it():
+    """binding/python3/test/test.py:22-28 / binding/go/test/test.go:37-50: verify(vk_json, proof_json) == true; return codes
+    of binding/c/native/src/lib.rs:10-13 and the `len >= size` buffer rule of lib.rs:23."""
+    import json
+    import za_b200
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "groth16_example.json")))
+    vk = {k: bytes.fromhex(v) for k, v in g["vk"].items() if k != "ic"}
+    vk["ic"] = [bytes.fromhex(x) for x in g["vk"]["ic"]]
+    vk_json = za_b200.vk_to_json(vk, ["main.r"]).encode()
+    L = _za2c()
+    L.verbose(0)
+    err = ctypes.create_string_buffer(512)
+    assert L.verify(vk_json, g["proof_json"].encode(), err, 512) == 0
+    tampered = json.loads(g["proof_json"]); tampered["public_inputs"] = ["7"]
+    assert L.verify(vk_json, json.dumps(tampered).encode(), err, 512) == 2          # ERR_VERIFICATION_FAILED
+    assert L.verify(vk_json, b'{"a":1}', err, 512) == 100 and len(err.value) > 0    # ERR_CUSTOM, text in err_buf
+    assert L.verify(vk_json, b'{"a":1}', err, 4) == 1                               # ERR_BUFFER_TOO_SMALL
+
+
+def test_za2c_setup_and_prove_fail_loudly_without_the_front_end():
+    L = _za2c()
+    err = ctypes.create_string_buffer(1024)
+    out = ctypes.create_string_buffer(64)
+    assert L.prove(b"proving.key", b'{"p":2,"q":3}', out, 64, err, 1024) == 100
+    assert b"za_create_proof" in err.value and b"front-end" in err.value
+    assert L.setup(b"circuit.za", b"proving.key", b"json", out, 64, err, 1024) == 100 and b"za_generate_parameters" in err.value
+    assert L.setup(b"circuit.za", b"proving.key", b"yaml", out, 64, err, 1024) == 100 and err.value == b"invalid validator type"
+    assert L.prove(b"proving.key", b"{}", out, 64, err, 8) == 1
