@@ -1,0 +1,4 @@
+#!/bin/bash
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+exec < /dev/null
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "babyadd" 2>&1 | tail -5

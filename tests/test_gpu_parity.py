@@ -233,6 +233,18 @@ def test_create_proof_config2_2pow16(ctx):
     _prove_case(ctx, circuits.mul_chain_fast(nc, x0=0x5A410002), toxic, r=2 ** 200 + 17, s=2 ** 100 + 3)
 
 
+@pytest.mark.parametrize("kat", [0, 1, 2])
+def test_create_proof_circomlib_babyadd(ctx, kat):
+    """Config 3's building block: circomlib BabyAdd (babyjub.circom:23-50, R1CS extracted by hand in tests/circuits.py)
+    on the inputs of the reference's own tests (za_test/babyjub.za:4-34); the public outputs are the values those tests
+    assert, the witness is full of zeros in the first case, and the proof is bit-identical to the oracle's."""
+    args, expect = circuits.BABYADD_KATS[kat]
+    cs, out = circuits.babyjub_add(*args)
+    assert out == expect
+    proof, pub, _ = _prove_case(ctx, cs, [0x5A410003 + kat, 3, 5, 7, 11], r=2 ** 190 + kat, s=2 ** 90 + 7)
+    assert tuple(pub) == expect
+
+
 def test_create_proof_rejects_non_canonical_witness(ctx):
     """A witness element >= r is refused (ZA_ERR_NOT_CANONICAL, first offending index named) — the range check runs on
     the uploaded copy on the GPU — and the same call with the value reduced still proves."""
