@@ -29,6 +29,9 @@ Ctx::~Ctx() {
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.sort_ev) cudaEventDestroy(sl.sort_ev);
         if (sl.side) cudaStreamDestroy(sl.side);
+        if (sl.side2) cudaStreamDestroy(sl.side2);
+        if (sl.red_fork) cudaEventDestroy(sl.red_fork);
+        if (sl.red_join) cudaEventDestroy(sl.red_join);
     }
     if (side) cudaStreamDestroy(side);
     if (g2_stream) cudaStreamDestroy(g2_stream);

@@ -87,6 +87,8 @@ struct MsmSlot {
     cudaEvent_t acc_done = nullptr, done = nullptr;
     cudaEvent_t sort_ev = nullptr;        // recorded behind this slot's digit sort
     cudaStream_t side = nullptr;         // this slot's reduction stream (high priority, so it is not starved by accumulations)
+    cudaStream_t side2 = nullptr;        // row sums of the row / column reduction run here, next to the column sums on `side`
+    cudaEvent_t red_fork = nullptr, red_join = nullptr;
     cudaEvent_t dbg_start = nullptr, dbg_acc = nullptr, dbg_done = nullptr;   // ZA_DEBUG_TIMELINE only
     bool busy = false;                   // enqueued, not yet finished
     bool done_valid = false;             // `done` has been recorded at least once

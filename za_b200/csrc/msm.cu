@@ -1314,8 +1314,19 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
             XYZZ<F>* d_out3 = d_r + r_elems;
             const XYZZ<F>* d_c = d_buckets;
             if (H > 1) {
-                // row sums: every row (Lw contiguous buckets) is a batch of Lw one-point "rows" for the same kernel
+                // row sums: every row (Lw contiguous buckets) is a batch of Lw one-point "rows" for the same kernel.  They
+                // run on the slot's second side stream, next to the column sums (both chains are latency bound)
+                if (!sl.side2) {
+                    int lo_prio = 0, hi_prio = 0;
+                    ZA_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+                    ZA_CUDA(cudaStreamCreateWithPriority(&sl.side2, cudaStreamNonBlocking, hi_prio));
+                    ZA_CUDA(cudaEventCreateWithFlags(&sl.red_fork, cudaEventDisableTiming));
+                    ZA_CUDA(cudaEventCreateWithFlags(&sl.red_join, cudaEventDisableTiming));
+                }
+                ZA_CUDA(cudaEventRecord(sl.red_fork, side));
+                ZA_CUDA(cudaStreamWaitEvent(sl.side2, sl.red_fork, 0));
                 {
+                    cudaStream_t side = sl.side2;        // shadows the slot's first side stream inside this block
                     const uint32_t rows = (uint32_t)Wr * H;
                     const XYZZ<F>* cur = d_buckets;
                     int pp = 0;
@@ -1329,6 +1340,7 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
                         pp ^= 1;
                         cnt = cnt_out;
                     }
+                    ZA_CUDA(cudaEventRecord(sl.red_join, side));
                 }
                 // column sums: H rows of Lw points, eight rows per thread and stage
                 const XYZZ<F>* cur = d_buckets;
@@ -1343,6 +1355,7 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
                     rows_in = rows_out;
                 }
                 d_c = cur;
+                ZA_CUDA(cudaStreamWaitEvent(side, sl.red_join, 0));
             }
             msm_small_weighted_kernel<F><<<2 * Wr, 256, 0, side>>>(d_r, H > 1 ? H : 0, d_c, Lw, (uint32_t)Wr, d_out3);
             ctx->launches++;
