@@ -337,6 +337,9 @@ def run_gpu(args):
         breakdown = {k: round(v["ms"] / steps_profiled, 4) for k, v in prof.items() if v["ms"] > 0}
         breakdown["note"] = "event time per kernel class per step; the classes run on concurrent streams, so the sum exceeds the step"
         h2d = int(wit_host.numel())
+        # read back per proof: six partial results of the bucket reduction per multiexp (4 x G1 of 128 B points, 1 x G2 of
+        # 256 B points) and the 8-byte verdict of the witness range check; the proof itself is assembled on the host
+        D2H_BYTES = 4 * 6 * 128 + 6 * 256 + 8
         line = {"metric": METRIC, "value": prove_ms, "unit": "ms", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": prove_ms,
                 "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                 "config": {"workload": f"synthetic mul-chain R1CS, {nc} constraints (domain 2^{log_m}), {na} aux: "
@@ -345,7 +348,7 @@ def run_gpu(args):
                            "log_m": log_m, "parallelism": f"msm point-range x{world}, rank 0 (H pipeline) takes {rank0_weight:.3f} of a share of the witness multiexps" if world > 1 else "single GPU",
                            "l2": "inputs larger than L2: proving key 470 MB + witness 32 MB per step"},
                 "roofline": roofline, "roofline_g2": roofline_g2, "roofline_ntt": roofline_ntt, "kernel_ms_per_step": breakdown,
-                "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 256 + 16 * 128 * 5 + 16 * 256},
+                "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": D2H_BYTES},
                 "gpu_launches": int(launches), "clocks": clocks, "imad_peak_timads": imad_peak / 1e12}
 
     # ---- sub-metrics: 2^log_msm-point G1 MSM (point range sharded over the ranks, fixed-base table per shard,
