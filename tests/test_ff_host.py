@@ -115,3 +115,7 @@ def test_curve_ops_host(shim):
     k = rng.randrange(P.R_MOD)
     o = PT(); shim.shim_g1_mul(pack(p5), tol(k), o); assert unpack(o) == P.g1_mul(p5, k)
     o = PT(); shim.shim_g1_mul(pack(p5), tol(P.R_MOD), o); assert unpack(o) is None
+    # external known answer (EIP-196 test vectors): 2 * (1, 2), through the product's own ec.cuh
+    two_g = (0x030644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd3, 0x15ed738c0e0a7c92e7845f96b2ae9c0a68a6a449e3538fc7ff3ebf7a5a18a2c4)
+    o = PT(); shim.shim_g1_mul(pack(P.G1_GEN), tol(2), o); assert unpack(o) == two_g
+    o = PT(); shim.shim_g1_add(pack(P.G1_GEN), pack(P.G1_GEN), o); assert unpack(o) == two_g

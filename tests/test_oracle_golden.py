@@ -211,3 +211,22 @@ def test_babyjub_add_restatement_matches_the_reference_kats():
             lc = [sum(int.from_bytes(coeff[w][t].tobytes(), "little") * val(int(var[w][t])) for t in range(ptr[w][k], ptr[w][k + 1])) % P.R_MOD
                   for w in range(3)]
             assert lc[0] * lc[1] % P.R_MOD == lc[2]
+
+
+# An EXTERNAL known answer for the curve arithmetic (not from the reference tree, which holds none): 2 * (1, 2) on
+# alt_bn128, the value the EIP-196 ecAdd / ecMul test vectors publish.  Written down from memory and checked here against
+# three independent implementations: the python-integer reference, the C oracle and (tests/test_ff_host.py) the
+# product's own host build of ec.cuh.
+ALT_BN128_2G = (0x030644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd3,
+                0x15ed738c0e0a7c92e7845f96b2ae9c0a68a6a449e3538fc7ff3ebf7a5a18a2c4)
+
+
+def test_published_double_of_the_generator():
+    assert P.g1_add(P.G1_GEN, P.G1_GEN) == ALT_BN128_2G and P.g1_mul(P.G1_GEN, 2) == ALT_BN128_2G
+    assert O.g1_add(P.G1_GEN, P.G1_GEN) == ALT_BN128_2G and O.g1_mul(P.G1_GEN, 2) == ALT_BN128_2G
+    assert P.g1_on_curve(ALT_BN128_2G)
+    # BN parameter u = 4965661367192848881: q = 36u^4 + 36u^3 + 24u^2 + 6u + 1, r = 36u^4 + 36u^3 + 18u^2 + 6u + 1 tie the
+    # two moduli of the reference tree (fs.rs:15-16, ethereum.rs:37) to the published curve family
+    u = 4965661367192848881
+    assert P.Q_MOD == 36 * u ** 4 + 36 * u ** 3 + 24 * u ** 2 + 6 * u + 1
+    assert P.R_MOD == 36 * u ** 4 + 36 * u ** 3 + 18 * u ** 2 + 6 * u + 1
