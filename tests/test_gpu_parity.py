@@ -245,6 +245,16 @@ def test_create_proof_circomlib_babyadd(ctx, kat):
     assert tuple(pub) == expect
 
 
+def test_create_proof_config3_eddsa_mimc(ctx):
+    """Config 3: the EdDSA-MiMC verification statement of circomlib (hand-built R1CS, tests/eddsa_circuit.py: 7 429
+    constraints, domain 2^13, thousands of boolean witness signals, partial A/B densities) on the reference's own
+    signature vector: every intermediate vector and multiexp and the proof bit-identical to the oracle's."""
+    from tests import eddsa_circuit as E
+    cs, info = E.eddsa_mimc_verifier(**E.KAT)
+    proof, pub, prm = _prove_case(ctx, cs, [0x5A410003, 3, 5, 7, 11], r=2 ** 190 + 1, s=2 ** 90 + 7)
+    assert pub[-1] == 1234 and prm.verify(proof, pub[:-1] + [1235]) == 0
+
+
 def test_create_proof_rejects_non_canonical_witness(ctx):
     """A witness element >= r is refused (ZA_ERR_NOT_CANONICAL, first offending index named) — the range check runs on
     the uploaded copy on the GPU — and the same call with the value reduced still proves."""

@@ -5,6 +5,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 
 from tests import oracle as O
 from tests import pyref as P
@@ -230,3 +231,28 @@ def test_published_double_of_the_generator():
     u = 4965661367192848881
     assert P.Q_MOD == 36 * u ** 4 + 36 * u ** 3 + 24 * u ** 2 + 6 * u + 1
     assert P.R_MOD == 36 * u ** 4 + 36 * u ** 3 + 18 * u ** 2 + 6 * u + 1
+
+
+def test_eddsa_mimc_statement_on_the_reference_vector():
+    """Config 3: the statement of circomlib's EdDSAMiMCVerifier (eddsamimc.circom:27-128) restated with python integers
+    accepts the reference's own test vector (za_test/eddsamimc.za:4-13) — MiMC7 round constants extracted into
+    tests/golden/mimc7_constants.json — the hand-built R1CS (tests/eddsa_circuit.py) is satisfied by its witness, a
+    tampered message is not, and the oracle's proof verifies with the seven public inputs and fails with a wrong one."""
+    from tests import eddsa_circuit as E
+    c = E.mimc7_constants()
+    k = E.KAT
+    h = E.multi_mimc7([k["R8x"], k["R8y"], k["Ax"], k["Ay"], k["M"]], 0, c)
+    a8 = E.baby_mul((k["Ax"], k["Ay"]), 8)
+    assert E.baby_mul(E.BASE8, k["S"]) == E.baby_add((k["R8x"], k["R8y"]), E.baby_mul(a8, h))
+    (ni, na, ptr, var, coeff, inputs, aux), info = E.eddsa_mimc_verifier(**k)
+    assert info["h"] == h and ni == 8 and info["constraints"] > 7000
+    ones = sum(1 for v in aux if int.from_bytes(v.tobytes(), "little") in (0, 1))
+    assert ones > 500                                              # bit-heavy witness (SURVEY §8d config 3)
+    with pytest.raises(AssertionError):
+        E.eddsa_mimc_verifier(**dict(k, M=1235))
+    ocs = O.CS(ni, na, ptr, var, coeff)
+    prm = O.Params.generate(ocs, [0x5A410003, 3, 5, 7, 11], threads=8)
+    rc, proof = prm.create_proof(ocs, inputs, aux, 2 ** 190 + 1, 2 ** 90 + 7, threads=8)
+    assert rc == 0
+    pub = [int.from_bytes(inputs[i].tobytes(), "little") for i in range(1, ni)]
+    assert prm.verify(proof, pub) == 1 and prm.verify(proof, pub[:-1] + [1235]) == 0
