@@ -433,6 +433,29 @@ def run_gpu(args):
                                         "verify_proof_host_ms": (t5 - t4) * 1e3, "proof_verifies": bool(ok),
                                         "wrong_public_input_rejected": bool(not bad), "timing": "host wall clock, one call each"}
             del pk2, circ2, blob
+        if world == 1 and not args.no_config3:
+            # config 3 (BASELINE.json): the EdDSA-MiMC verification statement of circomlib as a hand-built R1CS
+            # (tests/eddsa_circuit.py, 7 429 constraints, bit-heavy witness) through setup -> read -> prove -> verify
+            try:
+                from tests import eddsa_circuit as E3
+                (ni3, na3, ptr3, var3, coeff3, in3, aux3), info3 = E3.eddsa_mimc_verifier(**E3.KAT)
+                circ3 = za_b200.Circuit(ctx, ni3, na3, ptr3, var3, coeff3)
+                pk3 = za_b200.Parameters.read(ctx, za_b200.generate_parameters(ctx, circ3, 0x5A410031, 0x5A410032, 0x5A410033, 0x5A410034, 0x5A410035), checked=True)
+                for _ in range(3):
+                    pr3 = za_b200.create_proof(ctx, pk3, circ3, in3, aux3, R_FIXED, S_FIXED)
+                t0 = time.perf_counter()
+                reps3 = 10
+                for _ in range(reps3):
+                    pr3 = za_b200.create_proof(ctx, pk3, circ3, in3, aux3, R_FIXED, S_FIXED)
+                t1 = time.perf_counter()
+                pub3 = [int.from_bytes(in3[i].tobytes(), "little") for i in range(1, ni3)]
+                sub["config3_eddsa_mimc"] = {"constraints": info3["constraints"], "num_aux": na3, "create_proof_host_buffers_ms": (t1 - t0) * 1e3 / reps3,
+                                             "proof_verifies": bool(za_b200.verify_proof(pk3.vk(), pr3, pub3)),
+                                             "wrong_message_rejected": bool(not za_b200.verify_proof(pk3.vk(), pr3, pub3[:-1] + [1235])),
+                                             "note": "statement of circomlib EdDSAMiMCVerifier on the vector of za_test/eddsamimc.za, R1CS built by hand (not za's compiler output)"}
+                del pk3, circ3
+            except Exception as e:      # a sub-metric must never cost the headline line
+                sub["config3_eddsa_mimc"] = {"error": repr(e)[:200]}
         if line is not None:
             line["submetrics"] = sub
 
@@ -495,6 +518,7 @@ def main():
     ap.add_argument("--log-m", dest="log_m", type=int, default=20, help="log2 of the evaluation domain of the prove workload")
     ap.add_argument("--log-msm", dest="log_msm", type=int, default=24)
     ap.add_argument("--log-ntt", dest="log_ntt", type=int, default=24)
+    ap.add_argument("--no-config3", dest="no_config3", action="store_true", help="skip the config-3 (EdDSA-MiMC) sub-metric")
     ap.add_argument("--log-setup", dest="log_setup", type=int, default=18, help="domain of the real-key pipeline sub-metric (0 = skip)")
     ap.add_argument("--cpu-log-m", dest="cpu_log_m", type=int, default=20, help="domain of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
