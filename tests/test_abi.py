@@ -119,3 +119,33 @@ def test_za2c_setup_and_prove_fail_loudly_without_the_front_end():
     assert L.setup(b"circuit.za", b"proving.key", b"json", out, 64, err, 1024) == 100 and b"za_generate_parameters" in err.value
     assert L.setup(b"circuit.za", b"proving.key", b"yaml", out, 64, err, 1024) == 100 and err.value == b"invalid validator type"
     assert L.prove(b"proving.key", b"{}", out, 64, err, 8) == 1
+
+
+def test_headers_are_plain_c_and_a_c_program_links(tmp_path):
+    """The boundary is a C ABI: both headers compile as C99 (no C++, no torch types) and a C program that calls through
+    them links against the two libraries and runs the host-only entry points (no GPU needed for these)."""
+    import subprocess
+    from za_b200 import build as zb
+    src = tmp_path / "abi_smoke.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "za_b200.h"
+#include "za2c.h"
+int main(void) {
+    char err[256];
+    if (za_version() < 1) return 1;
+    if (verify("{", "{", err, sizeof err) != ZA2C_ERR_CUSTOM) return 2;      /* malformed JSON -> 100, text in err */
+    if (strlen(err) == 0) return 3;
+    if (prove("proving.key", "{}", err, 4, err, 4) != ZA2C_ERR_BUFFER_TOO_SMALL) return 4;
+    printf("devices %d\n", za_device_count());
+    return 0;
+}
+''')
+    exe = tmp_path / "abi_smoke"
+    lib_dir = os.path.dirname(zb.OUT)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L" + lib_dir, "-lza2c", "-lza_b200", "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert out.stdout.startswith("devices ")
