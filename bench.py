@@ -286,7 +286,12 @@ def run_gpu(args):
 
     iso1 = iso2 = iso_ntt = None
     if rank == 0 and world == 1 and log_m <= 22:
-        iso1, iso2, iso_ntt = isolated_accumulation(1), isolated_accumulation(2), isolated_ntt()
+        try:
+            iso1, iso2, iso_ntt = isolated_accumulation(1), isolated_accumulation(2), isolated_ntt()
+        except Exception as e:          # fall back to the in-step event times rather than lose the line
+            print(f"isolated kernel timing failed: {e!r}", file=sys.stderr)
+            ctx.profile(False)
+            iso1 = iso2 = iso_ntt = None
 
     line = None
     if rank == 0:
@@ -409,30 +414,33 @@ def run_gpu(args):
                              "order": "natural in, natural out, forward"}
             del v
         if world == 1 and args.log_setup > 0:
-            # the rows either side of create_proof on a REAL key: generate_parameters on the
-            # GPU -> Parameters::write stream -> Parameters::read(checked) -> create_proof (host buffers) -> verify_proof
-            log_s = min(log_m, args.log_setup)
-            nc_s = (1 << log_s) - 2
-            ni2, na2, ptr2, var2, coeff2, in2, aux2 = synthetic.mul_chain(nc_s, x0=0x5A410002)
-            circ2 = za_b200.Circuit(ctx, ni2, na2, ptr2, var2, coeff2)
-            t0 = time.perf_counter()
-            blob = za_b200.generate_parameters(ctx, circ2, 0x5A410011, 0x5A410012, 0x5A410013, 0x5A410014, 0x5A410015)
-            t1 = time.perf_counter()
-            pk2 = za_b200.Parameters.read(ctx, blob, checked=True)
-            t2 = time.perf_counter()
-            pr2 = za_b200.create_proof(ctx, pk2, circ2, in2, aux2, R_FIXED, S_FIXED)      # first call: buffers are allocated
-            t3 = time.perf_counter()
-            pr2 = za_b200.create_proof(ctx, pk2, circ2, in2, aux2, R_FIXED, S_FIXED)
-            t4 = time.perf_counter()
-            pub = [int.from_bytes(in2[i].tobytes(), "little") for i in range(1, ni2)]
-            ok = za_b200.verify_proof(pk2.vk(), pr2, pub)
-            t5 = time.perf_counter()
-            bad = za_b200.verify_proof(pk2.vk(), pr2, [(pub[0] + 1) % R_MOD] + pub[1:])
-            sub["real_key_pipeline"] = {"log_m": log_s, "parameters_bytes": len(blob), "generate_parameters_ms": (t1 - t0) * 1e3,
-                                        "parameters_read_checked_ms": (t2 - t1) * 1e3, "create_proof_host_buffers_ms": (t4 - t3) * 1e3,
-                                        "verify_proof_host_ms": (t5 - t4) * 1e3, "proof_verifies": bool(ok),
-                                        "wrong_public_input_rejected": bool(not bad), "timing": "host wall clock, one call each"}
-            del pk2, circ2, blob
+            try:
+                # the rows either side of create_proof on a REAL key: generate_parameters on the
+                # GPU -> Parameters::write stream -> Parameters::read(checked) -> create_proof (host buffers) -> verify_proof
+                log_s = min(log_m, args.log_setup)
+                nc_s = (1 << log_s) - 2
+                ni2, na2, ptr2, var2, coeff2, in2, aux2 = synthetic.mul_chain(nc_s, x0=0x5A410002)
+                circ2 = za_b200.Circuit(ctx, ni2, na2, ptr2, var2, coeff2)
+                t0 = time.perf_counter()
+                blob = za_b200.generate_parameters(ctx, circ2, 0x5A410011, 0x5A410012, 0x5A410013, 0x5A410014, 0x5A410015)
+                t1 = time.perf_counter()
+                pk2 = za_b200.Parameters.read(ctx, blob, checked=True)
+                t2 = time.perf_counter()
+                pr2 = za_b200.create_proof(ctx, pk2, circ2, in2, aux2, R_FIXED, S_FIXED)      # first call: buffers are allocated
+                t3 = time.perf_counter()
+                pr2 = za_b200.create_proof(ctx, pk2, circ2, in2, aux2, R_FIXED, S_FIXED)
+                t4 = time.perf_counter()
+                pub = [int.from_bytes(in2[i].tobytes(), "little") for i in range(1, ni2)]
+                ok = za_b200.verify_proof(pk2.vk(), pr2, pub)
+                t5 = time.perf_counter()
+                bad = za_b200.verify_proof(pk2.vk(), pr2, [(pub[0] + 1) % R_MOD] + pub[1:])
+                sub["real_key_pipeline"] = {"log_m": log_s, "parameters_bytes": len(blob), "generate_parameters_ms": (t1 - t0) * 1e3,
+                                            "parameters_read_checked_ms": (t2 - t1) * 1e3, "create_proof_host_buffers_ms": (t4 - t3) * 1e3,
+                                            "verify_proof_host_ms": (t5 - t4) * 1e3, "proof_verifies": bool(ok),
+                                            "wrong_public_input_rejected": bool(not bad), "timing": "host wall clock, one call each"}
+                del pk2, circ2, blob
+            except Exception as e:      # a sub-metric must never cost the headline line
+                sub["real_key_pipeline"] = {"error": repr(e)[:200]}
         if world == 1 and not args.no_config3:
             # config 3 (BASELINE.json): the EdDSA-MiMC verification statement of circomlib as a hand-built R1CS
             # (tests/eddsa_circuit.py, 7 429 constraints, bit-heavy witness) through setup -> read -> prove -> verify
