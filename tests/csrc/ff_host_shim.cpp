@@ -43,3 +43,14 @@ void shim_g1_mul(const uint32_t* a, const uint32_t* k, uint32_t* r) {
     st_aff(r, xyzz_to_affine<Fq>(xyzz_mul<Fq>(G1XYZZ::from_affine(ld_aff(a)), k)));
 }
 }
+// round 2: dedicated squaring, 512-bit products, stand-alone reduction, lazily reduced Fq2 product
+extern "C" {
+UNOP(shim_fr_sqr, Fr, fp_sqr(x))
+UNOP(shim_fq_sqr, Fq, fp_sqr(x))
+BINOP(shim_fq2_mul_lazy, Fq2, fq2_mul_lazy(x, y))
+BINOP(shim_fq2_mul_karatsuba, Fq2, fq2_mul_karatsuba(x, y))
+void shim_mul_wide(const uint32_t* a, const uint32_t* b, uint32_t* t) { uint32_t w[16]; memset(w, 0xa5, sizeof w); u256_mul_wide(w, a, b); memcpy(t, w, sizeof w); }
+void shim_sqr_wide(const uint32_t* a, uint32_t* t) { uint32_t w[16]; memset(w, 0xa5, sizeof w); u256_sqr_wide(w, a); memcpy(t, w, sizeof w); }
+void shim_fq_redc_wide(const uint32_t* t, uint32_t* r) { Fq z = fp_redc_wide<FqParams>(t); memcpy(r, &z, sizeof z); }
+void shim_fr_redc_wide(const uint32_t* t, uint32_t* r) { Fr z = fp_redc_wide<FrParams>(t); memcpy(r, &z, sizeof z); }
+}

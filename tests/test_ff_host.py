@@ -119,3 +119,46 @@ def test_curve_ops_host(shim):
     two_g = (0x030644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd3, 0x15ed738c0e0a7c92e7845f96b2ae9c0a68a6a449e3538fc7ff3ebf7a5a18a2c4)
     o = PT(); shim.shim_g1_mul(pack(P.G1_GEN), tol(2), o); assert unpack(o) == two_g
     o = PT(); shim.shim_g1_add(pack(P.G1_GEN), pack(P.G1_GEN), o); assert unpack(o) == two_g
+
+
+def test_wide_products_and_reduction(shim):
+    """u256_mul_wide / u256_sqr_wide on arbitrary 256-bit operands (the lazily reduced Fq2 product feeds unreduced sums
+    below 2^255 and full limbs), fp_redc_wide on every T < p 2^256, and the dedicated squaring."""
+    rng = random.Random(7)
+    full = (1 << 256) - 1
+    ops = [0, 1, full, full - 1, 1 << 255, (1 << 255) - 1, 0xFFFFFFFF, full ^ 0xFFFFFFFF, P.Q_MOD, 2 * P.Q_MOD - 2, P.R_MOD - 1] + \
+          [rng.getrandbits(256) for _ in range(200)] + [rng.getrandbits(256) | (full << 224 & full) for _ in range(20)]
+    T16 = ctypes.c_uint32 * 16
+    for x in ops:
+        o = T16(); shim.shim_sqr_wide(tol(x), o); assert frl(o) == x * x, hex(x)
+        for y in rng.sample(ops, 6) + [full, 0, 1]:
+            o = T16(); shim.shim_mul_wide(tol(x), tol(y), o); assert frl(o) == x * y, (hex(x), hex(y))
+    for name, p in (("fr", P.R_MOD), ("fq", P.Q_MOD)):
+        Ri = pow(R, -1, p)
+        wide = [0, 1, p, p * R - 1, p * R - p, (p - 1) * (p - 1), 2 * (p - 1) * (p - 1), R - 1, R, R + 1, (R - 1) * p] + \
+               [rng.randrange(p * R) for _ in range(300)]
+        for t in wide:
+            o = A(); getattr(shim, f"shim_{name}_redc_wide")(T16(*[(t >> (32 * i)) & 0xFFFFFFFF for i in range(16)]), o)
+            assert frl(o) == t * Ri % p, hex(t)
+        edge = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, R % p, (1 << 253), p - (1 << 200), (1 << 254) - 1 if (1 << 254) - 1 < p else p - 3]
+        for x in edge + [rng.randrange(p) for _ in range(300)]:
+            assert unop(shim, f"shim_{name}_sqr", x) == x * x * Ri % p, hex(x)
+    assert shim.shim_lost_carries() == 0
+
+
+def test_fq2_lazy_product(shim):
+    """Three wide products + two reductions == Karatsuba with three full products == the python reference,
+    including the operands that make a0 b0 - a1 b1 negative, zero, and the largest sums."""
+    rng = random.Random(8)
+    q = P.Q_MOD
+    def pack(a): return A2(*[(v >> (32 * i)) & 0xFFFFFFFF for v in a for i in range(8)])
+    def unpack(o): return (frl(o[:8]), frl(o[8:]))
+    Ri = pow(R, -1, q)
+    edge = [0, 1, q - 1, q - 2, (q - 1) // 2, R % q]
+    cases = [((a0, a1), (b0, b1)) for a0 in edge for a1 in edge for b0 in (0, 1, q - 1) for b1 in (0, q - 1, 5)]
+    cases += [((rng.randrange(q), rng.randrange(q)), (rng.randrange(q), rng.randrange(q))) for _ in range(300)]
+    for a, b in cases:
+        want = ((a[0] * b[0] - a[1] * b[1]) * Ri % q, (a[0] * b[1] + a[1] * b[0]) * Ri % q)
+        o = A2(); shim.shim_fq2_mul_lazy(pack(a), pack(b), o); assert unpack(o) == want, (a, b)
+        o = A2(); shim.shim_fq2_mul_karatsuba(pack(a), pack(b), o); assert unpack(o) == want, (a, b)
+    assert shim.shim_lost_carries() == 0

@@ -7,7 +7,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libza_b200.so")
+# ZA_B200_SO: development override (a variant build from `python -m za_b200.build --variant`); it must still be a build
+# of this library — every symbol of include/za_b200.h is resolved below
+SO_PATH = os.environ.get("ZA_B200_SO") or os.path.join(_HERE, "libza_b200.so")
 
 ZA_OK = 0
 ERR_NAMES = {

@@ -27,6 +27,28 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def build_variant(tag, defines, verbose=False):
+    """Development only: a second copy of the library compiled with extra -D flags into za_b200/variants/ (selected at
+    run time with ZA_B200_SO=<path>) so that one GPU call can time several code variants side by side."""
+    out_dir = os.path.join(HERE, "variants")
+    os.makedirs(os.path.join(out_dir, "build_" + tag), exist_ok=True)
+    out = os.path.join(out_dir, f"libza_b200_{tag}.so")
+    procs, objs = [], []
+    for s in SOURCES:
+        o = os.path.join(out_dir, "build_" + tag, s + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
+    for s, p in procs:
+        o, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {s} ({tag}):\n{o}")
+        if verbose:
+            sys.stderr.write(o)
+    subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs + ["-lcudart"])
+    return out
+
+
 def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     if not force and not needs_build():
@@ -66,4 +88,8 @@ def build_za2c():
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:       # python -m za_b200.build --variant TAG DEFINE [DEFINE ...]
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if not a.startswith("-")], verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -201,10 +201,10 @@ static __device__ __forceinline__ void g1_madd_hot(XYZZ<Fq>& acc, const Fq& x, c
         else acc = XYZZ<Fq>::inf();
         return;
     }
-    Fq PP = fq_mul_call(P, P);
+    Fq PP = fq_sqr_call(P);
     Fq PPP = fq_mul_call(P, PP);
     Fq Q = fq_mul_call(acc.X, PP);
-    Fq X3 = fq_mul_call(R, R) - PPP - dbl(Q);
+    Fq X3 = fq_sqr_call(R) - PPP - dbl(Q);
     acc.Y = fq_mul_call(R, Q - X3) - fq_mul_call(acc.Y, PPP);
     acc.X = X3;
     acc.ZZ = fq_mul_call(acc.ZZ, PP);

@@ -368,8 +368,164 @@ ZA_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
 #endif
 }
 
+// ---------------------------------------------------------------------------
+// 512-bit products, the stand-alone Montgomery reduction, and what is built on them: a dedicated squaring
+// (36 limb products instead of 64) and the lazily reduced Fq2 product (three wide products, two reductions).
+// Same instruction discipline as fp_mad_redc: independent mul.wide products folded in with add.cc chains, the
+// q*p rows as mad.lo.cc / madc.hi.cc pairs.
+// ---------------------------------------------------------------------------
+// T[0..15] = a * b for any 256-bit a, b.  X collects the products a_j b_i with j even (limb i + j), Y those with j odd
+// (limb i + j, kept one limb lower); each half-row tiles eight consecutive limbs, so a row is two carry chains.
+ZA_HD void u256_mul_wide(uint32_t* T, const uint32_t* a, const uint32_t* b) {
+    uint32_t Y[16];
+    uint32_t* X = T;
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        p_mul_wide(X[j], X[j + 1], a[j], b[0]);
+        p_mul_wide(Y[j], Y[j + 1], a[j + 1], b[0]);
+    }
+    X[8] = 0; Y[8] = 0;
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+        uint32_t pl[8], ph[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) p_mul_wide(pl[j], ph[j], a[j], b[i]);
+        X[i] = p_add_cc(X[i], pl[0]);
+        X[i + 1] = p_addc_cc(X[i + 1], ph[0]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            X[i + j] = p_addc_cc(X[i + j], pl[j]);
+            X[i + j + 1] = p_addc_cc(X[i + j + 1], ph[j]);
+        }
+        X[i + 8] = p_addc(0u, 0u);
+        Y[i] = p_add_cc(Y[i], pl[1]);
+        Y[i + 1] = p_addc_cc(Y[i + 1], ph[1]);
+#pragma unroll
+        for (int j = 2; j < 6; j += 2) {
+            Y[i + j] = p_addc_cc(Y[i + j], pl[j + 1]);
+            Y[i + j + 1] = p_addc_cc(Y[i + j + 1], ph[j + 1]);
+        }
+        Y[i + 6] = p_addc_cc(Y[i + 6], pl[7]);
+        if (i < 7) { Y[i + 7] = p_addc_cc(Y[i + 7], ph[7]); Y[i + 8] = p_addc(0u, 0u); }
+        else Y[i + 7] = p_addc(Y[i + 7], ph[7]);       // 2^32 Y <= a b: limb 15 of Y stays empty
+    }
+    // T = X + 2^32 Y
+    T[1] = p_add_cc(X[1], Y[0]);
+#pragma unroll
+    for (int k = 2; k < 15; k++) T[k] = p_addc_cc(X[k], Y[k - 1]);
+    T[15] = p_addc(X[15], Y[14]);
+}
+
+// T[0..15] = a^2.  The 28 cross products a_i a_j (i < j) by diagonals d = j - i — diagonal d tiles the limbs
+// [d, 16 - d) — doubled, plus the eight squares, which tile all 16 limbs.
+ZA_HD void u256_sqr_wide(uint32_t* T, const uint32_t* a) {
+    uint32_t S[16], c[8];
+    S[0] = 0; S[15] = 0;
+#pragma unroll
+    for (int i = 0; i < 7; i++) p_mul_wide(S[2 * i + 1], S[2 * i + 2], a[i], a[i + 1]);
+#pragma unroll
+    for (int d = 2; d < 8; d++) {
+        uint32_t pl[6], ph[6];
+#pragma unroll
+        for (int i = 0; i + d < 8; i++) p_mul_wide(pl[i], ph[i], a[i], a[i + d]);
+        S[d] = p_add_cc(S[d], pl[0]);
+        S[d + 1] = p_addc_cc(S[d + 1], ph[0]);
+#pragma unroll
+        for (int i = 1; i + d < 8; i++) {
+            S[2 * i + d] = p_addc_cc(S[2 * i + d], pl[i]);
+            S[2 * i + d + 1] = p_addc_cc(S[2 * i + d + 1], ph[i]);
+        }
+        c[d] = p_addc(0u, 0u);                          // carry out of the diagonal: one unit of limb 16 - d
+    }
+    S[9] = p_add_cc(S[9], c[7]);
+#pragma unroll
+    for (int k = 10; k < 15; k++) S[k] = p_addc_cc(S[k], c[16 - k]);
+    S[15] = p_addc(S[15], 0u);
+    // T = 2 S + sum a_i^2 2^(64 i)
+    uint32_t ql[8], qh[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) p_mul_wide(ql[i], qh[i], a[i], a[i]);
+    S[1] = p_add_cc(S[1], S[1]);
+#pragma unroll
+    for (int k = 2; k < 15; k++) S[k] = p_addc_cc(S[k], S[k]);
+    S[15] = p_addc(S[15], S[15]);
+    T[0] = ql[0];
+    T[1] = p_add_cc(S[1], qh[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) {
+        T[2 * i] = p_addc_cc(S[2 * i], ql[i]);
+        T[2 * i + 1] = p_addc_cc(S[2 * i + 1], qh[i]);
+    }
+    T[14] = p_addc_cc(S[14], ql[7]);
+    T[15] = p_addc(S[15], qh[7]);
+}
+
+// One round of the stand-alone reduction: (E, O) += q p with q = -E[0] / p mod 2^32, then the implicit >> 32 by
+// role swap.  The previous round's odd array is shifted down by two limbs inside the multiply-adds (its limb 1,
+// now of weight 2^0, moves over to E[0] first).
+template <class P, bool FIRST>
+ZA_HD void fp_redc_round(uint32_t* E, uint32_t* O) {
+    if (!FIRST) E[0] = p_add_cc(E[0], O[1]);
+    const uint32_t q = p_mul_lo(E[0], P::inv);
+    if (FIRST) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) p_mul_wide(O[j], O[j + 1], P::mod(j + 1), q);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 6; j += 2) {
+            O[j] = p_madc_lo_cc(P::mod(j + 1), q, O[j + 2]);
+            O[j + 1] = p_madc_hi_cc(P::mod(j + 1), q, O[j + 3]);
+        }
+        O[6] = p_madc_lo_cc(P::mod(7), q, 0u);
+        O[7] = p_madc_hi(P::mod(7), q, 0u);
+    }
+    E[0] = p_mad_lo_cc(P::mod(0), q, E[0]);
+    E[1] = p_madc_hi_cc(P::mod(0), q, E[1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+        E[j] = p_madc_lo_cc(P::mod(j), q, E[j]);
+        E[j + 1] = p_madc_hi_cc(P::mod(j), q, E[j + 1]);
+    }
+    O[7] = p_addc(O[7], 0u);
+}
+
+// T / 2^256 mod p for T < p 2^256, result in [0, p).  Only the low half takes part in the eight rounds (a Montgomery
+// product of T_lo by 1, at most p); the high half is added at the end: (T_lo + sum q_i p 2^(32 i)) / 2^256 + T_hi < 2 p.
 template <class P>
-ZA_HD Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul<P>(a, a); }
+ZA_HD Fp<P> fp_redc_wide(const uint32_t* T) {
+    uint32_t ev[8], od[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) ev[i] = T[i];
+    fp_redc_round<P, true>(ev, od);
+    fp_redc_round<P, false>(od, ev);
+#pragma unroll
+    for (int i = 2; i < 8; i += 2) {
+        fp_redc_round<P, false>(ev, od);
+        fp_redc_round<P, false>(od, ev);
+    }
+    Fp<P> r;
+    r.v[0] = p_add_cc(ev[0], od[1]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = p_addc_cc(ev[i], od[i + 1]);
+    r.v[7] = p_addc(ev[7], 0u);
+    r.v[0] = p_add_cc(r.v[0], T[8]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.v[i] = p_addc_cc(r.v[i], T[8 + i]);
+    r.v[7] = p_addc(r.v[7], T[15]);
+    fp_final_sub<P>(r.v);
+    return r;
+}
+
+template <class P>
+ZA_HD Fp<P> fp_sqr(const Fp<P>& a) {
+#if !defined(__CUDA_ARCH__) && !defined(ZA_FF_EMULATE_PTX)
+    return fp_mul<P>(a, a);
+#else
+    uint32_t T[16];
+    u256_sqr_wide(T, a.v);
+    return fp_redc_wide<P>(T);
+#endif
+}
 
 // canonical (non-Montgomery) little-endian limbs  <->  Montgomery
 template <class P>
@@ -518,6 +674,7 @@ template <class P> ZA_HD Fp<P> operator*(const Fp<P>& a, const Fp<P>& b) { retur
 // (Fq2 arithmetic, the G1 bucket-accumulation loop): less code than the instruction cache, seconds of ptxas.
 #if defined(__CUDA_ARCH__)
 static __device__ __noinline__ Fp<FqParams> fq_mul_call(const Fp<FqParams> a, const Fp<FqParams> b) { return fp_mul<FqParams>(a, b); }
+static __device__ __noinline__ Fp<FqParams> fq_sqr_call(const Fp<FqParams> a) { return fp_sqr<FqParams>(a); }
 #endif
 template <class P> ZA_HD Fp<P> operator-(const Fp<P>& a) { return fp_neg<P>(a); }
 template <class P> ZA_HD Fp<P> sqr(const Fp<P>& a) { return fp_sqr<P>(a); }
@@ -546,8 +703,46 @@ ZA_D Fq fq2_base_mul(const Fq& a, const Fq& b) { return fq_mul_call(a, b); }
 #else
 inline Fq fq2_base_mul(const Fq& a, const Fq& b) { return fp_mul<FqParams>(a, b); }
 #endif
+// Lazily reduced Karatsuba: three 512-bit products, two Montgomery reductions (instead of three full products):
+//   c1 = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1   (in [0, 2 p^2), the sums unreduced: < 2^255)
+//   c0 = a0 b0 - a1 b1                        (+ p 2^256 if negative: in [0, p 2^256))
+ZA_HD Fq2 fq2_mul_lazy(const Fq2& a, const Fq2& b) {
+    uint32_t T0[16], T1[16], T2[16], sa[8], sb[8];
+    sa[0] = p_add_cc(a.c0.v[0], a.c1.v[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) sa[i] = p_addc_cc(a.c0.v[i], a.c1.v[i]);
+    sa[7] = p_addc(a.c0.v[7], a.c1.v[7]);
+    sb[0] = p_add_cc(b.c0.v[0], b.c1.v[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) sb[i] = p_addc_cc(b.c0.v[i], b.c1.v[i]);
+    sb[7] = p_addc(b.c0.v[7], b.c1.v[7]);
+    u256_mul_wide(T2, sa, sb);
+    u256_mul_wide(T0, a.c0.v, b.c0.v);
+    T2[0] = p_sub_cc(T2[0], T0[0]);
+#pragma unroll
+    for (int i = 1; i < 15; i++) T2[i] = p_subc_cc(T2[i], T0[i]);
+    T2[15] = p_subc(T2[15], T0[15]);
+    u256_mul_wide(T1, a.c1.v, b.c1.v);
+    T2[0] = p_sub_cc(T2[0], T1[0]);
+#pragma unroll
+    for (int i = 1; i < 15; i++) T2[i] = p_subc_cc(T2[i], T1[i]);
+    T2[15] = p_subc(T2[15], T1[15]);
+    Fq2 r;
+    r.c1 = fp_redc_wide<FqParams>(T2);
+    T0[0] = p_sub_cc(T0[0], T1[0]);
+#pragma unroll
+    for (int i = 1; i < 16; i++) T0[i] = p_subc_cc(T0[i], T1[i]);
+    const uint32_t borrow = p_subc(0u, 0u);
+    T0[8] = p_add_cc(T0[8], FqParams::mod(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < 7; i++) T0[8 + i] = p_addc_cc(T0[8 + i], FqParams::mod(i) & borrow);
+    // the carry out of the top limb cancels the earlier borrow and is discarded on purpose
+    T0[15] = p_addc_cc(T0[15], FqParams::mod(7) & borrow);
+    r.c0 = fp_redc_wide<FqParams>(T0);
+    return r;
+}
 // Karatsuba: 3 Fq products
-ZA_HD Fq2 operator*(const Fq2& a, const Fq2& b) {
+ZA_HD Fq2 fq2_mul_karatsuba(const Fq2& a, const Fq2& b) {
     Fq aa = fq2_base_mul(a.c0, b.c0);
     Fq bb = fq2_base_mul(a.c1, b.c1);
     Fq s = fq2_base_mul(a.c0 + a.c1, b.c0 + b.c1);
@@ -555,6 +750,20 @@ ZA_HD Fq2 operator*(const Fq2& a, const Fq2& b) {
     r.c0 = aa - bb;
     r.c1 = s - aa - bb;
     return r;
+}
+// The Fq2 product of every kernel: on the device ONE shared copy of the lazily reduced product (320 limb
+// products instead of 384); ZA_FQ2_KARATSUBA restores the three full products.  The host uses the 64-bit path.
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ Fq2 fq2_mul_call(const Fq2 a, const Fq2 b) { return fq2_mul_lazy(a, b); }
+#endif
+ZA_HD Fq2 operator*(const Fq2& a, const Fq2& b) {
+#if defined(__CUDA_ARCH__) && !defined(ZA_FQ2_KARATSUBA)
+    return fq2_mul_call(a, b);
+#elif defined(ZA_FF_EMULATE_PTX) && !defined(ZA_FQ2_KARATSUBA)
+    return fq2_mul_lazy(a, b);
+#else
+    return fq2_mul_karatsuba(a, b);
+#endif
 }
 // complex squaring: 2 Fq products
 ZA_HD Fq2 sqr(const Fq2& a) {

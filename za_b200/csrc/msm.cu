@@ -34,6 +34,11 @@
 #ifndef ZA_PAIR_G2_BLOCKS
 #define ZA_PAIR_G2_BLOCKS 2
 #endif
+// register cap of the kernels over Fq2 (accumulation and pair rounds): 255 = two CTAs of 128 threads per SM and nothing
+// else; 192 leaves the registers of one G1 accumulation CTA next to them
+#ifndef ZA_G2_MAXNREG
+#define ZA_G2_MAXNREG 255
+#endif
 
 namespace za {
 
@@ -205,7 +210,7 @@ __global__ void __launch_bounds__(1024) msm_scan_apply_kernel(const uint32_t* co
 // DIRECT: the stream is the output of the pair rounds (K5a) — entry `pos` is the point bases[pos] itself, no sign,
 // and may be the point at infinity (P + (-P) in a round).
 template <class F, bool DIRECT>
-__global__ void __launch_bounds__(128, (sizeof(F) == sizeof(Fq) ? ZA_ACC_G1_BLOCKS : ZA_ACC_G2_BLOCKS)) msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ entries,
+__global__ void __launch_bounds__(128) __maxnreg__(sizeof(F) == sizeof(Fq) ? 512 / ZA_ACC_G1_BLOCKS : ZA_G2_MAXNREG) msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ entries,
                                                              const uint32_t* __restrict__ offsets, uint32_t nkeys, uint32_t Lc,
                                                              XYZZ<F>* bucket_sums, XYZZ<F>* part_head, XYZZ<F>* part_tail,
                                                              uint32_t* tail_owner_key) {
@@ -278,8 +283,10 @@ static __device__ __forceinline__ void sm_st(uint32_t a, const Fq& r) {
 }
 #if defined(__CUDA_ARCH__)
 static __device__ __noinline__ void fq_mul_sm(uint32_t d, uint32_t a, uint32_t b) { sm_st(d, fp_mul<FqParams>(sm_ld(a), sm_ld(b))); }
+static __device__ __noinline__ void fq_sqr_sm(uint32_t d, uint32_t a) { sm_st(d, fp_sqr<FqParams>(sm_ld(a))); }
 #else
 static inline void fq_mul_sm(uint32_t, uint32_t, uint32_t) {}
+static inline void fq_sqr_sm(uint32_t, uint32_t) {}
 #endif
 static __device__ __forceinline__ void cp_async16_sm(uint32_t smem_addr, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
@@ -358,10 +365,10 @@ __global__ void __launch_bounds__(ACC_SM_NT, 4) msm_accumulate_g1_sm_kernel(cons
                     }
                 } else {
                     sm_st(var(AV_P), P); sm_st(var(AV_R), R);
-                    fq_mul_sm(var(AV_PP), var(AV_P), var(AV_P));
+                    fq_sqr_sm(var(AV_PP), var(AV_P));
                     fq_mul_sm(var(AV_PPP), var(AV_P), var(AV_PP));
                     fq_mul_sm(var(AV_Q), var(AV_X), var(AV_PP));
-                    fq_mul_sm(var(AV_P), var(AV_R), var(AV_R));       // R^2 (P is dead)
+                    fq_sqr_sm(var(AV_P), var(AV_R));                  // R^2 (P is dead)
                     const Fq Q = sm_ld(var(AV_Q));
                     const Fq X3 = sm_ld(var(AV_P)) - sm_ld(var(AV_PPP)) - dbl(Q);
                     sm_st(var(AV_X), X3);
@@ -406,10 +413,11 @@ __global__ void __launch_bounds__(ACC_SM_NT, 4) msm_accumulate_g1_sm_kernel(cons
 // After a few rounds the remaining points go through the XYZZ accumulation (DIRECT) as before.
 #if !defined(__CUDA_ARCH__)
 static inline Fq fq_mul_call(const Fq& a, const Fq& b) { return a * b; }      // host pass only parses the kernels
+static inline Fq fq_sqr_call(const Fq& a) { return a * a; }
 #endif
 static __device__ __forceinline__ Fq fmul(const Fq& a, const Fq& b) { return fq_mul_call(a, b); }
 static __device__ __forceinline__ Fq2 fmul(const Fq2& a, const Fq2& b) { return a * b; }
-static __device__ __forceinline__ Fq fsqr(const Fq& a) { return fq_mul_call(a, a); }
+static __device__ __forceinline__ Fq fsqr(const Fq& a) { return fq_sqr_call(a); }
 static __device__ __forceinline__ Fq2 fsqr(const Fq2& a) { return sqr(a); }
 static __device__ __noinline__ Fq fq_inv_call(const Fq a) { return fp_inv_kaliski<FqParams>(a); }
 static __device__ __forceinline__ Fq finv(const Fq& a) { return fq_inv_call(a); }
@@ -458,7 +466,7 @@ template <class F>
 static __device__ __forceinline__ const Affine<F>* pair_ptr(const Affine<F>* pts, uint32_t ref) { return pts + (ref & 0x7fffffffu); }
 
 template <class F, bool FIRST, int NT, int LP>
-__global__ void __launch_bounds__(NT, (sizeof(F) == sizeof(Fq) ? 512 : ZA_PAIR_G2_BLOCKS * 128) / NT) msm_pair_round_kernel(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
+__global__ void __launch_bounds__(NT) __maxnreg__(sizeof(F) == sizeof(Fq) ? 128 : ZA_G2_MAXNREG) msm_pair_round_kernel(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ entries,
                                                                   const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out,
                                                                   uint32_t nkeys, Affine<F>* __restrict__ out) {
     constexpr int FB = sizeof(F) == sizeof(Fq) ? 4 : 2;      // forward pass: loads of FB outputs in flight per thread

@@ -536,8 +536,16 @@ static void prove_msms_enqueue(Ctx* ctx, const Pk* pk, const Circuit* c, const u
             ZA_CUDA(cudaStreamWaitEvent(ctx->g2_stream, ctx->g2_fork, 0));
         }
         multiexp_enqueue<Fq>(ctx, 3, pk->b_g1.get(), lo, sb + lo * 8, hi - lo);
+        // The two B multiexps run over the same exponents and share one digit sort — but only if both resolve to the
+        // same bucket layout: with a fixed-base table on one side only (the G2 table is twice the size and may be over
+        // the memory cap when the G1 table is not) or tables of different window sizes, G2 sorts for itself.
+        int share = -1;
+        if (hi - lo > 64) {
+            const bool t1 = table_for<Fq>(pk->b_g1.get(), lo, hi - lo) != nullptr, t2 = table_for<Fq2>(pk->b_g2.get(), lo, hi - lo) != nullptr;
+            if (t1 == t2 && (!t1 || (pk->b_g1->tab_c == pk->b_g2->tab_c && pk->b_g1->tab_W == pk->b_g2->tab_W))) share = 3;
+        }
         if (!g2_inline) ctx->stream = ctx->g2_stream;
-        try { multiexp_enqueue<Fq2>(ctx, 4, pk->b_g2.get(), lo, sb + lo * 8, hi - lo, hi - lo > 64 ? 3 : -1); }
+        try { multiexp_enqueue<Fq2>(ctx, 4, pk->b_g2.get(), lo, sb + lo * 8, hi - lo, share); }
         catch (...) { ctx->stream = main_st; throw; }
         ctx->stream = main_st;
     }

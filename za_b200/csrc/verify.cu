@@ -184,6 +184,8 @@ struct JVal {
 };
 struct JParser {
     const char* p; const char* end;
+    int depth = 0;                      // serde_json (which the reference parses with) refuses more than 128 nested values
+    static constexpr int MAX_DEPTH = 128;
     void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++; }
     [[noreturn]] void bad(const char* m) { throw ZaError(ZA_ERR_BAD_ENCODING, std::string("json: ") + m); }
     std::string str() {
@@ -198,9 +200,22 @@ struct JParser {
         p++;
         return out;
     }
+    // the whole document: one value, then nothing but white space (serde_json: "trailing characters")
+    JVal document() {
+        JVal v = val();
+        ws();
+        if (p < end) bad("trailing characters after the top-level value");
+        return v;
+    }
+    struct DepthGuard {
+        JParser& j;
+        explicit DepthGuard(JParser& jp) : j(jp) { if (++j.depth > MAX_DEPTH) j.bad("recursion limit exceeded"); }
+        ~DepthGuard() { j.depth--; }
+    };
     JVal val() {
         ws();
         if (p >= end) bad("unexpected end");
+        DepthGuard guard(*this);
         JVal v;
         if (*p == '"') { v.kind = JVal::STR; v.s = str(); }
         else if (*p == '[') {
@@ -317,9 +332,9 @@ int za_verify_json(const char* vk_json, const char* proof_json, int* valid) {
     if (!vk_json || !proof_json || !valid) return fail(ZA_ERR_INVALID, "NULL argument");
     ZA_TRY
     JParser pv{vk_json, vk_json + strlen(vk_json)};
-    JVal v = pv.val();
+    JVal v = pv.document();
     JParser pp{proof_json, proof_json + strlen(proof_json)};
-    JVal p = pp.val();
+    JVal p = pp.document();
     if (v.kind != JVal::OBJ || p.kind != JVal::OBJ) throw ZaError(ZA_ERR_BAD_ENCODING, "json: expected an object");
     const JVal* ic = v.get("ic");
     if (!ic || ic->kind != JVal::ARR) throw ZaError(ZA_ERR_BAD_ENCODING, "json: vk.ic missing");
