@@ -199,6 +199,33 @@ int za_prove_msm_partials(za_ctx *ctx, const za_pk *pk, const za_circuit *circui
 int za_prove_assemble(const za_pk *pk, const uint8_t *partials, int world, const uint8_t *r, const uint8_t *s,
                       uint8_t *proof_out);
 
+/* ---- several GPUs of one box behind ONE call ----------------------------------------------
+ * The reference's caller is a single process (create_random_proof at prover.rs:173).  A za_prover owns a context, the
+ * proving key and the circuit on every listed device and one host thread per device; za_prover_create_proof is
+ * create_proof with every multiexp cut by point range over the devices: device 0 evaluates the constraints and runs
+ * the H-polynomial transforms, writes each peer's slice of the h scalars straight into that peer's memory over
+ * NVLink (cudaMemcpyPeerAsync), every device uploads only the witness span its point ranges read, and the host adds
+ * the per-device partial sums (8 points each) and assembles the proof.  No collective; nothing but CUDA runtime calls.
+ * With one device it is za_create_proof. */
+typedef struct za_prover za_prover;
+int za_prover_create(const int *devices, int n_devices, za_prover **out);
+void za_prover_destroy(za_prover *p);
+int za_prover_device_count(const za_prover *p);
+/* the context of device k (its launch counter and per-class timing: za_ctx_launch_count, za_ctx_profile) */
+za_ctx *za_prover_ctx(za_prover *p, int k);
+/* Parameters::read(params, checked) (format.rs:285) on every device, or a key of known multiples (za_pk_synthetic) */
+int za_prover_load_pk(za_prover *p, const uint8_t *params, size_t len, int checked);
+int za_prover_synthetic_pk(za_prover *p, const uint32_t *counts);
+int za_prover_set_circuit(za_prover *p, const za_r1cs *cs);
+int za_prover_vk(const za_prover *p, uint8_t *vk_out, size_t size);
+int za_prover_pk_counts(const za_prover *p, uint32_t *counts);
+/* create_proof(circuit, params, r, s).  inputs / aux: host buffers as for za_create_proof; inputs == NULL proves the
+ * witness of the last za_prover_upload_witness again (witness resident on the devices: bench.py's `value`). */
+int za_prover_upload_witness(za_prover *p, const uint8_t *inputs, const uint8_t *aux);
+int za_prover_create_proof(za_prover *p, const uint8_t *inputs, const uint8_t *aux, const uint8_t *r, const uint8_t *s,
+                           uint8_t *proof_out);
+uint64_t za_prover_launch_count(const za_prover *p);
+
 /* ---- synthetic inputs and measurement utilities ---------------------------------------
  * bases[i] = (first_multiple + i) * G: distinct points with known discrete logarithms, so a full-size
  * multiexp is checkable with one scalar multiplication.  Generated on the GPU. */

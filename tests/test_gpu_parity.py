@@ -15,7 +15,7 @@ def test_library_reports_device(ctx):
     assert _lib.lib().za_device_count() >= 1
 
 
-@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 4, 5, 8, 10, 11, 12, 13, 16, 18])
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20])
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_ntt_matches_oracle(ctx, log_n, mode):
     n = 1 << log_n

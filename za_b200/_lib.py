@@ -100,6 +100,18 @@ SYMBOLS = {
     "za_parameters_max_size": (sz, [vp]),
     "za_generate_parameters": (ci, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, ctypes.POINTER(sz)]),
     "za_proof_to_json": (ci, [vp, vp, sz, ctypes.c_char_p, sz]),
+    "za_prover_create": (ci, [ctypes.POINTER(ci), ci, ctypes.POINTER(vp)]),
+    "za_prover_destroy": (None, [vp]),
+    "za_prover_device_count": (ci, [vp]),
+    "za_prover_ctx": (vp, [vp, ci]),
+    "za_prover_load_pk": (ci, [vp, vp, sz, ci]),
+    "za_prover_synthetic_pk": (ci, [vp, vp]),
+    "za_prover_set_circuit": (ci, [vp, vp]),
+    "za_prover_vk": (ci, [vp, vp, sz]),
+    "za_prover_pk_counts": (ci, [vp, vp]),
+    "za_prover_upload_witness": (ci, [vp, vp, vp]),
+    "za_prover_create_proof": (ci, [vp, vp, vp, vp, vp, vp]),
+    "za_prover_launch_count": (ctypes.c_uint64, [vp]),
 }
 
 _lib = None

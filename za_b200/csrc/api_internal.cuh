@@ -9,7 +9,7 @@ Fr host_domain_omega(int log_n);
 void launch_powers_public(Ctx* ctx, Fr* out, size_t count, const Fr& base, const Fr& first);
 void fr_convert(Ctx* ctx, Fr* d, size_t n, int dir);
 void ntt_mode(Ctx* ctx, Fr* buf, int log_n, int mode, int batch);
-void h_poly_device(Ctx* ctx, Fr* a, Fr* b, Fr* c, int log_m);
+void h_poly_device(Ctx* ctx, Fr* a, Fr* b, Fr* c, int log_m, Fr* h_out = nullptr);
 void h_poly_checkpointed(Ctx* ctx, Fr* a, Fr* b, Fr* c, int log_m, uint8_t* ck);
 
 // msm.cu
@@ -19,6 +19,7 @@ template <class F> void msm_enqueue(Ctx* ctx, int slot, const Affine<F>* d_bases
                                     const Affine<F>* d_table, int tab_c, int tab_W);
 template <class F> void bases_table_build(Ctx* ctx, const Affine<F>* d_pts, size_t n, int c, int W, Affine<F>* d_table);
 template <class F> XYZZ<F> msm_finish(Ctx* ctx, int slot);
+void msm_abort(Ctx* ctx);
 int msm_window_bits(size_t n);
 template <class F> void bases_generate(Ctx* ctx, Affine<F>* d_out, size_t n, uint64_t first, const Affine<F>& G);
 double imad_peak(Ctx* ctx);

@@ -69,6 +69,7 @@ struct NttDomain {
     DevBuf pow_g;       // g^i                      (coset_fft pre-scale), built lazily
     DevBuf pow_g_minv;  // m^-1 g^i                 (fused ifft -> coset_fft)
     DevBuf pow_ginv_minv;  // m^-1 g^-i             (icoset_fft post-scale)
+    DevBuf pow_ginv_minv_canon;  // the same out of Montgomery form: the last store of the H pipeline leaves canonical values
     DevBuf consts;      // [0] = m^-1, [1] = (g^m - 1)^-1
     bool have_coset = false;
 };
@@ -89,7 +90,7 @@ struct MsmSlot {
     cudaStream_t side = nullptr;         // this slot's reduction stream (high priority, so it is not starved by accumulations)
     cudaStream_t side2 = nullptr;        // row sums of the row / column reduction run here, next to the column sums on `side`
     cudaEvent_t red_fork = nullptr, red_join = nullptr;
-    cudaEvent_t dbg_start = nullptr, dbg_acc = nullptr, dbg_done = nullptr;   // ZA_DEBUG_TIMELINE only
+    cudaEvent_t dbg_start = nullptr, dbg_sort = nullptr, dbg_acc = nullptr, dbg_done = nullptr;   // ZA_DEBUG_TIMELINE only
     bool busy = false;                   // enqueued, not yet finished
     bool done_valid = false;             // `done` has been recorded at least once
     uint32_t sort_users = 0;             // slots that reuse this slot's digit sort since its last enqueue
@@ -120,6 +121,7 @@ struct Ctx {
     cudaEvent_t h_fork = nullptr, h_join = nullptr;
     unsigned long long* host_flag = nullptr;   // pinned: verdict of the witness range check of create_proof
     uint64_t launches = 0;              // kernels launched through this context (bench: gpu_launches)
+    bool ntt_attr_set = false;          // the > 48 KiB shared-memory attribute of the NTT kernels is set on this context's device
     // optional per-kernel-class timing with CUDA events on `stream` (bench.py roofline numbers)
     bool profile = false;
     std::vector<ProfSpan> spans;

@@ -1083,7 +1083,7 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
     }
     static const bool timeline = getenv("ZA_DEBUG_TIMELINE") != nullptr;
     if (timeline) {
-        if (!sl.dbg_start) { cudaEventCreate(&sl.dbg_start); cudaEventCreate(&sl.dbg_acc); cudaEventCreate(&sl.dbg_done); }
+        if (!sl.dbg_start) { cudaEventCreate(&sl.dbg_start); cudaEventCreate(&sl.dbg_sort); cudaEventCreate(&sl.dbg_acc); cudaEventCreate(&sl.dbg_done); }
         cudaEventRecord(sl.dbg_start, st);
     }
     const size_t want_host = 64 + 6 * 128 * sizeof(XYZZ<Fq2>); // header (entry count) + up to 128 bucket spaces x 6 partial results
@@ -1253,6 +1253,7 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
     } else if (ctx->slots[share_sort].sort_ev) {
         ZA_CUDA(cudaStreamWaitEvent(st, ctx->slots[share_sort].sort_ev, 0));
     }
+    if (timeline) cudaEventRecord(sl.dbg_sort, st);
     {
         ProfScope prof(ctx, sl.acc_cat, 0);
         const Affine<F>* cur_pts = d_bases;
@@ -1464,6 +1465,20 @@ XYZZ<F> msm_finish(Ctx* ctx, int slot_id) {
 }
 template XYZZ<Fq> msm_finish<Fq>(Ctx*, int);
 template XYZZ<Fq2> msm_finish<Fq2>(Ctx*, int);
+
+// After a failed enqueue or collect: wait for whatever is in flight on this context and return every slot to idle, so
+// that the next call on the context starts clean (a slot left busy would refuse every later multiexp).
+void msm_abort(Ctx* ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->g2_stream) cudaStreamSynchronize(ctx->g2_stream);
+    if (ctx->h_stream) cudaStreamSynchronize(ctx->h_stream);
+    for (MsmSlot& sl : ctx->slots) {
+        if (sl.side) cudaStreamSynchronize(sl.side);
+        if (sl.side2) cudaStreamSynchronize(sl.side2);
+        sl.busy = false; sl.kind = 0; sl.sort_users = 0;
+    }
+    cudaGetLastError();
+}
 
 // One multiexp, synchronously.  d_scalars: n canonical scalars on device; has_infinity: bases may contain (0,0).
 template <class F>

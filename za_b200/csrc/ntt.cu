@@ -14,6 +14,7 @@
 // first load / last store.  HBM traffic per transform = passes x 64 B per element; the binding
 // resource is the integer pipe.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace za {
 
@@ -47,6 +48,9 @@ struct NttPass {
     const Fr* pre;        // pre-scale by natural input index (first pass) or nullptr
     const Fr* post;       // post-scale by natural output index (last pass) or nullptr
     const Fr* post_const; // single post-scale constant (last pass) or nullptr
+    const Fr* mul_b;      // first pass: x = (x * mul_b[g] - sub_c[g]) * pre_const  (mul_assign, sub_assign and
+    const Fr* sub_c;      //             divide_by_z_on_coset of create_proof fused into the load of the last transform)
+    const Fr* pre_const;
     int n;                // log2 N
     int lo;               // lowest global index bit of this pass's tile
     int K;                // tile = 2^K elements at stride 2^lo
@@ -88,12 +92,15 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(NttPass p) {
 
     Fr x[8];
     bool first_round = true;
-    for (int top = K; top > 0; top -= 3) {
-        const int rb = top > 3 ? top - 3 : 0;
-        const int nb = top - rb;
-        const int pbit = rb + tshift;
+    // rounds of (K - 1) % 3 + 1, 3, 3, ... stages: the short round comes first, so that the final round of the last pass
+    // is always the fixed 8-point network on the three lowest index bits (twiddles 1, w8, w8^2, w8^3: 5 products, not 12)
+    for (int top = K; top > 0;) {
+        const int nb = first_round ? (K - 1) % 3 + 1 : 3;
+        const int rb = top - nb;                 // this round runs the stages on the tile bits [rb, top)
+        const int wb = nb < 3 ? top - 3 : rb;    // a thread holds the three bits [wb, wb + 3): in a short round the stages use the upper nb of them
+        const int pbit = wb + tshift;
         const unsigned lbase = ((t >> pbit) << (pbit + 3)) | (t & ((1u << pbit) - 1));
-        unsigned rot = 3 - nb;
+        unsigned rot = 0;                        // x[j] is the element whose three local bits are rotr3(j, rot)
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             unsigned l = lbase | (rotr3(j, rot) << pbit);
@@ -101,14 +108,38 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(NttPass p) {
                 size_t g = gidx(l);
                 x[j] = ld_fr(in + g);
                 if (p.first && p.pre) x[j] = x[j] * ldg_fr(p.pre + g);
+                if (p.first && p.mul_b) x[j] = (x[j] * ldg_fr(p.mul_b + (size_t)blockIdx.y * p.batch_stride + g) - ldg_fr(p.sub_c + (size_t)blockIdx.y * p.batch_stride + g)) * ldg_fr(p.pre_const);
             } else {
                 x[j] = ld_fr(sm + l);
             }
         }
+        if (LAST && rb == 0 && nb == 3) {
+            // stage b = 2: twiddle w8^j for the pair (j, j + 4); b = 1: 1, 1, w4, w4; b = 0: all 1.  Inverse transform:
+            // w^-e = -w^(N/2 - e), the sign goes into the difference (as below).
+            const size_t e8 = (size_t)1 << (n - 3);
+            const Fr w1 = ldg_fr(p.tw + (p.inverse ? half_n - e8 : e8));
+            const Fr w2 = ldg_fr(p.tw + (p.inverse ? half_n - 2 * e8 : 2 * e8));
+            const Fr w3 = ldg_fr(p.tw + (p.inverse ? half_n - 3 * e8 : 3 * e8));
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const bool plain = k == 2 || (k == 1 && j < 2) || (k == 0 && j == 0);
+                    Fr u = x[j] + x[j + 4];
+                    if (plain) x[j + 4] = x[j] - x[j + 4];
+                    else {
+                        Fr d = p.inverse ? (x[j + 4] - x[j]) : (x[j] - x[j + 4]);
+                        x[j + 4] = d * (k == 1 ? w2 : j == 1 ? w1 : j == 2 ? w2 : w3);
+                    }
+                    x[j] = u;
+                }
+                Fr y1 = x[1], y2 = x[2], y3 = x[3], y4 = x[4], y5 = x[5], y6 = x[6];
+                x[2] = y1; x[4] = y2; x[6] = y3; x[1] = y4; x[3] = y5; x[5] = y6;
+            }
+        } else
 #pragma unroll 1
         for (int k = 0; k < nb; k++) {
-            const int sbit = nb - 1 - k;
-            const int b = lo + rb + sbit;
+            const int b = lo + wb + 2 - k;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 size_t i0 = gidx(lbase | (rotr3(j, rot) << pbit));
@@ -124,14 +155,15 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(NttPass p) {
             x[2] = y1; x[4] = y2; x[6] = y3; x[1] = y4; x[3] = y5; x[5] = y6;
             rot++;
         }
-        const bool more = top > 3;
+        const bool more = rb > 0;
+        top = rb;
         if (more || LAST) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) st_fr(sm + (lbase | ((unsigned)j << pbit)), x[j]);
+            for (int j = 0; j < 8; j++) st_fr(sm + (lbase | (rotr3(j, rot) << pbit)), x[j]);
             __syncthreads();
         } else {
 #pragma unroll
-            for (int j = 0; j < 8; j++) st_fr(out + gidx(lbase | ((unsigned)j << pbit)), x[j]);
+            for (int j = 0; j < 8; j++) st_fr(out + gidx(lbase | (rotr3(j, rot) << pbit)), x[j]);
         }
         first_round = false;
     }
@@ -287,33 +319,48 @@ NttDomain* get_domain(Ctx* ctx, int log_n, bool need_coset) {
 
 static const int NTT_L = 11;  // log2 elements per CTA tile (2^11 x 32 B = 64 KiB shared memory)
 
-// Split log_n into pass sizes.  Every pass needs K >= 3 (a thread owns 8 elements).
+// Split log_n into pass sizes.  Every pass needs 3 <= K <= NTT_L (a thread owns 8 elements).  Default: the fewest
+// passes, sizes as even as possible (2^20: 10 + 10; 2^24: 8 + 8 + 8); ZA_NTT_MAXK caps K (9 = the three-pass plan of
+// round 1 at 2^20).
 static std::vector<int> plan_passes(int n) {
     std::vector<int> ks;
     if (n <= NTT_L) { ks.push_back(n); return ks; }
-    int P = (n + 8) / 9;
+    int maxk = 10;
+    if (const char* e = getenv("ZA_NTT_MAXK")) { int v = atoi(e); if (v >= 6 && v <= NTT_L) maxk = v; }
+    int P = (n + maxk - 1) / maxk;
     int base = n / P, extra = n % P;
     for (int i = 0; i < P; i++) ks.push_back(base + (i < extra ? 1 : 0));
     return ks;
 }
 
-// One transform (batch vectors), data in `buf` (Montgomery), result back in `buf`.
-// scratch must hold batch * N elements.  pre/post/post_const as in NttPass.
-void ntt_run(Ctx* ctx, Fr* buf, Fr* scratch, int n, int batch, bool inverse, const Fr* tw, const Fr* pre, const Fr* post,
-             const Fr* post_const) {
+// what is fused into the first load / last store of a transform
+struct NttFuse {
+    const Fr* pre = nullptr;         // x *= pre[i]                        (coset shift)
+    const Fr* post = nullptr;        // y *= post[k]                       (1/m, coset un-shift)
+    const Fr* post_const = nullptr;  // y *= *post_const
+    const Fr* mul_b = nullptr;       // x = (x * mul_b[i] - sub_c[i]) * *pre_const
+    const Fr* sub_c = nullptr;
+    const Fr* pre_const = nullptr;
+    Fr* out = nullptr;               // the result goes here instead of back into `buf` (batch 1)
+};
+
+// One transform (batch vectors, `stride` elements apart), data in `buf` (Montgomery), result back in `buf`.
+// scratch must hold batch * stride elements.
+static void ntt_run(Ctx* ctx, Fr* buf, Fr* scratch, int n, int batch, size_t stride, bool inverse, const Fr* tw, const NttFuse& f) {
     const size_t N = (size_t)1 << n;
     ProfScope prof(ctx, PROF_NTT, (double)batch * (double)N);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->ntt_attr_set) {          // per device: a context belongs to one device, a process may hold several contexts
         ZA_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_L) * 32));
         ZA_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_L) * 32));
-        attr_set = true;
+        ctx->ntt_attr_set = true;
     }
     if (n < 3) {
-        ntt_tiny_kernel<<<dim3(1, batch), 4, 0, ctx->stream>>>(buf, scratch, N, tw, pre, post, post_const, n, inverse ? 1 : 0);
+        if (f.mul_b) throw ZaError(ZA_ERR_INVALID, "internal: fused pointwise load needs a domain of 8 or more elements");
+        ntt_tiny_kernel<<<dim3(1, batch), 4, 0, ctx->stream>>>(buf, scratch, stride, tw, f.pre, f.post, f.post_const, n, inverse ? 1 : 0);
         ctx->launches++;
         ZA_CUDA(cudaGetLastError());
-        ZA_CUDA(cudaMemcpyAsync(buf, scratch, (size_t)batch * N * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+        for (int v = 0; v < batch; v++)
+            ZA_CUDA(cudaMemcpyAsync((f.out ? f.out : buf) + (size_t)v * stride, scratch + (size_t)v * stride, N * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
         return;
     }
     std::vector<int> ks = plan_passes(n);
@@ -324,8 +371,9 @@ void ntt_run(Ctx* ctx, Fr* buf, Fr* scratch, int n, int batch, bool inverse, con
         lo -= K;
         const bool last = pi == P - 1;
         NttPass p;
-        p.batch_stride = N;
-        p.tw = tw; p.pre = pre; p.post = post; p.post_const = post_const;
+        p.batch_stride = stride;
+        p.tw = tw; p.pre = f.pre; p.post = f.post; p.post_const = f.post_const;
+        p.mul_b = f.mul_b; p.sub_c = f.sub_c; p.pre_const = f.pre_const;
         p.n = n; p.lo = lo; p.K = K; p.inverse = inverse ? 1 : 0; p.first = pi == 0;
         int logt = NTT_L - K;
         if (last) { if (logt > n - K) logt = n - K; } else { if (logt > lo) logt = lo; }
@@ -334,7 +382,7 @@ void ntt_run(Ctx* ctx, Fr* buf, Fr* scratch, int n, int batch, bool inverse, con
         // data flow: buf -> scratch (pass 0), scratch in place (middle), scratch -> buf (last); P == 1: buf -> scratch + copy
         if (P == 1) { p.in = buf; p.out = scratch; }
         else if (pi == 0) { p.in = buf; p.out = scratch; }
-        else if (last) { p.in = scratch; p.out = buf; }
+        else if (last) { p.in = scratch; p.out = f.out ? f.out : buf; }
         else { p.in = scratch; p.out = scratch; }
         dim3 grid((unsigned)(N >> L), batch);
         unsigned threads = 1u << (L - 3);
@@ -344,7 +392,9 @@ void ntt_run(Ctx* ctx, Fr* buf, Fr* scratch, int n, int batch, bool inverse, con
         ctx->launches++;
         ZA_CUDA(cudaGetLastError());
     }
-    if (P == 1) ZA_CUDA(cudaMemcpyAsync(buf, scratch, (size_t)batch * N * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (P == 1)
+        for (int v = 0; v < batch; v++)
+            ZA_CUDA(cudaMemcpyAsync((f.out ? f.out : buf) + (size_t)v * stride, scratch + (size_t)v * stride, N * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
 }
 
 static inline unsigned nblk(size_t n, unsigned per) { return (unsigned)((n + per - 1) / per); }
@@ -368,43 +418,69 @@ void ntt_mode(Ctx* ctx, Fr* buf, int log_n, int mode, int batch) {
     DevBuf& scratch = ctx->scratch[0];
     scratch.ensure((size_t)batch * N * sizeof(Fr));
     const Fr* tw = d->tw.as<Fr>();
-    const Fr* consts = d->consts.as<Fr>();
+    NttFuse f;
     switch (mode) {
-    case ZA_NTT_FFT: ntt_run(ctx, buf, scratch.as<Fr>(), log_n, batch, false, tw, nullptr, nullptr, nullptr); break;
-    case ZA_NTT_IFFT: ntt_run(ctx, buf, scratch.as<Fr>(), log_n, batch, true, tw, nullptr, nullptr, consts); break;
-    case ZA_NTT_COSET_FFT: ntt_run(ctx, buf, scratch.as<Fr>(), log_n, batch, false, tw, d->pow_g.as<Fr>(), nullptr, nullptr); break;
-    case ZA_NTT_ICOSET_FFT: ntt_run(ctx, buf, scratch.as<Fr>(), log_n, batch, true, tw, nullptr, d->pow_ginv_minv.as<Fr>(), nullptr); break;
+    case ZA_NTT_FFT: break;
+    case ZA_NTT_IFFT: f.post_const = d->consts.as<Fr>(); break;
+    case ZA_NTT_COSET_FFT: f.pre = d->pow_g.as<Fr>(); break;
+    case ZA_NTT_ICOSET_FFT: f.post = d->pow_ginv_minv.as<Fr>(); break;
     default: throw ZaError(ZA_ERR_INVALID, "unknown NTT mode");
     }
+    ntt_run(ctx, buf, scratch.as<Fr>(), log_n, batch, N, mode == ZA_NTT_IFFT || mode == ZA_NTT_ICOSET_FFT, tw, f);
 }
 
-// Fused H pipeline on device (create_proof step 4): 7 transforms, scalings folded into the
-// transforms' last stores, one pointwise kernel.  Result: canonical h coefficients in a[0..m-1).
-void h_poly_device(Ctx* ctx, Fr* a, Fr* b, Fr* c, int log_m) {
+// Fused H pipeline on device (create_proof step 4).  Seven transforms in three groups: a, b and c go through ifft
+// and coset_fft TOGETHER (one launch per pass, blockIdx.y = vector) when they lie `m` elements apart; the scalings ride
+// on the transforms' last stores (ifft -> coset shift: one multiplication by m^-1 g^i), mul_assign / sub_assign /
+// divide_by_z_on_coset on the first load of the last transform, and its last store multiplies by the CANONICAL
+// m^-1 g^-i, which also takes the result out of Montgomery form.  Result: canonical h coefficients in a[0..m-1).
+void h_poly_device(Ctx* ctx, Fr* a, Fr* b, Fr* c, int log_m, Fr* h_out) {
     if (log_m >= 28) throw ZaError(ZA_ERR_POLY_DEGREE_TOO_LARGE, "domain of 2^28 or more elements");
     size_t m = (size_t)1 << log_m;
     if (log_m == 0) {
         // m = 1: ifft/coset_fft are identities; h has m-1 = 0 coefficients
         return;
     }
+    if (h_out == a) h_out = nullptr;
     NttDomain* d = get_domain(ctx, log_m, true);
+    if (!d->pow_ginv_minv_canon.p) {
+        // the same table out of Montgomery form: montmul(x R, t) = x t
+        d->pow_ginv_minv_canon.alloc(m * sizeof(Fr));
+        ZA_CUDA(cudaMemcpyAsync(d->pow_ginv_minv_canon.p, d->pow_ginv_minv.p, m * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+        fr_convert(ctx, d->pow_ginv_minv_canon.as<Fr>(), m, 1);
+    }
+    const bool together = b == a + m && c == b + m;
     DevBuf& scratch = ctx->scratch[0];
-    scratch.ensure(m * sizeof(Fr));
+    scratch.ensure((together ? 3 : 1) * m * sizeof(Fr));
     const Fr* tw = d->tw.as<Fr>();
-    Fr* vecs[3] = {a, b, c};
-    for (int v = 0; v < 3; v++) {
-        // ifft then coset shift: one post-scale by m^-1 g^i
-        ntt_run(ctx, vecs[v], scratch.as<Fr>(), log_m, 1, true, tw, nullptr, d->pow_g_minv.as<Fr>(), nullptr);
-        ntt_run(ctx, vecs[v], scratch.as<Fr>(), log_m, 1, false, tw, nullptr, nullptr, nullptr);
+    NttFuse inv_shift; inv_shift.post = d->pow_g_minv.as<Fr>();       // ifft then coset shift: one post-scale by m^-1 g^i
+    NttFuse plain;
+    if (together) {
+        ntt_run(ctx, a, scratch.as<Fr>(), log_m, 3, m, true, tw, inv_shift);
+        ntt_run(ctx, a, scratch.as<Fr>(), log_m, 3, m, false, tw, plain);
+    } else {
+        Fr* vecs[3] = {a, b, c};
+        for (int v = 0; v < 3; v++) {
+            ntt_run(ctx, vecs[v], scratch.as<Fr>(), log_m, 1, m, true, tw, inv_shift);
+            ntt_run(ctx, vecs[v], scratch.as<Fr>(), log_m, 1, m, false, tw, plain);
+        }
     }
-    {
-        ProfScope prof(ctx, PROF_POINTWISE, (double)m);
-        h_pointwise_kernel<<<nblk(m, 256), 256, 0, ctx->stream>>>(a, b, c, d->consts.as<Fr>() + 1, m);
-        ctx->launches++;
-        ZA_CUDA(cudaGetLastError());
+    if (log_m >= 3) {
+        NttFuse last;
+        last.mul_b = b; last.sub_c = c; last.pre_const = d->consts.as<Fr>() + 1;
+        last.post = d->pow_ginv_minv_canon.as<Fr>();
+        last.out = h_out;
+        ntt_run(ctx, a, scratch.as<Fr>(), log_m, 1, m, true, tw, last);
+    } else {
+        {
+            ProfScope prof(ctx, PROF_POINTWISE, (double)m);
+            h_pointwise_kernel<<<nblk(m, 256), 256, 0, ctx->stream>>>(a, b, c, d->consts.as<Fr>() + 1, m);
+            ctx->launches++;
+            ZA_CUDA(cudaGetLastError());
+        }
+        NttFuse last; last.post = d->pow_ginv_minv_canon.as<Fr>(); last.out = h_out;
+        ntt_run(ctx, a, scratch.as<Fr>(), log_m, 1, m, true, tw, last);
     }
-    ntt_run(ctx, a, scratch.as<Fr>(), log_m, 1, true, tw, nullptr, d->pow_ginv_minv.as<Fr>(), nullptr);
-    fr_convert(ctx, a, m, 1);
 }
 
 // Unfused H pipeline that materialises every vector bellman materialises (parity checkpoints).

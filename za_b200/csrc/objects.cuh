@@ -48,6 +48,7 @@ struct Circuit {
     // positions in the witness vector [inputs | aux] of the exponents of the whole A query (all inputs, then
     // the aux with a_aux_density) and of the whole B query (inputs with b_input_density, then aux with b_aux_density)
     DevBuf a_cat_idx, b_cat_idx;
+    std::vector<uint32_t> h_a_cat, h_b_cat;      // host copies of the two lists
     uint32_t a_cat_total = 0, b_cat_total = 0;
 };
 

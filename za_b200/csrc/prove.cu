@@ -11,6 +11,11 @@
 #include <stdlib.h>
 #include <memory>
 #include <chrono>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <functional>
+#include <algorithm>
 
 namespace za {
 
@@ -121,12 +126,55 @@ static void check_scalars_canonical(const uint8_t* p, size_t n, const char* what
     }
 }
 
+// "Every scalar < r" for vectors that are already on the device (the digit recoding and the Montgomery conversion both
+// assume it): one pass on the context's stream, the verdict — index of the first element >= r, or ~0 — travels to
+// pinned host memory behind it and is read by whoever synchronises next.  Slots: 0 witness, 1 h scalars, 2 multiexp.
+__global__ void fr_canonical_check_kernel(const uint32_t* __restrict__ v, size_t n, unsigned long long* first_bad);
+enum { CHK_WITNESS = 0, CHK_H = 1, CHK_MSM = 2 };
+static void canonical_check_enqueue(Ctx* ctx, const void* d, size_t n, int which) {
+    DevBuf& bad = ctx->scratch[14];
+    bad.ensure(64);
+    if (!ctx->host_flag) {
+        ZA_CUDA(cudaHostAlloc((void**)&ctx->host_flag, 64, cudaHostAllocDefault));
+        for (int i = 0; i < 8; i++) ctx->host_flag[i] = ~0ull;
+    }
+    unsigned long long* d_flag = bad.as<unsigned long long>() + which;
+    ZA_CUDA(cudaMemsetAsync(d_flag, 0xff, 8, ctx->stream));
+    if (n) {
+        fr_canonical_check_kernel<<<nblk(n, 256), 256, 0, ctx->stream>>>((const uint32_t*)d, n, d_flag);
+        ctx->launches++;
+        ZA_CUDA(cudaGetLastError());
+    }
+    ZA_CUDA(cudaMemcpyAsync(ctx->host_flag + which, d_flag, 8, cudaMemcpyDeviceToHost, ctx->stream));
+}
+// after the stream has been synchronised past the copy above
+static unsigned long long canonical_check_verdict(Ctx* ctx, int which) {
+    if (!ctx->host_flag) return ~0ull;
+    const unsigned long long v = ctx->host_flag[which];
+    ctx->host_flag[which] = ~0ull;
+    return v;
+}
+
 template <class F>
-static XYZZ<F> multiexp_dev(Ctx* ctx, const Bases* b, size_t offset, const uint32_t* d_scalars, size_t n) {
+static XYZZ<F> multiexp_dev(Ctx* ctx, const Bases* b, size_t offset, const uint32_t* d_scalars, size_t n, bool check = false) {
     if (offset > b->n || n > b->n - offset)
         throw ZaError(ZA_ERR_IO, "multiexp: the base query is shorter than the exponent vector (bellman: unexpected EOF)");
-    msm_enqueue<F>(ctx, 0, b->pts.as<Affine<F>>() + offset, d_scalars, n, b->has_infinity, -1, table_for<F>(b, offset, n), b->tab_c, b->tab_W);
-    return msm_finish<F>(ctx, 0);
+    if (check) canonical_check_enqueue(ctx, d_scalars, n, CHK_MSM);
+    XYZZ<F> r;
+    try {
+        msm_enqueue<F>(ctx, 0, b->pts.as<Affine<F>>() + offset, d_scalars, n, b->has_infinity, -1, table_for<F>(b, offset, n), b->tab_c, b->tab_W);
+        r = msm_finish<F>(ctx, 0);
+    } catch (...) { msm_abort(ctx); throw; }
+    if (check) {
+        ZA_CUDA(cudaStreamSynchronize(ctx->stream));
+        const unsigned long long bad = canonical_check_verdict(ctx, CHK_MSM);
+        if (bad != ~0ull) {
+            char m[128];
+            snprintf(m, sizeof m, "scalars[%llu] is not a canonical Fr element (>= r)", bad);
+            throw ZaError(ZA_ERR_NOT_CANONICAL, m);
+        }
+    }
+    return r;
 }
 
 // ------------------------------------------------------------------ proving key
@@ -356,7 +404,11 @@ static std::unique_ptr<Circuit> circuit_upload(Ctx* ctx, const za_r1cs* cs) {
         for (uint32_t i = 0; i < dens.size(); i++) if (dens[i]) idx.push_back(i);
         total = (uint32_t)idx.size();
         out.alloc((size_t)total * 4);
-        if (total) ZA_CUDA(cudaMemcpy(out.p, idx.data(), (size_t)total * 4, cudaMemcpyHostToDevice));
+        if (total) {
+            // on the context's (non-blocking) stream, like every kernel that reads the list; `idx` is a local
+            ZA_CUDA(cudaMemcpyAsync(out.p, idx.data(), (size_t)total * 4, cudaMemcpyHostToDevice, ctx->stream));
+            ZA_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
     };
     make_idx(c->a_aux_density, c->a_aux_idx, c->a_aux_total);
     make_idx(c->b_in_density, c->b_in_idx, c->b_in_total);
@@ -369,8 +421,10 @@ static std::unique_ptr<Circuit> circuit_upload(Ctx* ctx, const za_r1cs* cs) {
         for (uint32_t i = 0; i < c->na; i++) if (c->b_aux_density[i]) b_cat.push_back(c->ni + i);
         c->a_cat_total = (uint32_t)a_cat.size(); c->b_cat_total = (uint32_t)b_cat.size();
         c->a_cat_idx.alloc((size_t)c->a_cat_total * 4); c->b_cat_idx.alloc((size_t)c->b_cat_total * 4);
-        if (c->a_cat_total) ZA_CUDA(cudaMemcpy(c->a_cat_idx.p, a_cat.data(), (size_t)c->a_cat_total * 4, cudaMemcpyHostToDevice));
-        if (c->b_cat_total) ZA_CUDA(cudaMemcpy(c->b_cat_idx.p, b_cat.data(), (size_t)c->b_cat_total * 4, cudaMemcpyHostToDevice));
+        if (c->a_cat_total) ZA_CUDA(cudaMemcpyAsync(c->a_cat_idx.p, a_cat.data(), (size_t)c->a_cat_total * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (c->b_cat_total) ZA_CUDA(cudaMemcpyAsync(c->b_cat_idx.p, b_cat.data(), (size_t)c->b_cat_total * 4, cudaMemcpyHostToDevice, ctx->stream));
+        ZA_CUDA(cudaStreamSynchronize(ctx->stream));
+        c->h_a_cat.swap(a_cat); c->h_b_cat.swap(b_cat);      // host copies: a rank's witness span follows from its point range
     }
     return c;
 }
@@ -383,6 +437,17 @@ static const uint32_t* gather(Ctx* ctx, const uint8_t* d_src, const DevBuf& idx,
     dst.ensure((size_t)total * 32);
     if (total) {
         gather_scalars_kernel<<<nblk(total, 256), 256, 0, ctx->stream>>>((const uint4*)d_src, idx.as<uint32_t>(), total, dst.as<uint4>());
+        ctx->launches++;
+        ZA_CUDA(cudaGetLastError());
+    }
+    return dst.as<uint32_t>();
+}
+// the same for the entries [lo, hi) of the index list only (a rank's point range): dst keeps the layout of the whole
+// exponent vector, so entry i is at dst + 32 i, and only the witness positions idx[lo..hi) are read
+static const uint32_t* gather_range(Ctx* ctx, const uint8_t* d_src, const DevBuf& idx, uint32_t total, size_t lo, size_t hi, DevBuf& dst) {
+    dst.ensure((size_t)total * 32);
+    if (hi > lo) {
+        gather_scalars_kernel<<<nblk(hi - lo, 256), 256, 0, ctx->stream>>>((const uint4*)d_src, idx.as<uint32_t>() + lo, hi - lo, dst.as<uint4>() + 2 * lo);
         ctx->launches++;
         ZA_CUDA(cudaGetLastError());
     }
@@ -404,14 +469,17 @@ static void prove_h(Ctx* ctx, const Circuit* c, const uint8_t* d_wit, Fr* d_h, z
     int log_m; const size_t m = domain_size(c, &log_m);
     const size_t len = (size_t)nc + ni;
     DevBuf& wit_mont = ctx->scratch[7];
-    wit_mont.ensure(((size_t)ni + na) * 32 + 2 * m * sizeof(Fr));
+    wit_mont.ensure(((size_t)ni + na) * 32 + 3 * m * sizeof(Fr));
     Fr* d_w = wit_mont.as<Fr>();
-    Fr* d_b = d_w + ni + na; Fr* d_c = d_b + m; Fr* d_a = d_h;
+    // a, b, c lie m elements apart: their transforms run as one batch (h_poly_device); the h scalars go to d_h
+    Fr* d_a = d_w + ni + na; Fr* d_b = d_a + m; Fr* d_c = d_b + m;
     ZA_CUDA(cudaMemcpyAsync(d_w, d_wit, ((size_t)ni + na) * 32, cudaMemcpyDeviceToDevice, st));
     fr_convert(ctx, d_w, (size_t)ni + na, 0);
     // steps 2-3: a, b, c = <row, witness>; then rows a = input_i, b = c = 0
-    ZA_CUDA(cudaMemsetAsync(d_a, 0, m * sizeof(Fr), st));
-    ZA_CUDA(cudaMemsetAsync(d_b, 0, 2 * m * sizeof(Fr), st));
+    // rows the constraint evaluation does not write: the padding behind the nc + ni rows of a and the nc rows of b and c
+    ZA_CUDA(cudaMemsetAsync(d_a + len, 0, (m - len) * sizeof(Fr), st));
+    ZA_CUDA(cudaMemsetAsync(d_b + nc, 0, (m - nc) * sizeof(Fr), st));
+    ZA_CUDA(cudaMemsetAsync(d_c + nc, 0, (m - nc) * sizeof(Fr), st));
     Fr* outs[3] = {d_a, d_b, d_c};
     if (nc) {
         ProfScope prof(ctx, PROF_R1CS, 3.0 * nc);
@@ -439,9 +507,9 @@ static void prove_h(Ctx* ctx, const Circuit* c, const uint8_t* d_wit, Fr* d_h, z
         if (tr->b_aux_density && na) memcpy(tr->b_aux_density, c->b_aux_density.data(), na);
     }
     // step 4
-    h_poly_device(ctx, d_a, d_b, d_c, log_m);
+    h_poly_device(ctx, d_a, d_b, d_c, log_m, d_h);
     if (tr && tr->h_coeffs && m > 1) {
-        ZA_CUDA(cudaMemcpyAsync(tr->h_coeffs, d_a, (m - 1) * 32, cudaMemcpyDeviceToHost, st));
+        ZA_CUDA(cudaMemcpyAsync(tr->h_coeffs, d_h, (m - 1) * 32, cudaMemcpyDeviceToHost, st));
         ZA_CUDA(cudaStreamSynchronize(st));
     }
 }
@@ -516,8 +584,8 @@ static void prove_msms_enqueue(Ctx* ctx, const Pk* pk, const Circuit* c, const u
     size_t lo, hi;
     if (which & MSM_WITNESS) {
         // G2 first: its (longest) bucket reduction then overlaps the G1 accumulations on the side stream
-        const uint32_t* sb = gather(ctx, d_wit, c->b_cat_idx, c->b_cat_total, ctx->scratch[13]);
         share_weighted(c->b_cat_total, rank, world, w0, lo, hi);
+        const uint32_t* sb = gather_range(ctx, d_wit, c->b_cat_idx, c->b_cat_total, lo, hi, ctx->scratch[13]);
         // The G2 multiexp goes to its own (high-priority) stream.  Its kernels hold 2 CTAs of 190+ registers per SM and
         // are latency bound (8 warps/SM, multiply pipe ~60 % busy); the registers they leave fit exactly one CTA of the
         // G1 accumulation, so the G1 multiexps on the main stream run next to it and fill the pipe
@@ -556,8 +624,8 @@ static void prove_msms_enqueue(Ctx* ctx, const Pk* pk, const Circuit* c, const u
     if (which & MSM_WITNESS) {
         share_weighted(na, rank, world, w0, lo, hi);
         multiexp_enqueue<Fq>(ctx, 1, pk->l.get(), lo, (const uint32_t*)(d_aux + lo * 32), hi - lo);
-        const uint32_t* sa = gather(ctx, d_wit, c->a_cat_idx, c->a_cat_total, ctx->scratch[12]);
         share_weighted(c->a_cat_total, rank, world, w0, lo, hi);
+        const uint32_t* sa = gather_range(ctx, d_wit, c->a_cat_idx, c->a_cat_total, lo, hi, ctx->scratch[12]);
         multiexp_enqueue<Fq>(ctx, 2, pk->a.get(), lo, sa + lo * 8, hi - lo);
     }
     if ((which & MSM_H) && !(which & MSM_WITNESS)) {
@@ -597,12 +665,17 @@ static void prove_msms_separate(Ctx* ctx, const Pk* pk, const Circuit* c, const 
     out.g2[1] = multiexp_dev<Fq2>(ctx, pk->b_g2.get(), c->b_in_total, sc, c->b_aux_total);
 }
 
+// what create_proof refuses before it touches the GPU: r, s >= the modulus, delta at infinity
+static void prove_validate(const Pk* pk, const uint8_t* r_le, const uint8_t* s_le) {
+    if (pk->delta_g1.is_inf() || pk->delta_g2.is_inf()) throw ZaError(ZA_ERR_UNEXPECTED_IDENTITY, "create_proof: delta is the point at infinity");
+    check_scalars_canonical(r_le, 1, "r"); check_scalars_canonical(s_le, 1, "s");
+}
+
 // The part of the assembly that does not depend on the multiexps (steps 6-7: delta*r + alpha, delta2*s + beta2,
 // delta*rs + alpha*s + beta*r); computed on the host while the GPU runs the multiexps.
 struct AssemblePre { G1XYZZ g_a, g_c; G2XYZZ g_b; uint32_t r[8], s[8]; };
 static AssemblePre prove_assemble_pre(const Pk* pk, const uint8_t* r_le, const uint8_t* s_le) {
-    if (pk->delta_g1.is_inf() || pk->delta_g2.is_inf()) throw ZaError(ZA_ERR_UNEXPECTED_IDENTITY, "create_proof: delta is the point at infinity");
-    check_scalars_canonical(r_le, 1, "r"); check_scalars_canonical(s_le, 1, "s");
+    prove_validate(pk, r_le, s_le);
     AssemblePre A;
     memcpy(A.r, r_le, 32); memcpy(A.s, s_le, 32);
     Fr rf, sf; memcpy(rf.v, A.r, 32); memcpy(sf.v, A.s, 32);
@@ -639,9 +712,60 @@ static void prove_msms(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* 
     prove_msms_collect(ctx, out);
 }
 
-// whole proof on one GPU, witness already on the device
+// ZA_DEBUG_TIMELINE: when each multiexp of the last proof started, finished accumulating and finished reducing
+static void print_timeline(Ctx* ctx) {
+    static const bool timeline = getenv("ZA_DEBUG_TIMELINE") != nullptr;
+    if (!timeline) return;
+    const int order[5] = {3, 4, 0, 1, 2};
+    const char* name[5] = {"B(G1)", "B(G2)", "H", "L", "A"};
+    cudaEvent_t base = ctx->slots[3].dbg_start;
+    for (int k = 0; k < 5; k++) {
+        MsmSlot& sl = ctx->slots[order[k]];
+        float a = 0, b = 0, d = 0, so = 0;
+        if (sl.dbg_start && sl.kind == 2) {
+            cudaEventSynchronize(sl.dbg_done);
+            cudaEventElapsedTime(&a, base, sl.dbg_start); cudaEventElapsedTime(&b, base, sl.dbg_acc); cudaEventElapsedTime(&d, base, sl.dbg_done);
+            if (sl.dbg_sort) cudaEventElapsedTime(&so, base, sl.dbg_sort);
+        }
+        fprintf(stderr, "[za timeline] %-6s start %.3f  sorted %.3f  accumulate done %.3f  reduce done %.3f\n", name[k], a, so, b, d);
+    }
+}
+
+static void create_proof_device_body(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* d_wit, const uint8_t* r_le, const uint8_t* s_le,
+                                     uint8_t* proof_out, za_trace* tr);
+
+// whole proof on one GPU, witness [inputs | aux] already on the device.  "Every witness element < r" is checked on the
+// device copy (a pass over 32 MB on the host would sit in front of every proof); the verdict travels back behind the
+// check and is read once the proof is done.  Any failure leaves the context reusable (msm_abort).
 static void create_proof_device(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* d_wit, const uint8_t* r_le, const uint8_t* s_le,
                                 uint8_t* proof_out, za_trace* tr) {
+    prove_validate(pk, r_le, s_le);
+    check_query_lengths(pk, c, domain_size(c, nullptr));
+    cudaStream_t st = ctx->stream;
+    const uint32_t ni = c->ni, na = c->na;
+    canonical_check_enqueue(ctx, d_wit, (size_t)ni + na, CHK_WITNESS);
+    bool failed = false;
+    try {
+        create_proof_device_body(ctx, pk, c, d_wit, r_le, s_le, proof_out, tr);
+    } catch (...) {
+        ctx->stream = st;
+        msm_abort(ctx);
+        if (!ctx->host_flag || ctx->host_flag[CHK_WITNESS] == ~0ull) throw;      // otherwise the non-canonical element below is the root cause
+        failed = true;
+    }
+    if (!failed) ZA_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long first_bad = canonical_check_verdict(ctx, CHK_WITNESS);
+    if (first_bad != ~0ull) {
+        memset(proof_out, 0, 256);
+        char b[128];
+        if (first_bad < ni) snprintf(b, sizeof b, "inputs[%llu] is not a canonical Fr element (>= r)", first_bad);
+        else snprintf(b, sizeof b, "aux[%llu] is not a canonical Fr element (>= r)", first_bad - ni);
+        throw ZaError(ZA_ERR_NOT_CANONICAL, b);
+    }
+}
+
+static void create_proof_device_body(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* d_wit, const uint8_t* r_le, const uint8_t* s_le,
+                                     uint8_t* proof_out, za_trace* tr) {
     const size_t m = domain_size(c, nullptr);
     DevBuf& h = ctx->scratch[9];
     h.ensure(m * sizeof(Fr));
@@ -673,6 +797,7 @@ static void create_proof_device(Ctx* ctx, const Pk* pk, const Circuit* c, const 
         Partials Q;
         prove_msms_collect(ctx, Q);
         prove_assemble_post(pre, Q, proof_out);
+        print_timeline(ctx);
         return;
     }
     prove_h(ctx, c, d_wit, h.as<Fr>(), tr);
@@ -701,16 +826,7 @@ static void create_proof_device(Ctx* ctx, const Pk* pk, const Circuit* c, const 
     prove_msms_collect(ctx, P);
     if (timeline) t3 = now();
     prove_assemble_post(pre, P, proof_out);
-    if (timeline) {
-        const int order[5] = {3, 4, 0, 1, 2};
-        cudaEvent_t base = ctx->slots[3].dbg_start;
-        for (int k = 0; k < 5; k++) {
-            MsmSlot& sl = ctx->slots[order[k]];
-            float a = 0, b = 0, d = 0;
-            if (sl.dbg_start && sl.kind == 2) { cudaEventElapsedTime(&a, base, sl.dbg_start); cudaEventElapsedTime(&b, base, sl.dbg_acc); cudaEventElapsedTime(&d, base, sl.dbg_done); }
-            fprintf(stderr, "[za timeline] slot %d: start %.3f  accumulate done %.3f  reduce done %.3f\n", order[k], a, b, d);
-        }
-    }
+    print_timeline(ctx);
     if (timeline) { t4 = now(); fprintf(stderr, "[za timeline] after H: enqueue %.3f ms, host pre %.3f, wait+combine %.3f, host post %.3f\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3); }
 }
 
@@ -732,31 +848,7 @@ static void create_proof(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t
     wit.ensure(((size_t)ni + na) * 32);
     ZA_CUDA(cudaMemcpyAsync(wit.p, inputs, (size_t)ni * 32, cudaMemcpyHostToDevice, st));
     if (na) ZA_CUDA(cudaMemcpyAsync((uint8_t*)wit.p + (size_t)ni * 32, aux, (size_t)na * 32, cudaMemcpyHostToDevice, st));
-    // "is every witness element < r" is checked on the uploaded copy (a pass over 32 MB on the host would sit in
-    // front of every proof); the verdict travels back behind the upload and is read once the proof is done
-    DevBuf& bad = ctx->scratch[14];
-    bad.ensure(64);
-    if (!ctx->host_flag) ZA_CUDA(cudaHostAlloc((void**)&ctx->host_flag, 64, cudaHostAllocDefault));
-    ZA_CUDA(cudaMemsetAsync(bad.p, 0xff, 8, st));
-    fr_canonical_check_kernel<<<nblk((size_t)ni + na, 256), 256, 0, st>>>((const uint32_t*)wit.p, (size_t)ni + na, bad.as<unsigned long long>());
-    ctx->launches++;
-    ZA_CUDA(cudaGetLastError());
-    ZA_CUDA(cudaMemcpyAsync(ctx->host_flag, bad.p, 8, cudaMemcpyDeviceToHost, st));
-    try {
-        create_proof_device(ctx, pk, c, (const uint8_t*)wit.p, r_le, s_le, proof_out, tr);
-    } catch (...) {
-        cudaStreamSynchronize(st);
-        if (*ctx->host_flag == ~0ull) throw;      // otherwise the non-canonical element below is the root cause
-    }
-    ZA_CUDA(cudaStreamSynchronize(st));
-    const unsigned long long first_bad = *ctx->host_flag;
-    if (first_bad != ~0ull) {
-        memset(proof_out, 0, 256);
-        char b[128];
-        if (first_bad < ni) snprintf(b, sizeof b, "inputs[%llu] is not a canonical Fr element (>= r)", first_bad);
-        else snprintf(b, sizeof b, "aux[%llu] is not a canonical Fr element (>= r)", first_bad - ni);
-        throw ZaError(ZA_ERR_NOT_CANONICAL, b);
-    }
+    create_proof_device(ctx, pk, c, (const uint8_t*)wit.p, r_le, s_le, proof_out, tr);
 }
 
 // synthetic proving key: every base is a known multiple of the generator (bench + full-size property tests)
@@ -786,7 +878,270 @@ static Affine<F> host_multiple(const Affine<F>& g, uint64_t k) {
     return xyzz_to_affine<F>(xyzz_mul<F>(XYZZ<F>::from_affine(g), w));
 }
 
+
+// ------------------------------------------------------------------ several GPUs, one process
+// The reference's caller is ONE process (create_random_proof at prover.rs:173), so the multi-GPU path sits behind one
+// call as well: a Prover owns a context, the proving key and the circuit on every device, and one host thread per
+// device that issues that device's work.  Per proof:
+//   device 0   witness H2D -> range check -> constraint evaluation -> H pipeline (alone: it is the critical path of
+//              every device) -> the h slice of device k straight into k's memory (cudaMemcpyPeerAsync over NVLink, an
+//              event per peer) -> its (smaller, za_pk_partition_weighted) share of the witness multiexps -> its H share
+//   device k   the witness span its point ranges need, H2D over its own PCIe link -> witness multiexps (L, A, B in G1,
+//              B in G2) -> waits for its h slice on the stream -> H multiexp
+//   host       delta r + alpha etc. while the GPUs work; then adds the partial sums (8 points per device) and
+//              assembles.  No collective and no torch / NCCL anywhere on the path.
+struct ProverWorker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool pending = false, quit = false;
+    int err_code = 0;
+    std::string err;
+};
+struct Prover {
+    int n = 0;
+    std::vector<int> devices;
+    std::vector<za_ctx*> ctx;
+    std::vector<za_pk*> pk;
+    std::vector<za_circuit*> circ;
+    std::vector<std::unique_ptr<ProverWorker>> workers;
+    std::vector<DevBuf> wit, h;                      // per device: witness [inputs | aux]; h scalars (m entries)
+    std::vector<cudaEvent_t> h_ready;                // on device 0's stream, behind the copy of device k's h slice
+    std::vector<std::vector<std::pair<size_t, size_t>>> spans;   // per device: witness positions [first, last) it reads
+    std::mutex h_mu;
+    std::condition_variable h_cv;
+    uint64_t h_issued = 0, generation = 0;           // device 0 has issued the h copies of proof `generation`
+    bool h_failed = false;
+    uint32_t rank0_weight = 1000;
+    std::vector<Partials> partials;
+    ~Prover();
+};
+
+static void prover_worker_loop(ProverWorker* w) {
+    for (;;) {
+        std::function<void()> job;
+        {
+            std::unique_lock<std::mutex> lk(w->mu);
+            w->cv.wait(lk, [&] { return w->pending || w->quit; });
+            if (w->quit) return;
+            job = w->job;
+        }
+        int code = 0; std::string text;
+        try { job(); }
+        catch (const ZaError& e) { code = e.code; text = e.what(); }
+        catch (const CudaError& e) { code = ZA_ERR_CUDA; text = e.what(); }
+        catch (const std::exception& e) { code = ZA_ERR_INVALID; text = e.what(); }
+        {
+            std::lock_guard<std::mutex> lk(w->mu);
+            w->err_code = code; w->err = text; w->pending = false;
+        }
+        w->cv.notify_all();
+    }
+}
+// run fn(k) on device k's thread for every device; the caller's thread runs `meanwhile`.  Throws the first error.
+static void prover_run_all(Prover* P, const std::function<void(int)>& fn, const std::function<void()>& meanwhile = nullptr) {
+    for (int k = 0; k < P->n; k++) {
+        ProverWorker* w = P->workers[k].get();
+        { std::lock_guard<std::mutex> lk(w->mu); w->job = [fn, k] { fn(k); }; w->pending = true; w->err_code = 0; w->err.clear(); }
+        w->cv.notify_all();
+    }
+    int mcode = 0; std::string mtext;
+    if (meanwhile) {
+        try { meanwhile(); }
+        catch (const ZaError& e) { mcode = e.code; mtext = e.what(); }
+        catch (const std::exception& e) { mcode = ZA_ERR_INVALID; mtext = e.what(); }
+    }
+    int code = 0; std::string text;
+    for (int k = 0; k < P->n; k++) {
+        ProverWorker* w = P->workers[k].get();
+        std::unique_lock<std::mutex> lk(w->mu);
+        w->cv.wait(lk, [&] { return !w->pending; });
+        if (w->err_code && !code) { code = w->err_code; text = "device " + std::to_string(P->devices[k]) + ": " + w->err; }
+    }
+    if (mcode) throw ZaError(mcode, mtext);
+    if (code) throw ZaError(code, text);
+}
+Prover::~Prover() {
+    for (auto& w : workers) {
+        { std::lock_guard<std::mutex> lk(w->mu); w->quit = true; }
+        w->cv.notify_all();
+        if (w->th.joinable()) w->th.join();
+    }
+    if (!devices.empty()) cudaSetDevice(devices[0]);
+    for (cudaEvent_t e : h_ready) if (e) cudaEventDestroy(e);
+    for (int k = 0; k < (int)ctx.size(); k++) {
+        cudaSetDevice(devices[k]);
+        if (k < (int)wit.size()) { wit[k].release(); h[k].release(); }
+        if (k < (int)circ.size() && circ[k]) delete circ[k];
+        if (k < (int)pk.size() && pk[k]) delete pk[k];
+    }
+    for (int k = 0; k < (int)ctx.size(); k++) if (ctx[k]) za_ctx_destroy(ctx[k]);
+}
+
+// witness positions device k reads: the aux range of its L share and the spans of its A and B index ranges (merged)
+static void prover_plan_spans(Prover* P) {
+    const Circuit* c = P->circ[0]->c.get();
+    P->spans.assign(P->n, {});
+    for (int k = 0; k < P->n; k++) {
+        std::vector<std::pair<size_t, size_t>> iv;
+        if (k == 0) { iv.push_back({0, (size_t)c->ni + c->na}); P->spans[k] = iv; continue; }      // device 0 evaluates the constraints
+        const uint32_t w0 = P->rank0_weight;
+        size_t lo, hi;
+        share_weighted(c->na, k, P->n, w0, lo, hi);
+        if (hi > lo) iv.push_back({c->ni + lo, c->ni + hi});
+        share_weighted(c->a_cat_total, k, P->n, w0, lo, hi);
+        if (hi > lo) iv.push_back({c->h_a_cat[lo], (size_t)c->h_a_cat[hi - 1] + 1});
+        share_weighted(c->b_cat_total, k, P->n, w0, lo, hi);
+        if (hi > lo) iv.push_back({c->h_b_cat[lo], (size_t)c->h_b_cat[hi - 1] + 1});
+        std::sort(iv.begin(), iv.end());
+        std::vector<std::pair<size_t, size_t>> merged;
+        for (auto& x : iv) {
+            if (!merged.empty() && x.first <= merged.back().second) merged.back().second = std::max(merged.back().second, x.second);
+            else merged.push_back(x);
+        }
+        P->spans[k] = merged;
+    }
+}
+
+static void prover_upload_witness(Prover* P, int k, const uint8_t* inputs, const uint8_t* aux) {
+    Ctx* cx = &P->ctx[k]->c;
+    const Circuit* c = P->circ[k]->c.get();
+    const size_t ni = c->ni;
+    uint8_t* d = (uint8_t*)P->wit[k].p;
+    for (auto& sp : P->spans[k]) {
+        size_t a = sp.first, b = sp.second;
+        if (a < ni) {
+            const size_t e = b < ni ? b : ni;
+            ZA_CUDA(cudaMemcpyAsync(d + a * 32, inputs + a * 32, (e - a) * 32, cudaMemcpyHostToDevice, cx->stream));
+            a = e;
+        }
+        if (b > a) ZA_CUDA(cudaMemcpyAsync(d + a * 32, aux + (a - ni) * 32, (b - a) * 32, cudaMemcpyHostToDevice, cx->stream));
+    }
+}
+
+// one device's part of one proof (runs on that device's thread)
+static void prover_device_step(Prover* P, int k, uint64_t gen, const uint8_t* inputs, const uint8_t* aux) {
+    ZA_CUDA(cudaSetDevice(P->devices[k]));
+    Ctx* cx = &P->ctx[k]->c;
+    const Pk* pk = P->pk[k]->p.get();
+    const Circuit* c = P->circ[k]->c.get();
+    const uint8_t* d_wit = (const uint8_t*)P->wit[k].p;
+    Fr* d_h = P->h[k].as<Fr>();
+    const size_t m = domain_size(c, nullptr);
+    const int n = P->n;
+    auto announce = [&](bool failed) {
+        { std::lock_guard<std::mutex> lk(P->h_mu); P->h_issued = gen; if (failed) P->h_failed = true; }
+        P->h_cv.notify_all();
+    };
+    try {
+        if (inputs) prover_upload_witness(P, k, inputs, aux);
+        if (k == 0) {
+            try {
+                canonical_check_enqueue(cx, d_wit, (size_t)c->ni + c->na, CHK_WITNESS);
+                prove_h(cx, c, d_wit, d_h, nullptr);
+                for (int j = 1; j < n; j++) {
+                    size_t lo, hi;
+                    share(m - 1, j, n, lo, hi);
+                    if (hi > lo) ZA_CUDA(cudaMemcpyPeerAsync(P->h[j].as<Fr>() + lo, P->devices[j], d_h + lo, P->devices[0], (hi - lo) * sizeof(Fr), cx->stream));
+                    ZA_CUDA(cudaEventRecord(P->h_ready[j], cx->stream));
+                }
+            } catch (...) { announce(true); throw; }
+            announce(false);
+            prove_msms_enqueue(cx, pk, c, d_wit, d_h, 0, n, MSM_WITNESS);
+            prove_msms_enqueue(cx, pk, c, d_wit, d_h, 0, n, MSM_H);
+        } else {
+            prove_msms_enqueue(cx, pk, c, d_wit, d_h, k, n, MSM_WITNESS);
+            bool failed;
+            {
+                std::unique_lock<std::mutex> lk(P->h_mu);
+                P->h_cv.wait(lk, [&] { return P->h_issued >= gen; });
+                failed = P->h_failed;
+            }
+            if (failed) throw ZaError(ZA_ERR_INVALID, "the H pipeline on the first device failed");
+            ZA_CUDA(cudaStreamWaitEvent(cx->stream, P->h_ready[k], 0));
+            prove_msms_enqueue(cx, pk, c, d_wit, d_h, k, n, MSM_H);
+        }
+        prove_msms_collect(cx, P->partials[k]);
+        if (k == 0) {
+            ZA_CUDA(cudaStreamSynchronize(cx->stream));
+            const unsigned long long bad = canonical_check_verdict(cx, CHK_WITNESS);
+            if (bad != ~0ull) {
+                char b[128];
+                if (bad < c->ni) snprintf(b, sizeof b, "inputs[%llu] is not a canonical Fr element (>= r)", bad);
+                else snprintf(b, sizeof b, "aux[%llu] is not a canonical Fr element (>= r)", bad - c->ni);
+                throw ZaError(ZA_ERR_NOT_CANONICAL, b);
+            }
+        }
+    } catch (...) {
+        msm_abort(cx);
+        if (k == 0 && cx->host_flag && cx->host_flag[CHK_WITNESS] != ~0ull) {
+            const unsigned long long bad = canonical_check_verdict(cx, CHK_WITNESS);
+            char b[128];
+            if (bad < c->ni) snprintf(b, sizeof b, "inputs[%llu] is not a canonical Fr element (>= r)", bad);
+            else snprintf(b, sizeof b, "aux[%llu] is not a canonical Fr element (>= r)", bad - c->ni);
+            throw ZaError(ZA_ERR_NOT_CANONICAL, b);
+        }
+        throw;
+    }
+}
+
+static void prover_create_proof(Prover* P, const uint8_t* inputs, const uint8_t* aux, const uint8_t* r_le, const uint8_t* s_le, uint8_t* proof_out) {
+    if (P->circ.empty() || P->pk.empty()) throw ZaError(ZA_ERR_INVALID, "za_prover: load a proving key and a circuit first");
+    const Pk* pk0 = P->pk[0]->p.get();
+    const Circuit* c0 = P->circ[0]->c.get();
+    prove_validate(pk0, r_le, s_le);
+    if (P->n == 1) {
+        Ctx* cx = &P->ctx[0]->c;
+        ZA_CUDA(cudaSetDevice(P->devices[0]));
+        if (inputs) prover_upload_witness(P, 0, inputs, aux);
+        create_proof_device(cx, pk0, c0, (const uint8_t*)P->wit[0].p, r_le, s_le, proof_out, nullptr);
+        return;
+    }
+    const uint64_t gen = ++P->generation;
+    { std::lock_guard<std::mutex> lk(P->h_mu); P->h_failed = false; }
+    AssemblePre pre;
+    prover_run_all(P, [&](int k) { prover_device_step(P, k, gen, inputs, aux); }, [&] { pre = prove_assemble_pre(pk0, r_le, s_le); });
+    Partials sum = P->partials[0];
+    for (int k = 1; k < P->n; k++) {
+        for (int i = 0; i < 6; i++) xyzz_add<Fq>(sum.g1[i], P->partials[k].g1[i]);
+        for (int i = 0; i < 2; i++) xyzz_add<Fq2>(sum.g2[i], P->partials[k].g2[i]);
+    }
+    prove_assemble_post(pre, sum, proof_out);
+}
+
+// after the key and the circuit are on every device: point ranges, tables of the ranges, witness / h buffers
+static void prover_finish_setup(Prover* P) {
+    if (P->circ.empty() || P->pk.empty()) return;
+    const Circuit* c0 = P->circ[0]->c.get();
+    const size_t m = domain_size(c0, nullptr);
+    if (P->n > 1) {
+        // device 0 runs the H pipeline (rho = its time / the time of the witness multiexps on one GPU; measured 2.1 ms /
+        // 18 ms at 2^20) while the others already accumulate: its share of the witness multiexps shrinks accordingly
+        double rho = 0.115;
+        if (const char* e = getenv("ZA_PROVER_H_RATIO")) { double v = atof(e); if (v >= 0 && v < 1) rho = v; }
+        double w = (1.0 - rho * (P->n - 1)) / (1.0 + rho);
+        if (w < 0.05) w = 0.05;
+        if (w > 1.0) w = 1.0;
+        P->rank0_weight = (uint32_t)(w * 1000.0 + 0.5);
+        if (P->rank0_weight < 1) P->rank0_weight = 1;
+    } else P->rank0_weight = 1000;
+    prover_run_all(P, [&](int k) {
+        ZA_CUDA(cudaSetDevice(P->devices[k]));
+        const Circuit* c = P->circ[k]->c.get();
+        if (P->n > 1) {
+            int rc = za_pk_partition_weighted(P->ctx[k], P->pk[k], P->circ[k], k, P->n, P->rank0_weight);
+            if (rc != ZA_OK) throw ZaError(rc, last_error());
+        } else check_query_lengths(P->pk[k]->p.get(), c, m);
+        P->wit[k].ensure(((size_t)c->ni + c->na) * 32);
+        P->h[k].ensure(m * sizeof(Fr));
+    });
+    prover_plan_spans(P);
+}
+
 }  // namespace za
+
+struct za_prover { za::Prover p; };
 
 using namespace za;
 
@@ -816,13 +1171,13 @@ int za_bases_upload(za_ctx* ctx, int group, const uint8_t* bases, size_t n, za_b
 void za_bases_free(za_bases* b) { delete b; }
 size_t za_bases_len(const za_bases* b) { return b ? b->b->n : 0; }
 
-static int multiexp_common(za_ctx* ctx, const za_bases* bases, size_t offset, const uint32_t* d_scalars, size_t n, uint8_t* out, bool partial) {
+static int multiexp_common(za_ctx* ctx, const za_bases* bases, size_t offset, const uint32_t* d_scalars, size_t n, uint8_t* out, bool partial, bool check) {
     Ctx* c = &ctx->c;
     if (bases->b->group == 1) {
-        G1XYZZ r = multiexp_dev<Fq>(c, bases->b.get(), offset, d_scalars, n);
+        G1XYZZ r = multiexp_dev<Fq>(c, bases->b.get(), offset, d_scalars, n, check);
         if (partial) xyzz_to_le(r, out); else g1_to_le(xyzz_to_affine<Fq>(r), out);
     } else {
-        G2XYZZ r = multiexp_dev<Fq2>(c, bases->b.get(), offset, d_scalars, n);
+        G2XYZZ r = multiexp_dev<Fq2>(c, bases->b.get(), offset, d_scalars, n, check);
         if (partial) xyzz_to_le(r, out); else g2_to_le(xyzz_to_affine<Fq2>(r), out);
     }
     return ZA_OK;
@@ -849,7 +1204,7 @@ int za_multiexp(za_ctx* ctx, const za_bases* bases, size_t offset, const uint8_t
     DevBuf& d = c->scratch[8];
     d.ensure(n * 32);
     if (n) ZA_CUDA(cudaMemcpyAsync(d.p, src, n * 32, cudaMemcpyHostToDevice, c->stream));
-    return multiexp_common(ctx, bases, offset, d.as<uint32_t>(), n, out, false);
+    return multiexp_common(ctx, bases, offset, d.as<uint32_t>(), n, out, false, false);
     ZA_CATCH
 }
 
@@ -857,7 +1212,7 @@ int za_multiexp_device(za_ctx* ctx, const za_bases* bases, size_t offset, const 
     if (!ctx || !bases || !out || (n && !d_scalars)) return fail(ZA_ERR_INVALID, "NULL argument");
     ZA_TRY
     ZA_CUDA(cudaSetDevice(ctx->c.device));
-    return multiexp_common(ctx, bases, offset, (const uint32_t*)d_scalars, n, out, false);
+    return multiexp_common(ctx, bases, offset, (const uint32_t*)d_scalars, n, out, false, true);
     ZA_CATCH
 }
 
@@ -865,7 +1220,7 @@ int za_multiexp_partial_device(za_ctx* ctx, const za_bases* bases, size_t offset
     if (!ctx || !bases || !out_xyzz || (n && !d_scalars)) return fail(ZA_ERR_INVALID, "NULL argument");
     ZA_TRY
     ZA_CUDA(cudaSetDevice(ctx->c.device));
-    return multiexp_common(ctx, bases, offset, (const uint32_t*)d_scalars, n, out_xyzz, true);
+    return multiexp_common(ctx, bases, offset, (const uint32_t*)d_scalars, n, out_xyzz, true, true);
     ZA_CATCH
 }
 
@@ -1041,6 +1396,7 @@ int za_pk_partition(za_ctx* ctx, za_pk* pk, const za_circuit* circuit, int rank,
 
 int za_circuit_satisfied(za_ctx* ctx, const za_circuit* circuit, const uint8_t* inputs, const uint8_t* aux, int64_t* first_bad) {
     if (!ctx || !circuit || !inputs || !first_bad) return fail(ZA_ERR_INVALID, "NULL argument");
+    if (circuit->c->na && !aux) return fail(ZA_ERR_INVALID, "aux is NULL");
     ZA_TRY
     Ctx* cx = &ctx->c;
     const Circuit* c = circuit->c.get();
@@ -1094,9 +1450,24 @@ int za_prove_h_device(za_ctx* ctx, const za_circuit* circuit, const void* d_witn
     if (!ctx || !circuit || !d_witness || !d_h) return fail(ZA_ERR_INVALID, "NULL argument");
     ZA_TRY
     ZA_CUDA(cudaSetDevice(ctx->c.device));
-    prove_h(&ctx->c, circuit->c.get(), (const uint8_t*)d_witness, (Fr*)d_h, nullptr);
+    const Circuit* c = circuit->c.get();
+    canonical_check_enqueue(&ctx->c, d_witness, (size_t)c->ni + c->na, CHK_WITNESS);      // verdict: za_prove_msm_collect / _partials
+    prove_h(&ctx->c, c, (const uint8_t*)d_witness, (Fr*)d_h, nullptr);
     return ZA_OK;
     ZA_CATCH
+}
+
+// verdicts of the range checks the staged entry points enqueued on this context (after a synchronisation)
+static void staged_check_verdicts(Ctx* ctx, const Circuit* c) {
+    ZA_CUDA(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long w = canonical_check_verdict(ctx, CHK_WITNESS), h = canonical_check_verdict(ctx, CHK_H);
+    char b[128];
+    if (w != ~0ull) {
+        if (c && w >= c->ni) snprintf(b, sizeof b, "aux[%llu] is not a canonical Fr element (>= r)", w - c->ni);
+        else snprintf(b, sizeof b, "witness[%llu] is not a canonical Fr element (>= r)", w);
+        throw ZaError(ZA_ERR_NOT_CANONICAL, b);
+    }
+    if (h != ~0ull) { snprintf(b, sizeof b, "h[%llu] is not a canonical Fr element (>= r)", h); throw ZaError(ZA_ERR_NOT_CANONICAL, b); }
 }
 
 int za_prove_msm_partials(za_ctx* ctx, const za_pk* pk, const za_circuit* circuit, const void* d_witness, const void* d_h, int rank, int world,
@@ -1106,7 +1477,12 @@ int za_prove_msm_partials(za_ctx* ctx, const za_pk* pk, const za_circuit* circui
     ZA_TRY
     ZA_CUDA(cudaSetDevice(ctx->c.device));
     Partials P;
-    prove_msms(&ctx->c, pk->p.get(), circuit->c.get(), (const uint8_t*)d_witness, (const Fr*)d_h, rank, world, P);
+    const Circuit* c = circuit->c.get();
+    canonical_check_enqueue(&ctx->c, d_witness, (size_t)c->ni + c->na, CHK_WITNESS);
+    { size_t lo, hi; share(domain_size(c, nullptr) - 1, rank, world, lo, hi); canonical_check_enqueue(&ctx->c, (const Fr*)d_h + lo, hi - lo, CHK_H); }
+    try { prove_msms(&ctx->c, pk->p.get(), c, (const uint8_t*)d_witness, (const Fr*)d_h, rank, world, P); }
+    catch (...) { msm_abort(&ctx->c); throw; }
+    staged_check_verdicts(&ctx->c, c);
     partials_to_le(P, partials_out);
     return ZA_OK;
     ZA_CATCH
@@ -1119,7 +1495,11 @@ int za_prove_msm_enqueue(za_ctx* ctx, const za_pk* pk, const za_circuit* circuit
     if (!(which & (MSM_WITNESS | MSM_H)) || ((which & MSM_H) && !d_h)) return fail(ZA_ERR_INVALID, "bad multiexp selection");
     ZA_TRY
     ZA_CUDA(cudaSetDevice(ctx->c.device));
-    prove_msms_enqueue(&ctx->c, pk->p.get(), circuit->c.get(), (const uint8_t*)d_witness, (const Fr*)d_h, rank, world, which);
+    const Circuit* c = circuit->c.get();
+    if (which & MSM_WITNESS) canonical_check_enqueue(&ctx->c, d_witness, (size_t)c->ni + c->na, CHK_WITNESS);
+    if (which & MSM_H) { size_t lo, hi; share(domain_size(c, nullptr) - 1, rank, world, lo, hi); canonical_check_enqueue(&ctx->c, (const Fr*)d_h + lo, hi - lo, CHK_H); }
+    try { prove_msms_enqueue(&ctx->c, pk->p.get(), c, (const uint8_t*)d_witness, (const Fr*)d_h, rank, world, which); }
+    catch (...) { msm_abort(&ctx->c); throw; }
     return ZA_OK;
     ZA_CATCH
 }
@@ -1131,7 +1511,9 @@ int za_prove_msm_collect(za_ctx* ctx, uint8_t* partials_out) {
     for (int s : {0, 1, 2, 3, 4})
         if (!ctx->c.slots[s].busy) return fail(ZA_ERR_INVALID, "za_prove_msm_collect: multiexp %d was not enqueued", s);
     Partials P;
-    prove_msms_collect(&ctx->c, P);
+    try { prove_msms_collect(&ctx->c, P); }
+    catch (...) { msm_abort(&ctx->c); throw; }
+    staged_check_verdicts(&ctx->c, nullptr);
     partials_to_le(P, partials_out);
     return ZA_OK;
     ZA_CATCH
@@ -1155,6 +1537,148 @@ int za_create_proof_device(za_ctx* ctx, const za_pk* pk, const za_circuit* circu
     create_proof_device(&ctx->c, pk->p.get(), circuit->c.get(), (const uint8_t*)d_witness, r, s, proof_out, nullptr);
     return ZA_OK;
     ZA_CATCH
+}
+
+// ---- several GPUs behind one call
+int za_prover_create(const int* devices, int n_devices, za_prover** out) {
+    if (!devices || !out || n_devices < 1 || n_devices > 64) return fail(ZA_ERR_INVALID, "bad argument");
+    *out = nullptr;
+    for (int i = 0; i < n_devices; i++) for (int j = 0; j < i; j++) if (devices[i] == devices[j]) return fail(ZA_ERR_INVALID, "device %d listed twice", devices[i]);
+    ZA_TRY
+    std::unique_ptr<za_prover> h(new za_prover());
+    Prover* P = &h->p;
+    P->n = n_devices;
+    P->devices.assign(devices, devices + n_devices);
+    P->ctx.assign(n_devices, nullptr); P->pk.clear(); P->circ.clear();
+    P->wit.resize(n_devices); P->h.resize(n_devices); P->h_ready.assign(n_devices, nullptr); P->partials.resize(n_devices);
+    for (int k = 0; k < n_devices; k++) {
+        int rc = za_ctx_create(devices[k], &P->ctx[k]);
+        if (rc != ZA_OK) return rc;
+    }
+    // recorded on device 0's stream (an event belongs to the device it was created on); the peers wait on them
+    ZA_CUDA(cudaSetDevice(devices[0]));
+    for (int k = 0; k < n_devices; k++) ZA_CUDA(cudaEventCreateWithFlags(&P->h_ready[k], cudaEventDisableTiming));
+    // device 0 writes the h slices straight into its peers' memory
+    for (int k = 1; k < n_devices; k++) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, devices[0], devices[k]) == cudaSuccess && can) {
+            cudaSetDevice(devices[0]);
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[k], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { /* the copy falls back to staging through the host */ }
+            cudaGetLastError();
+        }
+    }
+    for (int k = 0; k < n_devices; k++) {
+        P->workers.emplace_back(new ProverWorker());
+        ProverWorker* w = P->workers.back().get();
+        w->th = std::thread(prover_worker_loop, w);
+    }
+    *out = h.release();
+    return ZA_OK;
+    ZA_CATCH
+}
+void za_prover_destroy(za_prover* p) { delete p; }
+int za_prover_device_count(const za_prover* p) { return p ? p->p.n : 0; }
+za_ctx* za_prover_ctx(za_prover* p, int k) { return (p && k >= 0 && k < p->p.n) ? p->p.ctx[k] : nullptr; }
+
+static void prover_drop_pk(Prover* P) {
+    for (int k = 0; k < (int)P->pk.size(); k++) { cudaSetDevice(P->devices[k]); delete P->pk[k]; }
+    P->pk.clear();
+}
+int za_prover_load_pk(za_prover* p, const uint8_t* params, size_t len, int checked) {
+    if (!p || !params) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    Prover* P = &p->p;
+    prover_drop_pk(P);
+    P->pk.assign(P->n, nullptr);
+    try {
+        prover_run_all(P, [&](int k) {
+            ZA_CUDA(cudaSetDevice(P->devices[k]));
+            std::unique_ptr<za_pk> h(new za_pk());
+            h->p = pk_load(&P->ctx[k]->c, params, len, checked != 0);
+            P->pk[k] = h.release();
+        });
+        prover_finish_setup(P);
+    } catch (...) { prover_drop_pk(P); throw; }
+    return ZA_OK;
+    ZA_CATCH
+}
+int za_prover_synthetic_pk(za_prover* p, const uint32_t* counts) {
+    if (!p || !counts) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    Prover* P = &p->p;
+    prover_drop_pk(P);
+    P->pk.assign(P->n, nullptr);
+    try {
+        prover_run_all(P, [&](int k) {
+            za_pk* h = nullptr;
+            int rc = za_pk_synthetic(P->ctx[k], counts, &h);
+            if (rc != ZA_OK) throw ZaError(rc, last_error());
+            P->pk[k] = h;
+        });
+        prover_finish_setup(P);
+    } catch (...) { prover_drop_pk(P); throw; }
+    return ZA_OK;
+    ZA_CATCH
+}
+int za_prover_set_circuit(za_prover* p, const za_r1cs* cs) {
+    if (!p || !cs) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    Prover* P = &p->p;
+    for (int k = 0; k < (int)P->circ.size(); k++) { cudaSetDevice(P->devices[k]); delete P->circ[k]; }
+    P->circ.assign(P->n, nullptr);
+    try {
+        prover_run_all(P, [&](int k) {
+            ZA_CUDA(cudaSetDevice(P->devices[k]));
+            std::unique_ptr<za_circuit> h(new za_circuit());
+            h->c = circuit_upload(&P->ctx[k]->c, cs);
+            P->circ[k] = h.release();
+        });
+        prover_finish_setup(P);
+    } catch (...) {
+        for (int k = 0; k < (int)P->circ.size(); k++) { cudaSetDevice(P->devices[k]); delete P->circ[k]; }
+        P->circ.clear();
+        throw;
+    }
+    return ZA_OK;
+    ZA_CATCH
+}
+int za_prover_vk(const za_prover* p, uint8_t* vk_out, size_t size) {
+    if (!p || p->p.pk.empty()) return fail(ZA_ERR_INVALID, "za_prover: no proving key loaded");
+    return za_pk_vk(p->p.pk[0], vk_out, size);
+}
+int za_prover_pk_counts(const za_prover* p, uint32_t* counts) {
+    if (!p || p->p.pk.empty()) return fail(ZA_ERR_INVALID, "za_prover: no proving key loaded");
+    return za_pk_counts(p->p.pk[0], counts);
+}
+int za_prover_upload_witness(za_prover* p, const uint8_t* inputs, const uint8_t* aux) {
+    if (!p || !inputs) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    Prover* P = &p->p;
+    if (P->circ.empty() || P->pk.empty()) return fail(ZA_ERR_INVALID, "za_prover: load a proving key and a circuit first");
+    if (P->circ[0]->c->na && !aux) return fail(ZA_ERR_INVALID, "aux is NULL");
+    prover_run_all(P, [&](int k) {
+        ZA_CUDA(cudaSetDevice(P->devices[k]));
+        prover_upload_witness(P, k, inputs, aux);
+        ZA_CUDA(cudaStreamSynchronize(P->ctx[k]->c.stream));
+    });
+    return ZA_OK;
+    ZA_CATCH
+}
+int za_prover_create_proof(za_prover* p, const uint8_t* inputs, const uint8_t* aux, const uint8_t* r, const uint8_t* s, uint8_t* proof_out) {
+    if (!p || !r || !s || !proof_out) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    Prover* P = &p->p;
+    if (P->circ.empty() || P->pk.empty()) return fail(ZA_ERR_INVALID, "za_prover: load a proving key and a circuit first");
+    if (inputs && P->circ[0]->c->na && !aux) return fail(ZA_ERR_INVALID, "aux is NULL");
+    prover_create_proof(P, inputs, aux, r, s, proof_out);
+    return ZA_OK;
+    ZA_CATCH
+}
+uint64_t za_prover_launch_count(const za_prover* p) {
+    uint64_t t = 0;
+    if (p) for (za_ctx* c : p->p.ctx) t += c->c.launches;
+    return t;
 }
 
 int za_create_proof(za_ctx* ctx, const za_pk* pk, const za_circuit* circuit, const uint8_t* inputs, const uint8_t* aux, const uint8_t* r,

@@ -244,6 +244,20 @@ class Parameters:
             pass
 
 
+def _r1cs_struct(num_inputs, num_aux, ptr, var, coeff):
+    """za_r1cs over numpy arrays; returns (struct, the arrays it points into)."""
+    ptr = [np.ascontiguousarray(p, dtype=np.uint32) for p in ptr]
+    var = [np.ascontiguousarray(v, dtype=np.uint32) for v in var]
+    coeff = [_u8(c, 32) for c in coeff]
+    s = ZaR1CS()
+    s.num_inputs, s.num_aux, s.num_constraints = num_inputs, num_aux, len(ptr[0]) - 1
+    for w in range(3):
+        s.ptr[w] = ptr[w].ctypes.data_as(u32p)
+        s.var[w] = var[w].ctypes.data_as(u32p)
+        s.coeff[w] = coeff[w].ctypes.data_as(u8p)
+    return s, (ptr, var, coeff)
+
+
 class Circuit:
     """The enforce(A, B, C) rows CircomCircuit::synthesize (prover.rs:45-103) hands to bellman, on the GPU.
 
@@ -253,16 +267,8 @@ class Circuit:
     def __init__(self, ctx, num_inputs, num_aux, ptr, var, coeff):
         self.ctx = ctx
         self.num_inputs, self.num_aux = num_inputs, num_aux
-        self._ptr = [np.ascontiguousarray(p, dtype=np.uint32) for p in ptr]
-        self._var = [np.ascontiguousarray(v, dtype=np.uint32) for v in var]
-        self._coeff = [_u8(c, 32) for c in coeff]
-        self.num_constraints = len(self._ptr[0]) - 1
-        s = ZaR1CS()
-        s.num_inputs, s.num_aux, s.num_constraints = num_inputs, num_aux, self.num_constraints
-        for w in range(3):
-            s.ptr[w] = self._ptr[w].ctypes.data_as(u32p)
-            s.var[w] = self._var[w].ctypes.data_as(u32p)
-            s.coeff[w] = self._coeff[w].ctypes.data_as(u8p)
+        s, self._keep = _r1cs_struct(num_inputs, num_aux, ptr, var, coeff)
+        self.num_constraints = s.num_constraints
         h = ctypes.c_void_p()
         check(lib().za_circuit_upload(ctx.h, ctypes.byref(s), ctypes.byref(h)))
         self.h = h
@@ -305,6 +311,85 @@ class Circuit:
             self.close()
         except Exception:
             pass
+
+
+class _BorrowedContext(Context):
+    """The context of one device of a Prover (owned by the Prover)."""
+
+    def __init__(self, handle, device):
+        self.h, self.device = handle, device
+
+    def close(self):
+        self.h = None
+
+
+class Prover:
+    """za_prover: create_proof over several GPUs of one box behind one call (include/za_b200.h).
+    One host thread per device inside the library; nothing but CUDA runtime calls on the path."""
+
+    def __init__(self, devices):
+        self.devices = list(devices)
+        arr = (ctypes.c_int * len(self.devices))(*self.devices)
+        h = ctypes.c_void_p()
+        check(lib().za_prover_create(arr, len(self.devices), ctypes.byref(h)))
+        self.h = h
+        self.num_inputs = self.num_aux = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().za_prover_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ctx(self, k=0):
+        return _BorrowedContext(ctypes.c_void_p(lib().za_prover_ctx(self.h, k)), self.devices[k])
+
+    def load_pk(self, data, checked=True):
+        buf = np.frombuffer(bytes(data), np.uint8)
+        check(lib().za_prover_load_pk(self.h, _p(buf), buf.shape[0], 1 if checked else 0))
+
+    def synthetic_pk(self, ic, h, l, a, b_g1, b_g2):
+        c = (ctypes.c_uint32 * 6)(ic, h, l, a, b_g1, b_g2)
+        check(lib().za_prover_synthetic_pk(self.h, c))
+
+    def set_circuit(self, num_inputs, num_aux, ptr, var, coeff):
+        s, keep = _r1cs_struct(num_inputs, num_aux, ptr, var, coeff)
+        check(lib().za_prover_set_circuit(self.h, ctypes.byref(s)))
+        self.num_inputs, self.num_aux = num_inputs, num_aux
+
+    def vk(self):
+        c = (ctypes.c_uint32 * 6)()
+        check(lib().za_prover_pk_counts(self.h, c))
+        n_ic = c[0]
+        buf = np.zeros(64 * 3 + 128 * 3 + 64 * n_ic, np.uint8)
+        check(lib().za_prover_vk(self.h, _p(buf), buf.shape[0]))
+        b = buf.tobytes()
+        return dict(alpha_g1=b[0:64], beta_g1=b[64:128], beta_g2=b[128:256], gamma_g2=b[256:384], delta_g1=b[384:448],
+                    delta_g2=b[448:576], ic=[b[576 + 64 * i:640 + 64 * i] for i in range(n_ic)])
+
+    def upload_witness(self, inputs, aux):
+        inputs, aux = _u8(inputs, 32), _u8(aux, 32)
+        if inputs.shape[0] != self.num_inputs or aux.shape[0] != self.num_aux:
+            raise ValueError("witness size does not match the circuit")
+        check(lib().za_prover_upload_witness(self.h, _p(inputs), _p(aux)))
+
+    def create_proof(self, inputs, aux, r, s):
+        """inputs / aux: host arrays (uploaded inside the call), or None, None: the resident witness again."""
+        if inputs is not None:
+            inputs, aux = _u8(inputs, 32), _u8(aux, 32)
+            if inputs.shape[0] != self.num_inputs or aux.shape[0] != self.num_aux:
+                raise ValueError("witness size does not match the circuit")
+        proof = np.zeros(256, np.uint8)
+        check(lib().za_prover_create_proof(self.h, _p(inputs), _p(aux), _p(_scalar(r)), _p(_scalar(s)), _p(proof)))
+        return proof.tobytes()
+
+    def launch_count(self):
+        return int(lib().za_prover_launch_count(self.h))
 
 
 def _domain_size(n):
