@@ -225,6 +225,8 @@ int za_prover_upload_witness(za_prover *p, const uint8_t *inputs, const uint8_t 
 int za_prover_create_proof(za_prover *p, const uint8_t *inputs, const uint8_t *aux, const uint8_t *r, const uint8_t *s,
                            uint8_t *proof_out);
 uint64_t za_prover_launch_count(const za_prover *p);
+/* info[3] = witness bytes uploaded per proof over all devices, device 0's share weight (per mille), bytes read back */
+int za_prover_info(const za_prover *p, uint64_t *info);
 
 /* ---- synthetic inputs and measurement utilities ---------------------------------------
  * bases[i] = (first_multiple + i) * G: distinct points with known discrete logarithms, so a full-size

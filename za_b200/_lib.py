@@ -112,6 +112,7 @@ SYMBOLS = {
     "za_prover_upload_witness": (ci, [vp, vp, vp]),
     "za_prover_create_proof": (ci, [vp, vp, vp, vp, vp, vp]),
     "za_prover_launch_count": (ctypes.c_uint64, [vp]),
+    "za_prover_info": (ci, [vp, vp]),
 }
 
 _lib = None

@@ -121,6 +121,8 @@ struct Ctx {
     cudaEvent_t h_fork = nullptr, h_join = nullptr;
     unsigned long long* host_flag = nullptr;   // pinned: verdict of the witness range check of create_proof
     uint64_t launches = 0;              // kernels launched through this context (bench: gpu_launches)
+    cudaEvent_t dbg_t0 = nullptr;       // ZA_DEBUG_TIMELINE: start of the current proof on this device
+    bool dbg_t0_valid = false;
     bool ntt_attr_set = false;          // the > 48 KiB shared-memory attribute of the NTT kernels is set on this context's device
     // optional per-kernel-class timing with CUDA events on `stream` (bench.py roofline numbers)
     bool profile = false;

@@ -718,7 +718,8 @@ static void print_timeline(Ctx* ctx) {
     if (!timeline) return;
     const int order[5] = {3, 4, 0, 1, 2};
     const char* name[5] = {"B(G1)", "B(G2)", "H", "L", "A"};
-    cudaEvent_t base = ctx->slots[3].dbg_start;
+    cudaEvent_t base = ctx->dbg_t0_valid ? ctx->dbg_t0 : ctx->slots[3].dbg_start;
+    ctx->dbg_t0_valid = false;
     for (int k = 0; k < 5; k++) {
         MsmSlot& sl = ctx->slots[order[k]];
         float a = 0, b = 0, d = 0, so = 0;
@@ -1020,10 +1021,19 @@ static void prover_upload_witness(Prover* P, int k, const uint8_t* inputs, const
     }
 }
 
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 // one device's part of one proof (runs on that device's thread)
 static void prover_device_step(Prover* P, int k, uint64_t gen, const uint8_t* inputs, const uint8_t* aux) {
+    static const bool tl = getenv("ZA_DEBUG_TIMELINE") != nullptr;
+    double t_start = tl ? now_ms() : 0, t_wit = 0, t_h = 0, t_enq = 0, t_col = 0;
     ZA_CUDA(cudaSetDevice(P->devices[k]));
     Ctx* cx = &P->ctx[k]->c;
+    if (tl) {
+        if (!cx->dbg_t0) cudaEventCreate(&cx->dbg_t0);
+        cudaEventRecord(cx->dbg_t0, cx->stream);
+        cx->dbg_t0_valid = true;
+    }
     const Pk* pk = P->pk[k]->p.get();
     const Circuit* c = P->circ[k]->c.get();
     const uint8_t* d_wit = (const uint8_t*)P->wit[k].p;
@@ -1048,10 +1058,13 @@ static void prover_device_step(Prover* P, int k, uint64_t gen, const uint8_t* in
                 }
             } catch (...) { announce(true); throw; }
             announce(false);
+            if (tl) t_h = now_ms();
             prove_msms_enqueue(cx, pk, c, d_wit, d_h, 0, n, MSM_WITNESS);
+            if (tl) t_wit = now_ms();
             prove_msms_enqueue(cx, pk, c, d_wit, d_h, 0, n, MSM_H);
         } else {
             prove_msms_enqueue(cx, pk, c, d_wit, d_h, k, n, MSM_WITNESS);
+            if (tl) t_wit = now_ms();
             bool failed;
             {
                 std::unique_lock<std::mutex> lk(P->h_mu);
@@ -1059,10 +1072,18 @@ static void prover_device_step(Prover* P, int k, uint64_t gen, const uint8_t* in
                 failed = P->h_failed;
             }
             if (failed) throw ZaError(ZA_ERR_INVALID, "the H pipeline on the first device failed");
+            if (tl) t_h = now_ms();
             ZA_CUDA(cudaStreamWaitEvent(cx->stream, P->h_ready[k], 0));
             prove_msms_enqueue(cx, pk, c, d_wit, d_h, k, n, MSM_H);
         }
+        if (tl) t_enq = now_ms();
         prove_msms_collect(cx, P->partials[k]);
+        if (tl) {
+            t_col = now_ms();
+            fprintf(stderr, "[za prover] dev %d host ms since job start: witness msms enqueued %.3f, h issued/seen %.3f, all enqueued %.3f, collected %.3f\n", k,
+                    t_wit - t_start, t_h - t_start, t_enq - t_start, t_col - t_start);
+            print_timeline(cx);
+        }
         if (k == 0) {
             ZA_CUDA(cudaStreamSynchronize(cx->stream));
             const unsigned long long bad = canonical_check_verdict(cx, CHK_WITNESS);
@@ -1100,14 +1121,19 @@ static void prover_create_proof(Prover* P, const uint8_t* inputs, const uint8_t*
     }
     const uint64_t gen = ++P->generation;
     { std::lock_guard<std::mutex> lk(P->h_mu); P->h_failed = false; }
+    static const bool tl = getenv("ZA_DEBUG_TIMELINE") != nullptr;
+    const double t0 = tl ? now_ms() : 0;
     AssemblePre pre;
-    prover_run_all(P, [&](int k) { prover_device_step(P, k, gen, inputs, aux); }, [&] { pre = prove_assemble_pre(pk0, r_le, s_le); });
+    double t_pre = 0;
+    prover_run_all(P, [&](int k) { prover_device_step(P, k, gen, inputs, aux); }, [&] { pre = prove_assemble_pre(pk0, r_le, s_le); if (tl) t_pre = now_ms(); });
+    const double t1 = tl ? now_ms() : 0;
     Partials sum = P->partials[0];
     for (int k = 1; k < P->n; k++) {
         for (int i = 0; i < 6; i++) xyzz_add<Fq>(sum.g1[i], P->partials[k].g1[i]);
         for (int i = 0; i < 2; i++) xyzz_add<Fq2>(sum.g2[i], P->partials[k].g2[i]);
     }
     prove_assemble_post(pre, sum, proof_out);
+    if (tl) fprintf(stderr, "[za prover] proof %llu: host pre %.3f ms, devices done %.3f, combine + assemble %.3f\n", (unsigned long long)gen, t_pre - t0, t1 - t0, now_ms() - t1);
 }
 
 // after the key and the circuit are on every device: point ranges, tables of the ranges, witness / h buffers
@@ -1674,6 +1700,16 @@ int za_prover_create_proof(za_prover* p, const uint8_t* inputs, const uint8_t* a
     prover_create_proof(P, inputs, aux, r, s, proof_out);
     return ZA_OK;
     ZA_CATCH
+}
+int za_prover_info(const za_prover* p, uint64_t* info) {
+    if (!p || !info) return fail(ZA_ERR_INVALID, "NULL argument");
+    const Prover* P = &p->p;
+    uint64_t h2d = 0;
+    for (auto& dev : P->spans) for (auto& sp : dev) h2d += (sp.second - sp.first) * 32;
+    info[0] = h2d;                       // witness bytes uploaded per proof, all devices
+    info[1] = P->rank0_weight;           // per mille of an ordinary share that device 0 takes of the witness multiexps
+    info[2] = (uint64_t)P->n * (4 * 6 * 128 + 6 * 256) + 8;   // bytes read back per proof: 6 partial results per multiexp and device, one verdict
+    return ZA_OK;
 }
 uint64_t za_prover_launch_count(const za_prover* p) {
     uint64_t t = 0;

@@ -391,6 +391,11 @@ class Prover:
     def launch_count(self):
         return int(lib().za_prover_launch_count(self.h))
 
+    def info(self):
+        v = (ctypes.c_uint64 * 3)()
+        check(lib().za_prover_info(self.h, v))
+        return dict(h2d_bytes_per_proof=int(v[0]), device0_weight=v[1] / 1000.0, d2h_bytes_per_proof=int(v[2]))
+
 
 def _domain_size(n):
     m = 1
