@@ -255,6 +255,15 @@ int za_verify_proof(const uint8_t *vk, size_t n_ic, const uint8_t *proof, const 
 /* JsonVerifyingKey (format.rs:130-167): alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2, gamma_g2, ic, input_names */
 int za_vk_to_json(const uint8_t *vk, size_t n_ic, const char *const *input_names, size_t n_names, char *buf,
                   size_t size);
+/* generate_solidity (prover/src/groth16/ethereum.rs:216-261): the verifier contract as text, by substitution of the
+ * eight placeholders <%vk_a%> <%vk_b%> <%vk_gamma%> <%vk_delta%> <%vk_inputs_length%> <%vk_inputs%>
+ * <%vk_gammaABC_length%> <%vk_gammaABC_pts%> — G1 as "x,y", G2 as "[x.c1,x.c0],[y.c1,y.c0]" (ethereum.rs:227-238),
+ * coordinates in ff_ce's Repr Display ("0x" + 64 hex digits), the input names in Rust's {:?} list form.
+ * contract_template: the text to fill (the reference's CONTRACT_TEMPLATE, ethereum.rs:8-214, gives the reference's
+ * exact contract); NULL = the library's own template (an independent Groth16 verifier contract with the same
+ * verifyTx(a, b, c, input) / Verified interface).  *needed (optional) receives the size the text needs. */
+int za_vk_to_solidity(const uint8_t *vk, size_t n_ic, const char *const *input_names, size_t n_names,
+                      const char *contract_template, char *buf, size_t size, size_t *needed);
 /* helper::verify (helper.rs:149-158): vk JSON + proof-with-inputs JSON -> *valid */
 int za_verify_json(const char *vk_json, const char *proof_json, int *valid);
 

@@ -93,3 +93,69 @@ def test_pairing_constants_rederived():
     assert 36 * u ** 4 + 36 * u ** 3 + 24 * u ** 2 + 6 * u + 1 == q and 36 * u ** 4 + 36 * u ** 3 + 18 * u ** 2 + 6 * u + 1 == r
     assert 6 * u + 2 == (1 << 64) + 0x9d797039be763ba8
     assert (q ** 12 - 1) % r == 0 and ((q ** 12 - 1) // r) >> (43 * 64) == 0x2f4b6dc970
+
+
+# ---- Solidity verifier text (ethereum.rs:216-261)
+def _py_solidity(vk, names, template):
+    """Independent restatement of generate_solidity's substitutions in python (str.replace, python ints)."""
+    def c(b): return "0x%064x" % int.from_bytes(b, "little")
+    def g1(p): return c(p[0:32]) + "," + c(p[32:64])
+    def g2(p): return "[" + c(p[32:64]) + "," + c(p[0:32]) + "],[" + c(p[96:128]) + "," + c(p[64:96]) + "]"
+    def dbg(s): return '"' + s.replace("\\", "\\\\").replace('"', '\\"') + '"'
+    t = template
+    t = t.replace("<%vk_a%>", g1(vk["alpha_g1"])).replace("<%vk_b%>", g2(vk["beta_g2"])).replace("<%vk_gamma%>", g2(vk["gamma_g2"]))
+    t = t.replace("<%vk_delta%>", g2(vk["delta_g2"])).replace("<%vk_inputs_length%>", str(len(names)))
+    t = t.replace("<%vk_inputs%>", "[" + ", ".join(dbg(n) for n in names) + "]").replace("<%vk_gammaABC_length%>", str(len(vk["ic"])))
+    return t.replace("<%vk_gammaABC_pts%>", "\n".join("vk.gammaABC[%d] = Pairing.G1Point(%s);" % (i, g1(p)) for i, p in enumerate(vk["ic"])))
+
+
+def _golden_vk():
+    g = golden()
+    vk = {k: bytes.fromhex(v) for k, v in g["vk"].items() if k != "ic"}
+    vk["ic"] = [bytes.fromhex(x) for x in g["vk"]["ic"]]
+    return vk
+
+
+def test_solidity_text_against_python_expectation():
+    """Config 1's verifying key through za_vk_to_solidity with a caller-supplied template that uses every placeholder
+    (twice, to pin replace-all), against the python restatement of ethereum.rs:216-261."""
+    vk = _golden_vk()
+    tmpl = ("A(<%vk_a%>) B(<%vk_b%>) G(<%vk_gamma%>) D(<%vk_delta%>) n=<%vk_inputs_length%> // <%vk_inputs%>\n"
+            "len <%vk_gammaABC_length%>\n<%vk_gammaABC_pts%>\nagain <%vk_a%> <%vk_inputs_length%>\n")
+    for names in (["main.r"], ["main.a", 'we"ird\\name'], []):
+        vk2 = dict(vk)
+        if len(names) + 1 != len(vk["ic"]):
+            vk2["ic"] = (vk["ic"] * 3)[:len(names) + 1]
+        assert za_b200.vk_to_solidity(vk2, names, tmpl) == _py_solidity(vk2, names, tmpl)
+    # G2 is printed imaginary part first (ethereum.rs:227-238)
+    text = za_b200.vk_to_solidity(vk, ["main.r"], "<%vk_b%>")
+    assert text.startswith("[0x%064x,0x%064x]" % (int.from_bytes(vk["beta_g2"][32:64], "little"), int.from_bytes(vk["beta_g2"][0:32], "little")))
+
+
+def test_solidity_builtin_template_is_a_complete_contract():
+    vk = _golden_vk()
+    text = za_b200.vk_to_solidity(vk, ["main.r"])
+    assert "<%" not in text and "pragma solidity" in text and "function verifyTx(" in text
+    assert "uint[1] memory input" in text and 'public inputs, in order: ["main.r"]' in text
+    assert text.count("] = Bn128.G1(0x") == 2 and "new Bn128.G1[](2)" in text
+    assert "0x%064x" % int.from_bytes(vk["alpha_g1"][0:32], "little") in text
+    # the moduli the reference's template embeds (ethereum.rs:37, :173)
+    assert str(P.Q_MOD) in text and str(P.R_MOD) in text
+
+
+def test_solidity_with_the_reference_template_when_present():
+    """With the reference tree at hand (this container only), its CONTRACT_TEMPLATE through the library equals the python
+    restatement — the reference's exact contract for config 1's key."""
+    path = "/root/reference/prover/src/groth16/ethereum.rs"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    src = open(path).read()
+    start = src.index('r#"') + 3
+    tmpl = src[start:src.index('"#;', start)]
+    vk = _golden_vk()
+    got = za_b200.vk_to_solidity(vk, ["main.r"], tmpl)
+    assert got == _py_solidity(vk, ["main.r"], tmpl)
+    assert "<%" not in got and "vk.gammaABC[1] = Pairing.G1Point(0x" in got
+    vk_inf = dict(vk); vk_inf["alpha_g1"] = bytes(64)
+    with pytest.raises(za_b200.ZaError):                           # "non-infinite point expected" (ethereum.rs:224)
+        za_b200.vk_to_solidity(vk_inf, ["main.r"], tmpl)

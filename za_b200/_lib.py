@@ -93,6 +93,7 @@ SYMBOLS = {
     "za_verify_proof": (ci, [vp, sz, vp, vp, sz, ctypes.POINTER(ci)]),
     "za_vk_to_json": (ci, [vp, sz, ctypes.POINTER(ctypes.c_char_p), sz, ctypes.c_char_p, sz]),
     "za_verify_json": (ci, [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ci)]),
+    "za_vk_to_solidity": (ci, [vp, sz, ctypes.POINTER(ctypes.c_char_p), sz, ctypes.c_char_p, ctypes.c_char_p, sz, ctypes.POINTER(sz)]),
     "za_pkfile_scan": (ci, [vp, sz, vp, vp, vp, vp]),
     "za_pkfile_read": (ci, [vp, sz, vp, vp, vp, vp]),
     "za_pkfile_write": (ci, [vp, sz, ctypes.c_uint32, vp, vp, vp, vp, ctypes.c_uint32, vp, sz, vp, sz, vp]),

@@ -327,6 +327,154 @@ int za_vk_to_json(const uint8_t* vk, size_t n_ic, const char* const* input_names
     ZA_CATCH
 }
 
+// ---- Solidity verifier text (prover/src/groth16/ethereum.rs:216-261 `generate_solidity`)
+// The reference fills a contract template by plain text substitution of eight placeholders.  The substitution rules
+// are restated here; the template itself is data: a caller that wants the reference's exact contract passes the
+// reference's CONTRACT_TEMPLATE (ethereum.rs:8-214), otherwise the built-in template below is used — an independent
+// Groth16 verifier contract with the same placeholders and the same external interface (verifyTx / Verified).
+static const char* ZA_SOLIDITY_TEMPLATE = R"SOL(// Groth16 verifier over alt_bn128 (EIP-196 / EIP-197 precompiles).  Generated by za_b200.
+pragma solidity ^0.5.0;
+
+library Bn128 {
+    uint256 constant FIELD_Q = 21888242871839275222246405745257275088696311157297823662689037894645226208583;
+    struct G1 { uint256 x; uint256 y; }
+    struct G2 { uint256[2] x; uint256[2] y; }          // each coordinate as [imaginary, real]
+
+    function neg(G1 memory p) internal pure returns (G1 memory) {
+        if (p.x == 0 && p.y == 0) return G1(0, 0);
+        return G1(p.x, FIELD_Q - (p.y % FIELD_Q));
+    }
+    function add(G1 memory p, G1 memory q) internal view returns (G1 memory r) {
+        uint256[4] memory io = [p.x, p.y, q.x, q.y];
+        bool ok;
+        assembly { ok := staticcall(sub(gas, 2000), 6, io, 0x80, r, 0x40) }
+        require(ok, "bn128 add");
+    }
+    function mul(G1 memory p, uint256 k) internal view returns (G1 memory r) {
+        uint256[3] memory io = [p.x, p.y, k];
+        bool ok;
+        assembly { ok := staticcall(sub(gas, 2000), 7, io, 0x60, r, 0x40) }
+        require(ok, "bn128 mul");
+    }
+    // e(a[0], b[0]) * ... * e(a[3], b[3]) == 1
+    function product4IsOne(G1[4] memory a, G2[4] memory b) internal view returns (bool) {
+        uint256[24] memory io;
+        for (uint256 i = 0; i < 4; i++) {
+            io[6 * i] = a[i].x; io[6 * i + 1] = a[i].y;
+            io[6 * i + 2] = b[i].x[0]; io[6 * i + 3] = b[i].x[1];
+            io[6 * i + 4] = b[i].y[0]; io[6 * i + 5] = b[i].y[1];
+        }
+        uint256[1] memory out;
+        bool ok;
+        assembly { ok := staticcall(sub(gas, 2000), 8, io, 0x300, out, 0x20) }
+        require(ok, "bn128 pairing");
+        return out[0] == 1;
+    }
+}
+
+contract Verifier {
+    uint256 constant SCALAR_R = 21888242871839275222246405745257275088548364400416034343698204186575808495617;
+    struct Key { Bn128.G1 alpha; Bn128.G2 beta; Bn128.G2 gamma; Bn128.G2 delta; Bn128.G1[] ic; }
+    event Verified(string s);
+
+    function key() internal pure returns (Key memory vk) {
+        vk.alpha = Bn128.G1(<%vk_a%>);
+        vk.beta = Bn128.G2(<%vk_b%>);
+        vk.gamma = Bn128.G2(<%vk_gamma%>);
+        vk.delta = Bn128.G2(<%vk_delta%>);
+        vk.ic = new Bn128.G1[](<%vk_gammaABC_length%>);
+        <%vk_gammaABC_pts%>
+    }
+    // public inputs, in order: <%vk_inputs%>
+    function verifyTx(uint[2] memory a, uint[2][2] memory b, uint[2] memory c, uint[<%vk_inputs_length%>] memory input) public returns (bool) {
+        Key memory vk = key();
+        require(input.length + 1 == vk.ic.length, "input count");
+        Bn128.G1 memory acc = vk.ic[0];
+        for (uint256 i = 0; i < input.length; i++) {
+            require(input[i] < SCALAR_R, "input not in field");
+            acc = Bn128.add(acc, Bn128.mul(vk.ic[i + 1], input[i]));
+        }
+        Bn128.G1[4] memory g1 = [Bn128.G1(a[0], a[1]), Bn128.neg(acc), Bn128.neg(Bn128.G1(c[0], c[1])), Bn128.neg(vk.alpha)];
+        Bn128.G2[4] memory g2 = [Bn128.G2([b[0][1], b[0][0]], [b[1][1], b[1][0]]), vk.gamma, vk.delta, vk.beta];
+        if (!Bn128.product4IsOne(g1, g2)) return false;
+        emit Verified("Transaction successfully verified.");
+        return true;
+    }
+}
+)SOL";
+
+static std::string repr_hex(const uint8_t* le) {          // ff_ce `Display for FqRepr`: "0x" + 16 hex digits per limb, most significant first
+    static const char* d = "0123456789abcdef";
+    std::string s = "0x";
+    for (int i = 31; i >= 0; i--) { s.push_back(d[le[i] >> 4]); s.push_back(d[le[i] & 15]); }
+    return s;
+}
+static bool point_is_zero(const uint8_t* p, size_t n) { for (size_t i = 0; i < n; i++) if (p[i]) return false; return true; }
+static std::string sol_g1(const uint8_t* p) {               // ethereum.rs:221-226
+    if (point_is_zero(p, 64)) throw ZaError(ZA_ERR_UNEXPECTED_IDENTITY, "non-infinite point expected");
+    return repr_hex(p) + "," + repr_hex(p + 32);
+}
+static std::string sol_g2(const uint8_t* p) {               // ethereum.rs:227-238: [x.c1,x.c0],[y.c1,y.c0]
+    if (point_is_zero(p, 128)) throw ZaError(ZA_ERR_UNEXPECTED_IDENTITY, "non-infinite point expected");
+    return "[" + repr_hex(p + 32) + "," + repr_hex(p) + "],[" + repr_hex(p + 96) + "," + repr_hex(p + 64) + "]";
+}
+static std::string rust_debug_str(const char* s) {          // `{:?}` of a String
+    std::string o = "\"";
+    for (const unsigned char* c = (const unsigned char*)s; *c; c++) {
+        switch (*c) {
+        case '"': o += "\\\""; break;
+        case '\\': o += "\\\\"; break;
+        case '\n': o += "\\n"; break;
+        case '\r': o += "\\r"; break;
+        case '\t': o += "\\t"; break;
+        default:
+            if (*c < 0x20 || *c == 0x7f) { char b[16]; snprintf(b, sizeof b, "\\u{%x}", *c); o += b; }
+            else o.push_back((char)*c);
+        }
+    }
+    o += "\"";
+    return o;
+}
+static void replace_all(std::string& s, const std::string& what, const std::string& with) {      // str::replace
+    size_t pos = 0;
+    while ((pos = s.find(what, pos)) != std::string::npos) { s.replace(pos, what.size(), with); pos += with.size(); }
+}
+
+// generate_solidity (ethereum.rs:216-261).  contract_template == NULL: the built-in template.
+int za_vk_to_solidity(const uint8_t* vk, size_t n_ic, const char* const* input_names, size_t n_names, const char* contract_template, char* buf,
+                      size_t size, size_t* needed) {
+    if (!vk || !buf || (n_names && !input_names)) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    std::string c = contract_template ? contract_template : ZA_SOLIDITY_TEMPLATE;
+    // the same order of replacements as the reference: a replacement text never contains a later placeholder
+    replace_all(c, "<%vk_a%>", sol_g1(vk));
+    replace_all(c, "<%vk_b%>", sol_g2(vk + 128));
+    replace_all(c, "<%vk_gamma%>", sol_g2(vk + 256));
+    replace_all(c, "<%vk_delta%>", sol_g2(vk + 448));
+    replace_all(c, "<%vk_inputs_length%>", std::to_string(n_names));
+    std::string names = "[";
+    for (size_t i = 0; i < n_names; i++) { if (i) names += ", "; names += rust_debug_str(input_names[i]); }
+    names += "]";
+    replace_all(c, "<%vk_inputs%>", names);
+    replace_all(c, "<%vk_gammaABC_length%>", std::to_string(n_ic));
+    std::string pts;
+    for (size_t i = 0; i < n_ic; i++) {
+        if (i) pts += "\n";
+        pts += "vk.gammaABC[" + std::to_string(i) + "] = Pairing.G1Point(" + sol_g1(vk + 576 + 64 * i) + ");";
+    }
+    if (!contract_template) {                // the built-in template names the array and the point type differently
+        replace_all(pts, "vk.gammaABC[", "vk.ic[");
+        replace_all(pts, "Pairing.G1Point(", "Bn128.G1(");
+        replace_all(pts, "\n", "\n        ");
+    }
+    replace_all(c, "<%vk_gammaABC_pts%>", pts);
+    if (needed) *needed = c.size() + 1;
+    if (c.size() >= size) return fail(ZA_ERR_BUFFER_TOO_SMALL, "solidity text needs %zu bytes", c.size() + 1);
+    memcpy(buf, c.c_str(), c.size() + 1);
+    return ZA_OK;
+    ZA_CATCH
+}
+
 // helper::verify (helper.rs:149-158): JsonVerifyingKey + JsonProofAndInput -> verify_proof
 int za_verify_json(const char* vk_json, const char* proof_json, int* valid) {
     if (!vk_json || !proof_json || !valid) return fail(ZA_ERR_INVALID, "NULL argument");

@@ -532,6 +532,22 @@ def vk_to_json(vk, input_names=()):
     return buf.value.decode()
 
 
+def vk_to_solidity(vk, input_names=(), contract_template=None):
+    """generate_solidity (ethereum.rs:216-261).  contract_template=None: the library's own contract text."""
+    b, n_ic = vk_bytes(vk)
+    vb = np.frombuffer(b, np.uint8)
+    names = (ctypes.c_char_p * max(len(input_names), 1))(*[n.encode() for n in input_names])
+    tmpl = contract_template.encode() if contract_template is not None else None
+    need = ctypes.c_size_t(0)
+    probe = ctypes.create_string_buffer(1)
+    lib().za_vk_to_solidity(_p(vb), n_ic, names, len(input_names), tmpl, probe, 1, ctypes.byref(need))
+    if need.value == 0:
+        check(-2)
+    buf = ctypes.create_string_buffer(need.value)
+    check(lib().za_vk_to_solidity(_p(vb), n_ic, names, len(input_names), tmpl, buf, need.value, None))
+    return buf.value.decode()
+
+
 def verify(vk_json, proof_json):
     """helper::verify (helper.rs:149-158): both arguments are JSON text -> bool."""
     ok = ctypes.c_int(0)
