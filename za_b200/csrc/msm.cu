@@ -615,6 +615,272 @@ __global__ void __launch_bounds__(NT) __maxnreg__(sizeof(F) == sizeof(Fq) ? 128 
     }
 }
 
+// K5a' — the pair rounds over Fq2 with one Fq2 value split over a LANE PAIR (lane 2k holds c0, lane 2k + 1 holds c1).
+// The single-thread version above needs ~190-224 registers (8 warps per SM: latency bound, multiply pipe ~60 % busy,
+// 2.3 KB of local memory per thread).  Here every lane carries half of every value: the working set lives in shared
+// memory (12 slots of 32 bytes per lane, the layout of the G1 accumulation), the kernel fits 128 registers and four
+// CTAs per SM (16 warps), and the Fq2 product is convergent over the pair:
+//     lane 0:  c0 = a0 b0 + a1 (p - b1)        lane 1:  c1 = a0 b1 + a1 b0
+// i.e. both lanes run  x0 y0 + x1 y1  (two 512-bit products, one addition, ONE Montgomery reduction) on operands they
+// read from the pair's two slots; the squaring is one product per lane ((a0 + a1)(a0 - a1) and (2 a0) a1).  Per Fq2
+// product that is 4 wide products + 2 reductions (the three-product Karatsuba cannot be balanced over two lanes, and
+// the pipe is paid per warp instruction), the same count as round 1's three full products, but at twice the occupancy
+// and without argument marshalling or spills.
+#define LPK_NT 128
+enum { LV_I = 0, LV_PJ, LV_AX, LV_AY, LV_BX, LV_BY, LV_D, LV_NUM, LV_XS, LV_T, LV_PF, LV_SF, LV_COUNT };
+#define LPK_SM_BYTES (LV_COUNT * 32 * LPK_NT)
+static_assert(LPK_NT == ACC_SM_NT, "sm_ld / sm_st address the second half of a value ACC_SM_NT * 16 bytes further");
+static __device__ __forceinline__ void pair_sync() { __syncwarp(3u << (threadIdx.x & 30u)); }
+static __device__ __forceinline__ bool pair_all(bool v) {
+    const unsigned m = 3u << (threadIdx.x & 30u);
+    return __all_sync(m, v);
+}
+#if defined(__CUDA_ARCH__)
+// slot d = this lane's component of (slot a) * (slot b); a, b, d are the CALLING lane's slot addresses
+static __device__ __noinline__ void lp_mul_sm(uint32_t d, uint32_t a, uint32_t b) {
+    const uint32_t h = threadIdx.x & 1u;
+    const uint32_t a_c0 = a - h * 16u;
+    const Fq x0 = sm_ld(a_c0), x1 = sm_ld(a_c0 + 16u);
+    const Fq y0 = sm_ld(b);
+    Fq yo = sm_ld(h ? b - 16u : b + 16u);
+    {   // lane 0 multiplies a1 by -b1 = p - b1 (p itself when b1 = 0: the product is then a multiple of p)
+        uint32_t n[8];
+        n[0] = p_sub_cc(FqParams::mod(0), yo.v[0]);
+#pragma unroll
+        for (int i = 1; i < 7; i++) n[i] = p_subc_cc(FqParams::mod(i), yo.v[i]);
+        n[7] = p_subc(FqParams::mod(7), yo.v[7]);
+#pragma unroll
+        for (int i = 0; i < 8; i++) yo.v[i] = h ? yo.v[i] : n[i];
+    }
+    pair_sync();                                  // both lanes have read before either overwrites (d may be a or b)
+    uint32_t T[16], U[16];
+    u256_mul_wide(T, x0.v, y0.v);
+    u256_mul_wide(U, x1.v, yo.v);
+    T[0] = p_add_cc(T[0], U[0]);
+#pragma unroll
+    for (int i = 1; i < 15; i++) T[i] = p_addc_cc(T[i], U[i]);
+    T[15] = p_addc(T[15], U[15]);                 // x0 y0 + x1 y1 <= 2 p^2 < p 2^256
+    sm_st(d, fp_redc_wide<FqParams>(T));
+    pair_sync();
+}
+// slot d = this lane's component of (slot a)^2:  c0 = (a0 + a1)(a0 - a1),  c1 = (2 a0) a1
+static __device__ __noinline__ void lp_sqr_sm(uint32_t d, uint32_t a) {
+    const uint32_t h = threadIdx.x & 1u;
+    const uint32_t a_c0 = a - h * 16u;
+    const Fq a0 = sm_ld(a_c0), a1 = sm_ld(a_c0 + 16u);
+    Fq t;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.v[i] = h ? a0.v[i] : a1.v[i];
+    const Fq u = a0 + t;                          // lane 0: a0 + a1, lane 1: 2 a0
+    const Fq w = a0 - a1;
+    Fq v;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v.v[i] = h ? a1.v[i] : w.v[i];
+    pair_sync();
+    sm_st(d, fp_mul<FqParams>(u, v));
+    pair_sync();
+}
+#else
+static inline void lp_mul_sm(uint32_t, uint32_t, uint32_t) {}
+static inline void lp_sqr_sm(uint32_t, uint32_t) {}
+#endif
+static __device__ __forceinline__ Fq shfl_fq(const Fq& v, int src_lane) {
+    Fq r;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.v[k] = __shfl_sync(0xffffffffu, v.v[k], src_lane);
+    return r;
+}
+// component h of the point's x (which = 0) or y (which = 1) coordinate
+static __device__ __forceinline__ const Fq* lp_coord(const Affine<Fq2>* p, uint32_t ref, uint32_t which, uint32_t h) {
+    return reinterpret_cast<const Fq*>(p + (ref & 0x7fffffffu)) + 2 * which + h;
+}
+
+template <bool FIRST, int LP>
+__global__ void __launch_bounds__(LPK_NT, 4) msm_pair_round_g2lp_kernel(const Affine<Fq2>* __restrict__ pts, const uint32_t* __restrict__ entries,
+                                                                        const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out,
+                                                                        uint32_t nkeys, Affine<Fq2>* __restrict__ out) {
+    extern __shared__ uint4 lpk_sm[];
+    constexpr int FB = 2;
+    static_assert(LP % FB == 0, "LP must be a multiple of the forward batch");
+    const uint32_t n_out = off_out[nkeys];
+    const uint32_t tid = threadIdx.x, h = tid & 1u, lane = tid & 31u;
+    const uint64_t cta_first = (uint64_t)blockIdx.x * ((LPK_NT / 2) * LP);
+    if (cta_first + (uint64_t)((tid & ~31u) >> 1) * LP >= n_out) return;       // the whole warp is past the end
+    const uint64_t q0_64 = cta_first + (uint64_t)(tid >> 1) * LP;
+    const uint32_t q0 = (uint32_t)q0_64;
+    const uint32_t cnt = q0_64 < n_out ? (n_out - q0 < (uint32_t)LP ? n_out - q0 : (uint32_t)LP) : 0u;
+    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(lpk_sm) + tid * 16u;
+    auto var = [&](int v) { return sm0 + (uint32_t)v * (2 * LPK_NT * 16); };
+    const Fq one_h = h ? Fq::zero() : Fq::one();                               // this lane's component of 1
+    uint32_t ref0[LP], ref1[LP];
+    uint8_t flags[LP];
+    Fq pre[LP];
+    sm_st(var(LV_I), one_h);                                                    // running product of the differences
+    if (cnt) {
+        uint32_t lo = 0, hi = nkeys;
+        while (lo + 1 < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (off_out[mid] <= q0) lo = mid; else hi = mid;
+        }
+        uint32_t key = lo;
+        uint32_t obase = off_out[key], oend = off_out[key + 1], ibase = off_in[key], icnt = off_in[key + 1] - ibase;
+#pragma unroll 4
+        for (uint32_t j = 0; j < (uint32_t)LP; j++) {
+            uint32_t r0 = 0, r1 = 0xffffffffu;
+            if (j < cnt) {
+                const uint32_t q = q0 + j;
+                if (q == oend) {
+                    do { key++; } while (off_out[key + 1] <= q);
+                    obase = off_out[key]; oend = off_out[key + 1]; ibase = off_in[key]; icnt = off_in[key + 1] - ibase;
+                }
+                const uint32_t k = q - obase;
+                const uint32_t s0 = ibase + 2 * k;
+                r0 = FIRST ? entries[s0] : s0;
+                if (2 * k + 1 < icnt) r1 = FIRST ? entries[s0 + 1] : s0 + 1;
+            }
+            ref0[j] = r0; ref1[j] = r1;
+        }
+        // ---- forward: x differences, FB outputs' loads in flight at a time
+#pragma unroll 1
+        for (uint32_t j0 = 0; j0 < cnt; j0 += FB) {
+            Fq x0[FB], x1[FB];
+#pragma unroll
+            for (int u = 0; u < FB; u++) {
+                const uint32_t r0 = ref0[j0 + u], r1 = ref1[j0 + u];
+                x0[u] = ldg_vec(lp_coord(pts, r0, 0, h));
+                x1[u] = ldg_vec(lp_coord(pts, r1 == 0xffffffffu ? r0 : r1, 0, h));
+            }
+            if (j0 + FB < cnt) {
+#pragma unroll
+                for (int u = 0; u < FB; u++) {
+                    const uint32_t r0 = ref0[j0 + FB + u], r1 = ref1[j0 + FB + u];
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(lp_coord(pts, r0, 0, 0)));
+                    if (r1 != 0xffffffffu) asm volatile("prefetch.global.L1 [%0];" ::"l"(lp_coord(pts, r1, 0, 0)));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < FB; u++) {
+                const uint32_t j = j0 + u;
+                if (j >= cnt) break;
+                const uint32_t r0 = ref0[j], r1 = ref1[j];
+                uint32_t fl = PR_COPY0;
+                if (r1 != 0xffffffffu) {
+                    Fq d = x1[u] - x0[u];
+                    fl = PR_ADD;
+                    const bool dz = pair_all(d.is_zero()), x0z = pair_all(x0[u].is_zero()), x1z = pair_all(x1[u].is_zero());
+                    if (dz || x0z || x1z) {                                     // rare: look at the y coordinates
+                        Fq y0 = ldg_vec(lp_coord(pts, r0, 1, h)), y1 = ldg_vec(lp_coord(pts, r1, 1, h));
+                        if (r0 >> 31) y0 = -y0;
+                        if (r1 >> 31) y1 = -y1;
+                        const bool y0z = pair_all(y0.is_zero()), y1z = pair_all(y1.is_zero()), yeq = pair_all(y0 == y1);
+                        if (x0z && y0z) fl = PR_COPY1;
+                        else if (x1z && y1z) fl = PR_COPY0;
+                        else if (dz) {
+                            if (yeq && !y0z) { fl = PR_DBL; d = dbl(y0); }
+                            else fl = PR_INF;
+                        }
+                    }
+                    if (fl >= PR_ADD) {
+                        pre[j] = sm_ld(var(LV_I));
+                        sm_st(var(LV_D), d);
+                        pair_sync();
+                        lp_mul_sm(var(LV_I), var(LV_I), var(LV_D));
+                    }
+                }
+                flags[j] = (uint8_t)fl;
+            }
+        }
+    }
+    __syncwarp();
+    // ---- one inversion per warp over its 16 pairs: prefix and suffix products of the pair totals (shuffles by an even
+    // number of lanes keep the component), the warp product inverted once (every lane computes the same norm, so the
+    // binary-Euclid inverse stays convergent), 1 / total_pair = ginv * (product of the pairs before) * (... after)
+    {
+        const uint32_t pidx = lane >> 1;
+        sm_st(var(LV_PF), sm_ld(var(LV_I)));
+        sm_st(var(LV_SF), sm_ld(var(LV_I)));
+        __syncwarp();
+#pragma unroll 1
+        for (int d = 1; d < 16; d <<= 1) {
+            Fq up = shfl_up_vec(sm_ld(var(LV_PF)), 2 * d), dn = shfl_down_vec(sm_ld(var(LV_SF)), 2 * d);
+            if (pidx < (uint32_t)d) up = one_h;
+            if (pidx + d >= 16) dn = one_h;
+            sm_st(var(LV_T), up);
+            sm_st(var(LV_D), dn);
+            __syncwarp();
+            lp_mul_sm(var(LV_PF), var(LV_PF), var(LV_T));
+            lp_mul_sm(var(LV_SF), var(LV_SF), var(LV_D));
+        }
+        const Fq pf = sm_ld(var(LV_PF)), sf = sm_ld(var(LV_SF));
+        const Fq tot = shfl_fq(pf, 30 + (int)h);                               // this lane's component of the warp product
+        const Fq sq = fq_sqr_call(tot);
+        Fq oth;
+#pragma unroll
+        for (int k = 0; k < 8; k++) oth.v[k] = __shfl_xor_sync(0xffffffffu, sq.v[k], 1);
+        const Fq ninv = fq_inv_call(sq + oth);                                 // 1 / (t0^2 + t1^2)
+        Fq g = fq_mul_call(tot, ninv);
+        if (h) g = -g;                                                         // (t0 - t1 u) / norm
+        Fq e = shfl_up_vec(pf, 2), sfx = shfl_down_vec(sf, 2);
+        if (pidx == 0) e = one_h;
+        if (pidx == 15) sfx = one_h;
+        sm_st(var(LV_I), g); sm_st(var(LV_T), e); sm_st(var(LV_D), sfx);
+        __syncwarp();
+        lp_mul_sm(var(LV_I), var(LV_I), var(LV_T));
+        lp_mul_sm(var(LV_I), var(LV_I), var(LV_D));
+    }
+    // ---- backward
+    if (!cnt) return;
+    uint32_t nr0 = ref0[cnt - 1], nr1 = ref1[cnt - 1], nfl = flags[cnt - 1];
+    Fq npre = pre[cnt - 1];
+#pragma unroll 1
+    for (uint32_t j = cnt; j-- > 0;) {
+        const uint32_t r0 = nr0, r1 = nr1, fl = nfl;
+        const Fq pj = npre;
+        if (j) {                                   // the next output's operands and prefix product one iteration ahead
+            nr0 = ref0[j - 1]; nr1 = ref1[j - 1]; nfl = flags[j - 1];
+            npre = pre[j - 1];
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(lp_coord(pts, nr0, 0, 0)));
+            if (nr1 != 0xffffffffu) asm volatile("prefetch.global.L1 [%0];" ::"l"(lp_coord(pts, nr1, 0, 0)));
+        }
+        Fq rx, ry;
+        if (fl >= PR_ADD) {
+            Fq ax = ldg_vec(lp_coord(pts, r0, 0, h)), ay = ldg_vec(lp_coord(pts, r0, 1, h));
+            Fq bx = ldg_vec(lp_coord(pts, r1, 0, h)), by = ldg_vec(lp_coord(pts, r1, 1, h));
+            if (r0 >> 31) ay = -ay;
+            if (r1 >> 31) by = -by;
+            sm_st(var(LV_AX), ax); sm_st(var(LV_AY), ay);
+            sm_st(var(LV_PJ), pj);
+            if (fl == PR_DBL) {
+                pair_sync();
+                lp_sqr_sm(var(LV_T), var(LV_AX));
+                const Fq xx = sm_ld(var(LV_T));
+                sm_st(var(LV_D), dbl(ay)); sm_st(var(LV_NUM), dbl(xx) + xx); sm_st(var(LV_XS), dbl(ax));
+            } else {
+                sm_st(var(LV_D), bx - ax); sm_st(var(LV_NUM), by - ay); sm_st(var(LV_XS), ax + bx);
+            }
+            pair_sync();
+            lp_mul_sm(var(LV_PJ), var(LV_I), var(LV_PJ));          // 1 / d
+            lp_mul_sm(var(LV_I), var(LV_I), var(LV_D));
+            lp_mul_sm(var(LV_NUM), var(LV_NUM), var(LV_PJ));       // lambda
+            lp_sqr_sm(var(LV_T), var(LV_NUM));
+            rx = sm_ld(var(LV_T)) - sm_ld(var(LV_XS));
+            sm_st(var(LV_T), sm_ld(var(LV_AX)) - rx);
+            pair_sync();
+            lp_mul_sm(var(LV_T), var(LV_NUM), var(LV_T));
+            ry = sm_ld(var(LV_T)) - sm_ld(var(LV_AY));
+        } else if (fl == PR_INF) {
+            rx = Fq::zero(); ry = Fq::zero();
+        } else {
+            const uint32_t r = fl == PR_COPY1 ? r1 : r0;
+            rx = ldg_vec(lp_coord(pts, r, 0, h)); ry = ldg_vec(lp_coord(pts, r, 1, h));
+            if (r >> 31) ry = -ry;
+        }
+        Fq* o = reinterpret_cast<Fq*>(out + q0 + j);
+        st_vec(o + h, rx);
+        st_vec(o + 2 + h, ry);
+    }
+}
+
 // K5b: buckets that straddle chunk boundaries.  Element 0 of a chain is the tail partial of the chunk where
 // the bucket starts, element k the head partial of chunk + k.  Short chains (the common case) are folded
 // by one thread; long chains (one bucket holding a large share of all entries — witness vectors full of
@@ -1266,8 +1532,37 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
             msm_scan_ctas_kernel<<<1, 1024, 0, st>>>(d_pair_cta, nctas, nxt_off + nkeys);
             msm_scan_apply_kernel<<<nctas, 1024, 0, st>>>(cur_off, nkeys, d_pair_cta, nxt_off, nullptr, 1);
             cap = pair_cap[r];
+            bool lp_done = false;
+            if constexpr (sizeof(F) == sizeof(Fq2)) {
+                // Fq2 split over lane pairs (K5a'): 64 pairs per CTA, four CTAs per SM; LP outputs per pair, shorter runs
+                // when the round is small so that the grid still covers the SMs a few times
+                // MEASURED (profiles/r02_g2_lanepair.md): 8.48 ms against 7.75 ms for the single-thread rounds at 2^20 — the
+                // rounds are bound by their gathers, the per-warp inversion (19 % of the samples at 512 outputs per warp)
+                // and bookkeeping, not by occupancy, and the pair pays 4 wide products per Fq2 product where one thread
+                // pays 3.  Kept selectable (ZA_G2_LANEPAIR=1), off by default.
+                static const bool lanepair = getenv("ZA_G2_LANEPAIR") && atoi(getenv("ZA_G2_LANEPAIR")) != 0;
+                if (lanepair) {
+                    const uint64_t wave32 = (uint64_t)ctx->sm_count * 4 * (LPK_NT / 2) * 32;
+                    static const int lp_max = getenv("ZA_G2_LP_MAX") ? atoi(getenv("ZA_G2_LP_MAX")) : 32;
+                    int lp = cap >= 6 * wave32 ? 64 : cap >= 3 * wave32 ? 32 : cap >= wave32 ? 16 : 8;
+                    if (lp > lp_max) lp = lp_max;
+                    const unsigned grid = nblk(cap, (LPK_NT / 2) * lp);
+                    const Affine<Fq2>* in_pts = cur_pts;
+                    Affine<Fq2>* out_pts = nxt_pts;
+#define ZA_LPK_LAUNCH(FIRST_, LP_)                                                                                                         \
+    do {                                                                                                                                   \
+        ZA_CUDA(cudaFuncSetAttribute(msm_pair_round_g2lp_kernel<FIRST_, LP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, LPK_SM_BYTES)); \
+        msm_pair_round_g2lp_kernel<FIRST_, LP_><<<grid, LPK_NT, LPK_SM_BYTES, st>>>(in_pts, r == 0 ? d_entries : nullptr, cur_off, nxt_off, nkeys, out_pts); \
+    } while (0)
+                    if (r == 0) { if (lp == 64) ZA_LPK_LAUNCH(true, 64); else if (lp == 32) ZA_LPK_LAUNCH(true, 32); else if (lp == 16) ZA_LPK_LAUNCH(true, 16); else ZA_LPK_LAUNCH(true, 8); }
+                    else { if (lp == 64) ZA_LPK_LAUNCH(false, 64); else if (lp == 32) ZA_LPK_LAUNCH(false, 32); else if (lp == 16) ZA_LPK_LAUNCH(false, 16); else ZA_LPK_LAUNCH(false, 8); }
+#undef ZA_LPK_LAUNCH
+                    lp_done = true;
+                }
+            }
             // small rounds: shorter per-thread runs so that the grid still fills the SMs
-            if (pair_lp == 16 || cap < (uint64_t)ctx->sm_count * 4 * PAIR_NT * 32) {
+            if (lp_done) {
+            } else if (pair_lp == 16 || cap < (uint64_t)ctx->sm_count * 4 * PAIR_NT * 32) {
                 const unsigned grid = nblk(cap, PAIR_NT * 16);
                 if (r == 0) msm_pair_round_kernel<F, true, PAIR_NT, 16><<<grid, PAIR_NT, 0, st>>>(cur_pts, d_entries, cur_off, nxt_off, nkeys, nxt_pts);
                 else msm_pair_round_kernel<F, false, PAIR_NT, 16><<<grid, PAIR_NT, 0, st>>>(cur_pts, nullptr, cur_off, nxt_off, nkeys, nxt_pts);
