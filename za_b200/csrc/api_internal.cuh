@@ -15,10 +15,12 @@ void h_poly_checkpointed(Ctx* ctx, Fr* a, Fr* b, Fr* c, int log_m, uint8_t* ck);
 // msm.cu
 template <class F> uint32_t bases_import(Ctx* ctx, void* d_pts, size_t n);
 template <class F> XYZZ<F> msm_run(Ctx* ctx, const Affine<F>* d_bases, const uint32_t* d_scalars, size_t n, bool has_infinity);
+// a further query sorted / accumulated / reduced together with the first one (fixed-base table of the same window layout)
+struct MsmPart { const void* table; const uint32_t* scalars; size_t n; };
 template <class F> void msm_enqueue(Ctx* ctx, int slot, const Affine<F>* d_bases, const uint32_t* d_scalars, size_t n, bool has_infinity, int share_sort,
-                                    const Affine<F>* d_table, int tab_c, int tab_W);
+                                    const Affine<F>* d_table, int tab_c, int tab_W, const MsmPart* more = nullptr, int n_more = 0);
 template <class F> void bases_table_build(Ctx* ctx, const Affine<F>* d_pts, size_t n, int c, int W, Affine<F>* d_table);
-template <class F> XYZZ<F> msm_finish(Ctx* ctx, int slot);
+template <class F> XYZZ<F> msm_finish(Ctx* ctx, int slot, XYZZ<F>* parts_out = nullptr);
 void msm_abort(Ctx* ctx);
 int msm_window_bits(size_t n);
 template <class F> void bases_generate(Ctx* ctx, Affine<F>* d_out, size_t n, uint64_t first, const Affine<F>& G);

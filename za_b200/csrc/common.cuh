@@ -96,6 +96,8 @@ struct MsmSlot {
     uint32_t sort_users = 0;             // slots that reuse this slot's digit sort since its last enqueue
     int kind = 0;                        // 0 empty, 1 naive (small), 2 bucket method
     int c = 0, W = 0, warps = 0, acc_cat = 0;
+    int nparts = 1;                      // queries sorted and accumulated together in this slot (K4')
+    bool single = false;                 // fixed-base table mode: one bucket space per query
     uint32_t nkeys = 0, Lc = 0, nchunks = 0;
     size_t n = 0;
     uint32_t* d_offsets = nullptr;       // sort result (may be shared by a later multiexp over the same scalars)
@@ -123,6 +125,7 @@ struct Ctx {
     uint64_t launches = 0;              // kernels launched through this context (bench: gpu_launches)
     cudaEvent_t dbg_t0 = nullptr;       // ZA_DEBUG_TIMELINE: start of the current proof on this device
     bool dbg_t0_valid = false;
+    bool witness_merged = false;        // the last prove enqueued B (G1), L and A as one multiexp in slot 3
     bool ntt_attr_set = false;          // the > 48 KiB shared-memory attribute of the NTT kernels is set on this context's device
     // optional per-kernel-class timing with CUDA events on `stream` (bench.py roofline numbers)
     bool profile = false;

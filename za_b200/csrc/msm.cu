@@ -104,7 +104,8 @@ static __device__ __forceinline__ uint32_t warp_cursor_take(uint32_t* cursors, u
 
 // K3 + K4a: per-bucket entry counts
 // `single` != 0: fixed-base table mode — one bucket space for all windows, entry = (i * W + w) | sign.
-__global__ void msm_digits_hist_kernel(const uint32_t* __restrict__ scalars, size_t n, int c, int W, uint32_t B, uint32_t* counts, int single) {
+// `key_base`: first key of this part's bucket space when several queries are sorted into one key range (K4').
+__global__ void msm_digits_hist_kernel(const uint32_t* __restrict__ scalars, size_t n, int c, int W, uint32_t B, uint32_t* counts, int single, uint32_t key_base) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -115,14 +116,14 @@ __global__ void msm_digits_hist_kernel(const uint32_t* __restrict__ scalars, siz
     uint32_t carry = 0;
     for (int w = 0; w < W; w++) {
         int d = next_digit(s, w, c, carry);
-        if (d != 0) warp_count_add(counts, (single ? 0u : (uint32_t)w * B) + (uint32_t)(d < 0 ? -d : d) - 1);
+        if (d != 0) warp_count_add(counts, key_base + (single ? 0u : (uint32_t)w * B) + (uint32_t)(d < 0 ? -d : d) - 1);
     }
 }
 
 // K4c: scatter (point index | sign << 31) into bucket order.  Order inside a bucket is arbitrary;
 // the bucket sum is not (group addition is commutative and exact).
 __global__ void msm_digits_scatter_kernel(const uint32_t* __restrict__ scalars, size_t n, int c, int W, uint32_t B, uint32_t* cursors,
-                                          uint32_t* entries, int single) {
+                                          uint32_t* entries, int single, uint32_t key_base) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -134,7 +135,7 @@ __global__ void msm_digits_scatter_kernel(const uint32_t* __restrict__ scalars, 
     for (int w = 0; w < W; w++) {
         int d = next_digit(s, w, c, carry);
         if (d != 0) {
-            uint32_t pos = warp_cursor_take(cursors, (single ? 0u : (uint32_t)w * B) + (uint32_t)(d < 0 ? -d : d) - 1);
+            uint32_t pos = warp_cursor_take(cursors, key_base + (single ? 0u : (uint32_t)w * B) + (uint32_t)(d < 0 ? -d : d) - 1);
             entries[pos] = (single ? (uint32_t)i * (uint32_t)W + (uint32_t)w : (uint32_t)i) | (d < 0 ? 0x80000000u : 0u);
         }
     }
@@ -295,8 +296,16 @@ static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.asyn
 template <int N>
 static __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// K4' — several queries in ONE sort / accumulation / reduction: part p owns the keys [p << nb, (p + 1) << nb) (its own
+// bucket space) and its entries index its own fixed-base table.  The witness multiexps of a proof (B in G1, L, A) run
+// this way: one digit sort instead of three, one accumulation launch, one reduction chain.
+struct AccTabs {
+    const Affine<Fq>* tab[4];
+    uint32_t nb;          // log2 of the keys per part (31 when there is a single part)
+    uint32_t nparts;
+};
 template <bool DIRECT>
-__global__ void __launch_bounds__(ACC_SM_NT, 4) msm_accumulate_g1_sm_kernel(const Affine<Fq>* __restrict__ bases, const uint32_t* __restrict__ entries,
+__global__ void __launch_bounds__(ACC_SM_NT, 4) msm_accumulate_g1_sm_kernel(const AccTabs tabs, const uint32_t* __restrict__ entries,
                                                                              const uint32_t* __restrict__ offsets, uint32_t nkeys, uint32_t Lc,
                                                                              XYZZ<Fq>* bucket_sums, XYZZ<Fq>* part_head, XYZZ<Fq>* part_tail,
                                                                              uint32_t* tail_owner_key) {
@@ -318,21 +327,31 @@ __global__ void __launch_bounds__(ACC_SM_NT, 4) msm_accumulate_g1_sm_kernel(cons
     bool head_open = offsets[key] < start;
     uint32_t bend = offsets[key + 1];
     bool acc_inf = true;
-    auto fetch = [&](uint32_t e, uint32_t buf) {     // point e -> point buffer `buf` (x: 2 chunks, y: 2 chunks)
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(bases + (e & 0x7fffffffu));
+    const uint32_t nb = tabs.nb;
+    uint32_t part = tabs.nparts > 1 ? key >> nb : 0u;
+    const Affine<Fq>* bases = tabs.tab[part];
+    uint32_t part_end = tabs.nparts > 1 ? offsets[(part + 1) << nb] : 0xffffffffu;      // first entry of the next part
+    auto fetch = [&](uint32_t e, uint32_t buf, const Affine<Fq>* from) {     // point e -> point buffer `buf` (x: 2 chunks, y: 2 chunks)
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(from + (e & 0x7fffffffu));
         const uint32_t px = var(AV_PX0 + 2 * (int)buf), py = var(AV_PY0 + 2 * (int)buf);
         cp_async16_sm(px, src); cp_async16_sm(px + ACC_SM_NT * 16, src + 16);
         cp_async16_sm(py, src + 32); cp_async16_sm(py + ACC_SM_NT * 16, src + 48);
     };
     uint32_t e = DIRECT ? start : entries[start];
-    fetch(e, start & 1u);
+    fetch(e, start & 1u, bases);
     cp_async_commit();
     for (uint32_t pos = start; pos < end; pos++) {
         const uint32_t e_cur = e;
         const uint32_t buf = pos & 1u;
         if (pos + 1 < end) {                         // the next point travels while this one is added
             e = DIRECT ? pos + 1 : entries[pos + 1];
-            fetch(e, buf ^ 1u);
+            const Affine<Fq>* from = bases;
+            if (pos + 1 >= part_end) {               // it belongs to a later part (rare: twice per launch)
+                uint32_t p2 = part + 1;
+                while (p2 + 1 < tabs.nparts && offsets[(p2 + 1) << nb] <= pos + 1) p2++;
+                from = tabs.tab[p2];
+            }
+            fetch(e, buf ^ 1u, from);
         }
         cp_async_commit();
         cp_async_wait<1>();
@@ -394,6 +413,11 @@ __global__ void __launch_bounds__(ACC_SM_NT, 4) msm_accumulate_g1_sm_kernel(cons
             if (nxt < end) {
                 do { key++; } while (offsets[key + 1] <= nxt);
                 bend = offsets[key + 1];
+                if (tabs.nparts > 1 && (key >> nb) != part) {
+                    part = key >> nb;
+                    bases = tabs.tab[part];
+                    part_end = offsets[(part + 1) << nb];
+                }
             }
         }
     }
@@ -1326,8 +1350,11 @@ template uint32_t bases_import<Fq2>(Ctx*, void*, size_t);
 // msm_finish waits for the slot and does the window combination on the host.
 template <class F>
 void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t* d_scalars, size_t n, bool has_infinity, int share_sort,
-                 const Affine<F>* d_table, int tab_c, int tab_W) {
+                 const Affine<F>* d_table, int tab_c, int tab_W, const MsmPart* more, int n_more) {
     MsmSlot& sl = ctx->slots[slot_id];
+    if (n_more < 0 || n_more > 3 || (n_more && (!more || !d_table || sizeof(F) != sizeof(Fq) || n <= 64)))
+        throw ZaError(ZA_ERR_INVALID, "internal: several queries in one multiexp need G1 fixed-base tables");
+    const int nparts = 1 + n_more;
     if (!sl.side) {
         int lo_prio = 0, hi_prio = 0;
         ZA_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
@@ -1335,7 +1362,7 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
     }
     cudaStream_t st = ctx->stream, side = sl.side;
     if (sl.busy) throw ZaError(ZA_ERR_INVALID, "msm slot enqueued twice without msm_finish");
-    sl.kind = 0; sl.n = n;
+    sl.kind = 0; sl.n = n; sl.nparts = nparts; sl.single = false;
     if (n == 0) { sl.busy = true; return; }
     // this slot's buffers (and its sort, if another slot borrowed it) may still be read by side-stream work
     if (sl.done_valid) ZA_CUDA(cudaStreamWaitEvent(st, sl.done, 0));
@@ -1387,9 +1414,14 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
     const int c = single ? tab_c : msm_window_bits(n);
     const int W = single ? tab_W : (255 + c - 1) / c;
     const uint32_t B = 1u << (c - 1);
-    const int Wr = single ? 1 : W;                  // bucket spaces to reduce
+    const int Wr = single ? nparts : W;             // bucket spaces to reduce
     const uint32_t nkeys = (uint32_t)Wr * B;
-    const uint64_t Emax = (uint64_t)n * W;
+    uint64_t Emax = (uint64_t)n * W;
+    for (int p = 0; p < n_more; p++) {
+        if (more[p].n >= ((size_t)1 << 27)) throw ZaError(ZA_ERR_INVALID, "multiexp of 2^27 or more points is not supported");
+        Emax += (uint64_t)more[p].n * W;
+    }
+    sl.single = single;
     if (single) d_bases = d_table;
     if (Emax >= 0xffffffffull) throw ZaError(ZA_ERR_INVALID, "multiexp too large for 32-bit entry offsets");
     // batched-affine pair rounds before the XYZZ accumulation: worth it while buckets hold several points
@@ -1405,6 +1437,7 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
         if (sizeof(F) == sizeof(Fq2)) rounds = load >= 12 ? 4 : load >= 6 ? 3 : load >= 3 ? 1 : 0;
         if (Emax < (1u << 16)) rounds = 0;
         if (const char* e = getenv("ZA_MSM_ROUNDS")) { int v = atoi(e); if (v >= 0 && v <= PAIR_MAX_ROUNDS) rounds = v; }
+        if (nparts > 1) rounds = 0;
     }
     sl.rounds = rounds;
     int pair_lp = PAIR_LP;
@@ -1432,7 +1465,9 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
     uint32_t* d_entries;
     if (share_sort >= 0) {
         const MsmSlot& src = ctx->slots[share_sort];
-        if (src.kind != 2 || src.n != n || src.c != c || src.W != Wr) throw ZaError(ZA_ERR_INVALID, "msm sort sharing needs an identical scalar vector and window layout");
+        // the borrowed sort may cover several parts: this multiexp runs over its FIRST part (keys [0, B), entries from 0)
+        if (src.kind != 2 || src.n != n || src.c != c || src.single != single || (!single && src.W != Wr) || nparts != 1)
+            throw ZaError(ZA_ERR_INVALID, "msm sort sharing needs an identical scalar vector and window layout");
         d_offsets = src.d_offsets;
         d_entries = src.d_entries;
         ctx->slots[share_sort].sort_users |= 1u << slot_id;
@@ -1508,12 +1543,16 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
     if (share_sort < 0) {
         ZA_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nkeys * 4, st));
         ProfScope prof(ctx, PROF_MSM_SORT, (double)n);
-        msm_digits_hist_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_counts, single ? 1 : 0);
+        msm_digits_hist_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_counts, single ? 1 : 0, 0u);
+        for (int p = 0; p < n_more; p++)
+            if (more[p].n) msm_digits_hist_kernel<<<nblk(more[p].n, 256), 256, 0, st>>>(more[p].scalars, more[p].n, c, W, B, d_counts, 1, (uint32_t)(p + 1) * B);
         msm_scan_totals_kernel<<<nctas, 1024, 0, st>>>(d_counts, nkeys, d_cta, 0);
         msm_scan_ctas_kernel<<<1, 1024, 0, st>>>(d_cta, nctas, d_offsets + nkeys);
         msm_scan_apply_kernel<<<nctas, 1024, 0, st>>>(d_counts, nkeys, d_cta, d_offsets, d_cursors, 0);
-        msm_digits_scatter_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_cursors, d_entries, single ? 1 : 0);
-        ctx->launches += 5;
+        msm_digits_scatter_kernel<<<nblk(n, 256), 256, 0, st>>>(d_scalars, n, c, W, B, d_cursors, d_entries, single ? 1 : 0, 0u);
+        for (int p = 0; p < n_more; p++)
+            if (more[p].n) msm_digits_scatter_kernel<<<nblk(more[p].n, 256), 256, 0, st>>>(more[p].scalars, more[p].n, c, W, B, d_cursors, d_entries, 1, (uint32_t)(p + 1) * B);
+        ctx->launches += 5 + 2 * n_more;
         if (!sl.sort_ev) ZA_CUDA(cudaEventCreateWithFlags(&sl.sort_ev, cudaEventDisableTiming));
         ZA_CUDA(cudaEventRecord(sl.sort_ev, st));          // a multiexp that shares this sort from another stream waits for it
     } else if (ctx->slots[share_sort].sort_ev) {
@@ -1580,13 +1619,18 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
         static const bool acc_sm = !(getenv("ZA_MSM_ACC_SM") && atoi(getenv("ZA_MSM_ACC_SM")) == 0);
         bool launched = false;
         if constexpr (sizeof(F) == sizeof(Fq)) {
-            if (acc_sm) {
+            if (acc_sm || nparts > 1) {
+                AccTabs tabs;
+                tabs.tab[0] = rounds ? cur_pts : d_bases;
+                for (int p = 0; p < 3; p++) tabs.tab[p + 1] = p < n_more ? reinterpret_cast<const Affine<Fq>*>(more[p].table) : nullptr;
+                tabs.nparts = (uint32_t)nparts;
+                tabs.nb = nparts > 1 ? (uint32_t)(c - 1) : 31u;
                 if (rounds) {
                     ZA_CUDA(cudaFuncSetAttribute(msm_accumulate_g1_sm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACC_SM_BYTES));
-                    msm_accumulate_g1_sm_kernel<true><<<nblk(nchunks, ACC_SM_NT), ACC_SM_NT, ACC_SM_BYTES, st>>>(cur_pts, nullptr, cur_off, nkeys, Lc, d_buckets, d_head, d_tail, d_owner);
+                    msm_accumulate_g1_sm_kernel<true><<<nblk(nchunks, ACC_SM_NT), ACC_SM_NT, ACC_SM_BYTES, st>>>(tabs, nullptr, cur_off, nkeys, Lc, d_buckets, d_head, d_tail, d_owner);
                 } else {
                     ZA_CUDA(cudaFuncSetAttribute(msm_accumulate_g1_sm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACC_SM_BYTES));
-                    msm_accumulate_g1_sm_kernel<false><<<nblk(nchunks, ACC_SM_NT), ACC_SM_NT, ACC_SM_BYTES, st>>>(d_bases, d_entries, d_offsets, nkeys, Lc, d_buckets, d_head, d_tail, d_owner);
+                    msm_accumulate_g1_sm_kernel<false><<<nblk(nchunks, ACC_SM_NT), ACC_SM_NT, ACC_SM_BYTES, st>>>(tabs, d_entries, d_offsets, nkeys, Lc, d_buckets, d_head, d_tail, d_owner);
                 }
                 launched = true;
             }
@@ -1703,15 +1747,18 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
     sl.done_valid = true;
     sl.busy = true;
 }
-template void msm_enqueue<Fq>(Ctx*, int, const Affine<Fq>*, const uint32_t*, size_t, bool, int, const Affine<Fq>*, int, int);
-template void msm_enqueue<Fq2>(Ctx*, int, const Affine<Fq2>*, const uint32_t*, size_t, bool, int, const Affine<Fq2>*, int, int);
+template void msm_enqueue<Fq>(Ctx*, int, const Affine<Fq>*, const uint32_t*, size_t, bool, int, const Affine<Fq>*, int, int, const MsmPart*, int);
+template void msm_enqueue<Fq2>(Ctx*, int, const Affine<Fq2>*, const uint32_t*, size_t, bool, int, const Affine<Fq2>*, int, int, const MsmPart*, int);
 
+// parts_out != nullptr: the multiexp covered several queries (K4'); their sums go to parts_out[0 .. nparts), the return
+// value is the first one
 template <class F>
-XYZZ<F> msm_finish(Ctx* ctx, int slot_id) {
+XYZZ<F> msm_finish(Ctx* ctx, int slot_id, XYZZ<F>* parts_out) {
     MsmSlot& sl = ctx->slots[slot_id];
     XYZZ<F> result = XYZZ<F>::inf();
     if (!sl.busy) throw ZaError(ZA_ERR_INVALID, "msm_finish on an idle slot");
     sl.busy = false;
+    if ((sl.nparts > 1) != (parts_out != nullptr)) throw ZaError(ZA_ERR_INVALID, "internal: msm_finish and msm_enqueue disagree about the number of queries");
     if (sl.kind == 0) return result;
     ZA_CUDA(cudaEventSynchronize(sl.done));
     const XYZZ<F>* win = reinterpret_cast<const XYZZ<F>*>((const uint8_t*)sl.host_win + 64);
@@ -1751,6 +1798,11 @@ XYZZ<F> msm_finish(Ctx* ctx, int slot_id) {
         }
         win = spaces.data();
     }
+    if (parts_out) {
+        if (sl.red_mode != 1) throw ZaError(ZA_ERR_INVALID, "internal: several queries need the row / column reduction");
+        for (int p = 0; p < sl.nparts; p++) parts_out[p] = win[p];
+        return win[0];
+    }
     // window combination on the host: result = sum_w 2^(c w) S_w   (bellman: `higher.double()` x c, then add)
     for (int w = sl.W - 1; w >= 0; w--) {
         for (int k = 0; k < sl.c; k++) result = xyzz_dbl<F>(result);
@@ -1758,8 +1810,8 @@ XYZZ<F> msm_finish(Ctx* ctx, int slot_id) {
     }
     return result;
 }
-template XYZZ<Fq> msm_finish<Fq>(Ctx*, int);
-template XYZZ<Fq2> msm_finish<Fq2>(Ctx*, int);
+template XYZZ<Fq> msm_finish<Fq>(Ctx*, int, XYZZ<Fq>*);
+template XYZZ<Fq2> msm_finish<Fq2>(Ctx*, int, XYZZ<Fq2>*);
 
 // After a failed enqueue or collect: wait for whatever is in flight on this context and return every slot to idle, so
 // that the next call on the context starts clean (a slot left busy would refuse every later multiexp).

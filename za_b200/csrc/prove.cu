@@ -65,15 +65,17 @@ static int table_window_bits(size_t n, size_t point_bytes) {
     // measured on B200 (scratch/sweep_c.py): 2^16 -> 16, 2^18 -> 17, 2^20 and up -> 20
     int c = lg >= 20 ? 20 : lg >= 18 ? 17 : lg >= 15 ? 16 : lg + 1;
     size_t W = (255 + c - 1) / c;
-    if (n * W * point_bytes > ((size_t)24 << 30)) return 0;     // keep one query's table under 24 GiB
+    if (n * W * point_bytes > ((size_t)24 << 30)) return 0;     // keep one query's table under 24 GiB (TABLE_CAP_BYTES)
     return c;
 }
-// Build the table for bases [lo, lo + n) (default: the whole array); the window size follows n.
-static void bases_build_table(Ctx* ctx, Bases* b, size_t lo = 0, size_t n = (size_t)-1) {
+static const size_t TABLE_CAP_BYTES = (size_t)24 << 30;
+// Build the table for bases [lo, lo + n) (default: the whole array); the window size follows n unless `c_forced` > 0.
+static void bases_build_table(Ctx* ctx, Bases* b, size_t lo = 0, size_t n = (size_t)-1, int c_forced = 0) {
     if (n == (size_t)-1) n = b->n - lo;
     const size_t pb = b->group == 1 ? sizeof(G1Affine) : sizeof(G2Affine);
     b->table.release(); b->tab_c = 0; b->tab_W = 0; b->tab_lo = 0; b->tab_n = 0;
-    const int c = table_window_bits(n, pb);
+    int c = table_window_bits(n, pb);
+    if (c_forced > 0 && n > 64 && n * (size_t)((255 + c_forced - 1) / c_forced) * pb <= TABLE_CAP_BYTES) c = c_forced;
     if (!c || b->has_infinity) return;
     const int W = (255 + c - 1) / c;
     b->table.alloc(n * (size_t)W * pb);
@@ -81,6 +83,20 @@ static void bases_build_table(Ctx* ctx, Bases* b, size_t lo = 0, size_t n = (siz
     else bases_table_build<Fq2>(ctx, b->pts.as<G2Affine>() + lo, n, c, W, b->table.as<G2Affine>());
     b->tab_c = c; b->tab_W = W; b->tab_lo = lo; b->tab_n = n;
 }
+// Tables of the four witness queries (L, A, B in G1, B in G2) over the given ranges.  When the ranges are of similar
+// size the window is chosen JOINTLY (from the largest), so that B (G1), L and A can run as one multiexp with three bucket
+// spaces (K4') and the two B multiexps can share a sort; ranges more than 4x apart keep their own windows (a small query
+// should not pay for 2^19 buckets).
+static void pk_build_witness_tables(Ctx* ctx, Pk* pk, const size_t* lo, const size_t* n) {      // order: l, a, b
+    Bases* q[3] = {pk->l.get(), pk->a.get(), pk->b_g1.get()};
+    size_t nmax = 0, nmin = (size_t)-1;
+    for (int i = 0; i < 3; i++) { nmax = std::max(nmax, n[i]); nmin = std::min(nmin, n[i]); }
+    int joint = 0;
+    if (nmin > 64 && nmin * 4 >= nmax && !getenv("ZA_MSM_TABLE")) joint = table_window_bits(nmax, sizeof(G1Affine));
+    for (int i = 0; i < 3; i++) bases_build_table(ctx, q[i], lo[i], n[i], joint);
+    bases_build_table(ctx, pk->b_g2.get(), lo[2], n[2], joint);
+}
+
 template <class F>
 static const Affine<F>* table_for(const Bases* b, size_t offset, size_t n) {
     if (!b->tab_c || n <= 64 || offset < b->tab_lo || offset + n > b->tab_lo + b->tab_n) return nullptr;
@@ -247,7 +263,6 @@ static std::unique_ptr<Bases> read_query(Ctx* ctx, Reader& r, int group, bool ch
     // Parameters::read rejects points at infinity in every query
     std::unique_ptr<Bases> b = bases_from_le(ctx, group, le.data(), n, false, what);
     if (checked && group == 2) g2_subgroup_check(ctx, b.get(), what);
-    bases_build_table(ctx, b.get());
     return b;
 }
 
@@ -294,6 +309,9 @@ static std::unique_ptr<Pk> pk_load(Ctx* ctx, const uint8_t* data, size_t len, bo
     pk->a = read_query(ctx, r, 1, checked, "a query");
     pk->b_g1 = read_query(ctx, r, 1, checked, "b_g1 query");
     pk->b_g2 = read_query(ctx, r, 2, checked, "b_g2 query");
+    bases_build_table(ctx, pk->h.get());
+    const size_t lo[3] = {0, 0, 0}, n[3] = {pk->l->n, pk->a->n, pk->b_g1->n};
+    pk_build_witness_tables(ctx, pk.get(), lo, n);
     return pk;
 }
 
@@ -603,6 +621,27 @@ static void prove_msms_enqueue(Ctx* ctx, const Pk* pk, const Circuit* c, const u
             ZA_CUDA(cudaEventRecord(ctx->g2_fork, main_st));            // the B scalars are gathered
             ZA_CUDA(cudaStreamWaitEvent(ctx->g2_stream, ctx->g2_fork, 0));
         }
+        // K4': B (G1), L and A as ONE multiexp with three bucket spaces — one digit sort, one accumulation launch, one
+        // reduction chain instead of three of each — when all three ranges have fixed-base tables of the same window layout
+        // (pk_build_tables chooses the window jointly for exactly that reason).  ZA_MSM_MERGE=0: three multiexps as before.
+        static const bool merge_on = !(getenv("ZA_MSM_MERGE") && atoi(getenv("ZA_MSM_MERGE")) == 0) && !(getenv("ZA_MSM_ACC_SM") && atoi(getenv("ZA_MSM_ACC_SM")) == 0);
+        size_t l_lo, l_hi, a_lo, a_hi;
+        share_weighted(na, rank, world, w0, l_lo, l_hi);
+        share_weighted(c->a_cat_total, rank, world, w0, a_lo, a_hi);
+        const Affine<Fq>* tb = table_for<Fq>(pk->b_g1.get(), lo, hi - lo);
+        const Affine<Fq>* tl = table_for<Fq>(pk->l.get(), l_lo, l_hi - l_lo);
+        const Affine<Fq>* ta = table_for<Fq>(pk->a.get(), a_lo, a_hi - a_lo);
+        ctx->witness_merged = merge_on && tb && tl && ta && pk->b_g1->tab_c == pk->l->tab_c && pk->l->tab_c == pk->a->tab_c &&
+                              pk->b_g1->tab_W == pk->l->tab_W && pk->l->tab_W == pk->a->tab_W;
+        if (ctx->witness_merged) {
+            const uint32_t* sa = gather_range(ctx, d_wit, c->a_cat_idx, c->a_cat_total, a_lo, a_hi, ctx->scratch[12]);
+            MsmPart more[2] = {{tl, (const uint32_t*)(d_aux + l_lo * 32), l_hi - l_lo}, {ta, sa + a_lo * 8, a_hi - a_lo}};
+            if (!g2_inline) {                                              // the fork must lie behind the A gather as well
+                ZA_CUDA(cudaEventRecord(ctx->g2_fork, main_st));
+                ZA_CUDA(cudaStreamWaitEvent(ctx->g2_stream, ctx->g2_fork, 0));
+            }
+            msm_enqueue<Fq>(ctx, 3, pk->b_g1->pts.as<G1Affine>() + lo, sb + lo * 8, hi - lo, false, -1, tb, pk->b_g1->tab_c, pk->b_g1->tab_W, more, 2);
+        } else
         multiexp_enqueue<Fq>(ctx, 3, pk->b_g1.get(), lo, sb + lo * 8, hi - lo);
         // The two B multiexps run over the same exponents and share one digit sort — but only if both resolve to the
         // same bucket layout: with a fixed-base table on one side only (the G2 table is twice the size and may be over
@@ -621,7 +660,7 @@ static void prove_msms_enqueue(Ctx* ctx, const Pk* pk, const Circuit* c, const u
         share(m - 1, rank, world, lo, hi);
         multiexp_enqueue<Fq>(ctx, 0, pk->h.get(), lo, (const uint32_t*)(d_h + lo), hi - lo);
     }
-    if (which & MSM_WITNESS) {
+    if ((which & MSM_WITNESS) && !ctx->witness_merged) {
         share_weighted(na, rank, world, w0, lo, hi);
         multiexp_enqueue<Fq>(ctx, 1, pk->l.get(), lo, (const uint32_t*)(d_aux + lo * 32), hi - lo);
         share_weighted(c->a_cat_total, rank, world, w0, lo, hi);
@@ -636,6 +675,14 @@ static void prove_msms_enqueue(Ctx* ctx, const Pk* pk, const Circuit* c, const u
 // second half of prove_msms: wait for the five multiexps in completion order and combine their windows
 static void prove_msms_collect(Ctx* ctx, Partials& out) {
     out = partials_zero();
+    if (ctx->witness_merged && ctx->slots[3].busy && ctx->slots[3].nparts == 3) {
+        G1XYZZ parts[3];
+        msm_finish<Fq>(ctx, 3, parts);
+        out.g1[5] = parts[0]; out.g1[1] = parts[1]; out.g1[3] = parts[2];      // B, L, A
+        out.g2[1] = msm_finish<Fq2>(ctx, 4);
+        out.g1[0] = msm_finish<Fq>(ctx, 0);
+        return;
+    }
     out.g1[5] = msm_finish<Fq>(ctx, 3);      // b1_inputs + b1_aux
     out.g2[1] = msm_finish<Fq2>(ctx, 4);     // b2_inputs + b2_aux
     out.g1[0] = msm_finish<Fq>(ctx, 0);
@@ -1376,7 +1423,9 @@ int za_pk_synthetic(za_ctx* ctx, const uint32_t* counts, za_pk** out) {
         pk->a = bases_generated(c, 1, counts[3], ((uint64_t)3 << 32) + 1);
         pk->b_g1 = bases_generated(c, 1, counts[4], ((uint64_t)4 << 32) + 1);
         pk->b_g2 = bases_generated(c, 2, counts[5], ((uint64_t)4 << 32) + 1);
-        for (Bases* q : {pk->h.get(), pk->l.get(), pk->a.get(), pk->b_g1.get(), pk->b_g2.get()}) bases_build_table(c, q);
+        bases_build_table(c, pk->h.get());
+        const size_t lo3[3] = {0, 0, 0}, n3[3] = {pk->l->n, pk->a->n, pk->b_g1->n};
+        pk_build_witness_tables(c, pk, lo3, n3);
     } catch (...) { delete h; throw; }
     *out = h;
     return ZA_OK;
@@ -1408,11 +1457,11 @@ int za_pk_partition_weighted(za_ctx* ctx, za_pk* pk, const za_circuit* circuit, 
     const uint32_t w0 = world > 1 ? rank0_weight_permille : 1000u;
     size_t lo, hi;
     share(m - 1, rank, world, lo, hi); bases_build_table(&ctx->c, p->h.get(), lo, hi - lo);
-    share_weighted(c->na, rank, world, w0, lo, hi); bases_build_table(&ctx->c, p->l.get(), lo, hi - lo);
-    share_weighted(c->a_cat_total, rank, world, w0, lo, hi); bases_build_table(&ctx->c, p->a.get(), lo, hi - lo);
-    share_weighted(c->b_cat_total, rank, world, w0, lo, hi);
-    bases_build_table(&ctx->c, p->b_g1.get(), lo, hi - lo);
-    bases_build_table(&ctx->c, p->b_g2.get(), lo, hi - lo);
+    size_t los[3], ns[3];
+    share_weighted(c->na, rank, world, w0, lo, hi); los[0] = lo; ns[0] = hi - lo;
+    share_weighted(c->a_cat_total, rank, world, w0, lo, hi); los[1] = lo; ns[1] = hi - lo;
+    share_weighted(c->b_cat_total, rank, world, w0, lo, hi); los[2] = lo; ns[2] = hi - lo;
+    pk_build_witness_tables(&ctx->c, p, los, ns);
     return ZA_OK;
     ZA_CATCH
 }
@@ -1534,8 +1583,10 @@ int za_prove_msm_collect(za_ctx* ctx, uint8_t* partials_out) {
     if (!ctx || !partials_out) return fail(ZA_ERR_INVALID, "NULL argument");
     ZA_TRY
     ZA_CUDA(cudaSetDevice(ctx->c.device));
-    for (int s : {0, 1, 2, 3, 4})
+    for (int s : {0, 1, 2, 3, 4}) {
+        if ((s == 1 || s == 2) && ctx->c.witness_merged && ctx->c.slots[3].busy && ctx->c.slots[3].nparts == 3) continue;   // L and A ride in slot 3
         if (!ctx->c.slots[s].busy) return fail(ZA_ERR_INVALID, "za_prove_msm_collect: multiexp %d was not enqueued", s);
+    }
     Partials P;
     try { prove_msms_collect(&ctx->c, P); }
     catch (...) { msm_abort(&ctx->c); throw; }
