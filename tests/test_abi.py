@@ -110,15 +110,23 @@ def test_za2c_verify_like_the_bindings_use_it():
     assert L.verify(vk_json, b'{"a":1}', err, 4) == 1                               # ERR_BUFFER_TOO_SMALL
 
 
-def test_za2c_setup_and_prove_fail_loudly_without_the_front_end():
+def test_za2c_setup_and_prove_argument_rules_and_no_cpu_fallback(tmp_path):
+    """lib.rs:51-101: verifier type checked first ("invalid validator type"), errors as Debug text in err_buf, `len >= size`
+    is "too small".  Without a CUDA device the GPU stages fail loudly — there is no CPU path behind setup / prove."""
+    import torch
     L = _za2c()
     err = ctypes.create_string_buffer(1024)
     out = ctypes.create_string_buffer(64)
-    assert L.prove(b"proving.key", b'{"p":2,"q":3}', out, 64, err, 1024) == 100
-    assert b"za_create_proof" in err.value and b"front-end" in err.value
-    assert L.setup(b"circuit.za", b"proving.key", b"json", out, 64, err, 1024) == 100 and b"za_generate_parameters" in err.value
     assert L.setup(b"circuit.za", b"proving.key", b"yaml", out, 64, err, 1024) == 100 and err.value == b"invalid validator type"
-    assert L.prove(b"proving.key", b"{}", out, 64, err, 8) == 1
+    assert L.setup(b"/nonexistent/circuit.za", b"proving.key", b"json", out, 64, err, 1024) == 100 and len(err.value) > 0
+    assert L.prove(b"/nonexistent/proving.key", b"{}", out, 64, err, 8) == 1          # error text longer than err_buf
+    assert L.prove(b"/nonexistent/proving.key", b"{", out, 64, err, 1024) == 100      # malformed inputs JSON
+    if not torch.cuda.is_available():
+        circuit = tmp_path / "c.za"
+        circuit.write_text("template T() { signal private input p; signal output r; r <== p*p; }\ncomponent main = T();\n")
+        rc = L.setup(str(circuit).encode(), str(tmp_path / "proving.key").encode(), b"json", out, 64, err, 1024)
+        assert rc == 100 and b"no CPU fallback" in err.value
+        assert not (tmp_path / "proving.key").exists()
 
 
 def test_headers_are_plain_c_and_a_c_program_links(tmp_path):

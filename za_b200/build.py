@@ -7,6 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libza_b200.so")
 OUT_ZA2C = os.path.join(HERE, "libza2c.so")
+FRONTEND_SOURCES = ["parser.cpp", "bincode.cpp", "eval.cpp"]      # za's front-end (host C++), part of libza2c.so
 SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "prove.cu", "format.cu", "verify.cu", "setup.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-O2", "--expt-relaxed-constexpr", "-rdc=false"]
@@ -52,7 +53,8 @@ def build_variant(tag, defines, verbose=False):
 def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     if not force and not needs_build():
-        if not os.path.exists(OUT_ZA2C) or os.path.getmtime(OUT_ZA2C) < os.path.getmtime(os.path.join(CSRC, "za2c.cpp")):
+        fe = [os.path.join(CSRC, "za2c.cpp")] + [os.path.join(CSRC, "frontend", f) for f in os.listdir(os.path.join(CSRC, "frontend"))]
+        if not os.path.exists(OUT_ZA2C) or any(os.path.getmtime(OUT_ZA2C) < os.path.getmtime(f) for f in fe):
             build_za2c()
         return OUT
     objs = []
@@ -81,8 +83,8 @@ def build(force=False, verbose=False):
 
 def build_za2c():
     """libza2c.so: the outer C ABI of za's bindings (include/za2c.h) on top of libza_b200.so (host code only)."""
-    src = os.path.join(CSRC, "za2c.cpp")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", OUT_ZA2C, src, "-L" + HERE, "-lza_b200",
+    srcs = [os.path.join(CSRC, "za2c.cpp")] + [os.path.join(CSRC, "frontend", f) for f in FRONTEND_SOURCES]
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", OUT_ZA2C] + srcs + ["-L" + HERE, "-lza_b200",
                            "-Wl,-rpath,$ORIGIN"])
     return OUT_ZA2C
 
