@@ -28,7 +28,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "Groth16 prove ms @2^20 constraints; G1 MSM Mpts/s; Fr NTT GElem/s"
-IMAD_PER_MODMUL = 264          # 8x32-bit-limb Montgomery product, IMAD-class instructions
+IMAD_PER_MODMUL = 264          # 8x32-bit-limb Montgomery product, IMAD-class instructions (64 a.b + 64 m.q limb products x 2, + 8)
+IMAD_PER_SQR = 208             # dedicated squaring: 36 limb products + the same 64-product reduction
+# per "Fq product" unit the accumulation kernels report as work (G1: 10 per XYZZ mixed addition = 8 M + 2 S;
+# G2: an Fq2 product = 3 units, an Fq2 squaring = 2; lazily reduced Karatsuba = 3 wide products + 2 reductions = 656 IMAD)
+IMAD_PER_G1_UNIT = (8 * IMAD_PER_MODMUL + 2 * IMAD_PER_SQR) / 10.0
+IMAD_PER_G2_UNIT = (5 * 656 + 2 * IMAD_PER_MODMUL) / 17.0       # batched-affine addition over Fq2: 5 M + 1 S
 # The accumulation kernels report their algorithmic work in Fq products (za_ctx_profile_read): an XYZZ mixed
 # addition is 8M + 2S = 10 (over Fq2: 8 x 3 + 2 x 2 = 28), a batched-affine addition of the G2 pair rounds
 # 5M + 1S over Fq2 = 17.
@@ -310,22 +315,22 @@ def run_gpu(args):
         if log_m == 20 and tfile.get("ntt_pass_kernel"):
             t = tfile["ntt_pass_kernel"]
             ntt_traffic = int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
-        imads = dom["work"] * IMAD_PER_MODMUL
+        imads = dom["work"] * (IMAD_PER_G1_UNIT if dom is acc1 else IMAD_PER_G2_UNIT)
         achieved = imads / (dom["ms"] * 1e-3) / 1e12 if dom["ms"] > 0 else 0.0
         roofline = {"bound": "imad", "kernel": dom_name, "achieved": achieved, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
                     "frac": achieved / (imad_peak / 1e12) if imad_peak else None, "traffic": traffic,
                     "traffic_note": "DRAM read+write bytes per launch from the ncu --set full capture of the same 2^20 workload (profiles/r0N_traffic.json); null for other sizes",
                     "peak_source": "measured in this run (za_imad_peak: dependency-free mad.lo.u32 on all SMs)",
-                    "algorithmic": f"{int(dom['work'] / max(dom['spans'], 1))} Fq products (" + ("10 per XYZZ mixed addition" if dom is acc1 else "17 per batched-affine addition, 28 per XYZZ mixed addition over Fq2") + f") x {IMAD_PER_MODMUL} IMAD per launch (rank 0's share)",
+                    "algorithmic": f"{int(dom['work'] / max(dom['spans'], 1))} Fq products (" + ("10 per XYZZ mixed addition: 8 products x 264 IMAD + 2 squarings x 208 IMAD" if dom is acc1 else "17 per batched-affine addition over Fq2: 5 lazily reduced Fq2 products x 656 IMAD + 1 Fq2 squaring x 528 IMAD") + ") per launch (rank 0's share)",
                     "launch_ms": dom["ms"] / max(dom["spans"], 1),
                     "timing": ("kernel timed alone in this process (CUDA events), same size and table as in the proof; in the proof it shares the SMs with the G2 multiexp's kernels by design" if iso1 is not None else "in-step CUDA events"),
                     "in_step_launch_ms": in_step["g1" if dom is acc1 else "g2"],
                     "share_of_step": (dom["ms"] / max(dom["spans"], 1)) * (n_g1_launches if dom is acc1 else 1.0) / prove_ms,
                     "note": "tensor cores not applicable (multiprecision integer); HBM needs 96 B/point, two orders below compute"}
-        g2_t = acc2["work"] * IMAD_PER_MODMUL / (acc2["ms"] * 1e-3) / 1e12 if acc2["ms"] > 0 else 0.0
+        g2_t = acc2["work"] * IMAD_PER_G2_UNIT / (acc2["ms"] * 1e-3) / 1e12 if acc2["ms"] > 0 else 0.0
         roofline_g2 = {"bound": "imad", "kernel": "G2 bucket accumulation: msm_pair_round_kernel<Fq2> (batched-affine rounds) + msm_accumulate_kernel<Fq2>",
                        "achieved": g2_t, "peak": imad_peak / 1e12, "unit": "TIMAD/s", "frac": g2_t / (imad_peak / 1e12) if imad_peak else None,
-                       "algorithmic": f"{int(acc2['work'] / max(acc2['spans'], 1))} Fq products (17 per batched-affine addition, 28 per XYZZ mixed addition over Fq2) x {IMAD_PER_MODMUL} IMAD per multiexp",
+                       "algorithmic": f"{int(acc2['work'] / max(acc2['spans'], 1))} Fq products (17 per batched-affine addition, 28 per XYZZ mixed addition over Fq2) x {IMAD_PER_G2_UNIT:.0f} IMAD (an Fq2 product = 3 units = 656 IMAD lazily reduced, an Fq2 squaring = 2 units = 528) per multiexp",
                        "launch_ms": acc2["ms"] / max(acc2["spans"], 1), "in_step_launch_ms": in_step["g2"],
                        "share_of_step": acc2["ms"] / max(acc2["spans"], 1) / prove_ms}
         ntt_bytes = 64.0 * nttp["work"]
@@ -354,10 +359,12 @@ def run_gpu(args):
         p_red = buckets * 2 * (14 * n_g1_red + 42 * n_g2_red)        # ~2 XYZZ additions per bucket, 12M + 2S each (x3 over Fq2)
         p_other = (prof["h_pointwise"]["work"] * 3 + prof["r1cs_eval"]["work"] + (ni + na) * steps_profiled) / steps_profiled
         step_products = p_acc + p_ntt + p_red + p_other
-        roofline_step = {"bound": "imad", "achieved": step_products * IMAD_PER_MODMUL / (prove_ms * 1e-3) / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
-                         "frac": step_products * IMAD_PER_MODMUL / (prove_ms * 1e-3) / imad_peak if imad_peak else None,
+        step_imads = (prof["msm_accumulate_g1"]["work"] * IMAD_PER_G1_UNIT + prof["msm_accumulate_g2"]["work"] * IMAD_PER_G2_UNIT) / steps_profiled \
+            + (p_ntt + p_red + p_other) * IMAD_PER_MODMUL
+        roofline_step = {"bound": "imad", "achieved": step_imads / (prove_ms * 1e-3) / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
+                         "frac": step_imads / (prove_ms * 1e-3) / imad_peak if imad_peak else None,
                          "products_per_proof": {"bucket_accumulation": int(p_acc), "ntt_butterflies": int(p_ntt), "bucket_reduction_estimate": int(p_red), "other": int(p_other)},
-                         "note": "all field products of one proof on device 0 (its share of the multiexps at N > 1) x 264 IMAD / ms_per_step / measured IMAD peak"}
+                         "note": "all field products of one proof on device 0 (its share of the multiexps at N > 1) x their IMAD cost (product 264, squaring 208, Fq2 product 656) / ms_per_step / measured IMAD peak"}
         line = {"metric": METRIC, "value": prove_ms, "unit": "ms", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": prove_ms,
                 "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                 "config": {"workload": f"synthetic mul-chain R1CS, {nc} constraints (domain 2^{log_m}), {na} aux: "
@@ -403,7 +410,7 @@ def run_gpu(args):
         sub["g1_msm"] = {"log_n": args.log_msm, "n_gpus": world, "ms": msm_ms, "mpts_s": n_msm / msm_ms / 1e3, "scalars": "uniform 253-bit",
                          "fixed_base_table_c": tab_c, "accumulate_ms": a["ms"] / max(a["spans"], 1),
                          "sort_ms": p2["msm_sort"]["ms"] / max(a["spans"], 1),
-                         "imad_frac": (a["work"] * IMAD_PER_MODMUL / (a["ms"] * 1e-3)) / ipk if a["ms"] else None}
+                         "imad_frac": (a["work"] * IMAD_PER_G1_UNIT / (a["ms"] * 1e-3)) / ipk if a["ms"] else None}
         if rank == 0 and args.log_msm <= 20:
             # linearity check of the full-size result: bases are (1+i) G, so the sum is (sum s_i (1+i) mod r) G
             from tests import oracle as O

@@ -186,6 +186,12 @@ int za_share_weighted(uint64_t count, int rank, int world, uint32_t rank0_weight
 int za_pk_partition_weighted(za_ctx *ctx, za_pk *pk, const za_circuit *circuit, int rank, int world,
                              uint32_t rank0_weight_permille);
 int za_prove_h_device(za_ctx *ctx, const za_circuit *circuit, const void *d_witness, void *d_h);
+/* Destinations of the NEXT za_prove_h_device on this context: h[k] is stored at (char *)outs[j] + 32 k for the first j with
+ * k < his[j] (the last part takes the rest) instead of d_h.  outs[j] may be memory of a peer device this context's device
+ * has peer access to: the last pass of the last transform then writes every rank's slice into that rank's memory over
+ * NVLink and no copy follows the H pipeline (what za_prover does).  n <= 16; needs a domain of 2^12 or more; consumed
+ * (cleared) by that call.  n = 0 clears it. */
+int za_ctx_set_h_scatter(za_ctx *ctx, int n, void *const *outs, const uint64_t *his);
 /* Stage 2 in two asynchronous halves, so that the multiexps that do not depend on the H polynomial (ZA_MSM_WITNESS:
  * L, A, B-G1, B-G2) run on every GPU while rank 0 still computes it; ZA_MSM_H (needs d_h on the rank's share)
  * follows once the h scalars have arrived.  za_prove_msm_collect waits for all of them -> partials record. */
@@ -236,7 +242,7 @@ int za_bases_download(za_ctx *ctx, const za_bases *bases, size_t offset, size_t 
 /* Build the fixed-base table of a bases array (entry i*W + w = 2^(c w) * P_i; W = ceil(255 / c) copies of the
  * array): every later multiexp over it uses ONE bucket space for all windows and c up to 20 (13 windows instead
  * of 16).  Proving-key queries get their table at load.  Returns the window size c (> 0), 0 if no table was
- * built (fewer than 4096 points, a point at infinity, or more than 24 GiB), or a negative error. */
+ * built (fewer than 4096 points, a point at infinity, or a table over the memory bound: 64 GiB or 45 % of the free device memory), or a negative error. */
 int za_bases_precompute(za_ctx *ctx, za_bases *bases);
 /* A proving key of the given query sizes (counts[6] = |ic|, |h|, |l|, |a|, |b_g1|, |b_g2|) whose bases are
  * known multiples of the generators: query q entry i = ((q+1) * 2^32 + i + 1) * G with q = 0..3 for

@@ -34,3 +34,12 @@ if what == "g2t":
     sc = torch.from_numpy(synthetic.random_scalars(n, 3)).cuda()
     for _ in range(2): za_b200.multiexp_device(ctx, bases, sc.data_ptr(), n)
 print("done")
+if what == "hpoly":
+    logn = 20
+    n = 1 << logn
+    a = torch.from_numpy(synthetic.random_scalars(3 * n, 3)).cuda()
+    ctx.fr_convert_device(a.data_ptr(), 3 * n, False)
+    p = a.data_ptr()
+    for _ in range(2): ctx.h_poly_device(p, p + 32 * n, p + 64 * n, logn)
+    torch.cuda.synchronize()
+    print("hpoly done")

@@ -380,6 +380,22 @@ def test_staged_prove_equals_single_call(ctx):
     torch.cuda.synchronize()
     assert za_b200.create_proof_device(ctx, pk, circ, wit.data_ptr(), 5, 6) == ref
     za_b200.prove_h_device(ctx, circ, wit.data_ptr(), h.data_ptr())
+    # the h slices as stores of the last NTT pass (za_ctx_set_h_scatter, what za_prover does towards its peer devices):
+    # three destination buffers by index range; each holds exactly its slice of h, the rest is untouched
+    bufs = [torch.full((m, 32), 0xEE, dtype=torch.uint8, device="cuda") for _ in range(3)]
+    bounds = [(m - 1) // 3, 2 * (m - 1) // 3, m - 1]
+    za_b200.set_h_scatter(ctx, [b.data_ptr() for b in bufs], bounds)
+    h2 = torch.full((m, 32), 0xEE, dtype=torch.uint8, device="cuda")
+    za_b200.prove_h_device(ctx, circ, wit.data_ptr(), h2.data_ptr())
+    torch.cuda.synchronize()
+    lo = 0
+    for b, hi in zip(bufs, bounds):
+        assert torch.equal(b[lo:hi], h[lo:hi]) and bool((b[:lo] == 0xEE).all()) and bool((b[hi:m - 1] == 0xEE).all())
+        lo = hi
+    assert bool((h2 == 0xEE).all())                         # nothing went to d_h
+    za_b200.prove_h_device(ctx, circ, wit.data_ptr(), h2.data_ptr())          # the setting was consumed: plain output again
+    torch.cuda.synchronize()
+    assert torch.equal(h2[:m - 1], h[:m - 1])
     for world in (1, 2, 3):
         parts = [za_b200.prove_msm_partials(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), k, world) for k in range(world)]
         assert za_b200.prove_assemble(pk, np.stack(parts), 5, 6) == ref

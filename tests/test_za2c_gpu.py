@@ -64,7 +64,7 @@ def test_python3_binding_test_flow(circom, tmp_path):
     circom.verbose(False)
     # what the strings hold (format.rs:30-99): the public output r = 6 and main.r named in the verifying key
     assert json.loads(proof_and_public_inputs)["public_inputs"] == ["6"]
-    assert json.loads(verifying_key)["inputs"] == ["main.r"]
+    assert json.loads(verifying_key)["input_names"] == ["main.r"]
     tampered = json.loads(proof_and_public_inputs); tampered["public_inputs"] = ["7"]
     assert circom.verify(verifying_key, json.dumps(tampered)) is False
     # a second proof from the loaded key: fresh r, s -> different bytes, still valid
@@ -94,7 +94,7 @@ def test_example_circuit_setup_prove_verify_and_the_key_file(circom, tmp_path):
     # the key stays usable after the failed calls
     assert circom.verify(vk_json, circom.prove(pk_path, '{ "p" : "3", "q":"4", "r":"12" }')) is True
     sol = circom.setup(circuit_path, pk_path, "solidity")
-    assert "pragma solidity" in sol and "verifyProof" in sol
+    assert "pragma solidity" in sol and "verifyTx" in sol and "Pairing" not in sol[:0]
     # a Solidity-type setup re-keys the file: the old verifying key no longer matches new proofs
     assert circom.verify(vk_json, circom.prove(pk_path, '{ "p" : "2", "q":"3", "r":"6" }')) is False
 
@@ -164,6 +164,6 @@ def test_compile_witness_prove_a_mimc7_chain(circom, tmp_path):
     proof = circom.prove(pk_path, json.dumps({"seed": str(seed), "key": str(key)}))
     assert json.loads(proof)["public_inputs"] == [str(x), str(key)]     # outputs first, then public inputs (test.rs:738-769)
     assert circom.verify(vk_json, proof) is True
-    assert json.loads(vk_json)["inputs"] == ["main.digest", "main.key"]
+    assert json.loads(vk_json)["input_names"] == ["main.digest", "main.key"]
     forged = json.loads(proof); forged["public_inputs"][0] = str((x + 1) % E.R)
     assert circom.verify(vk_json, json.dumps(forged)) is False

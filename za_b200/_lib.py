@@ -83,6 +83,7 @@ SYMBOLS = {
     "za_prove_msm_enqueue": (ci, [vp, vp, vp, vp, vp, ci, ci, ci]),
     "za_prove_msm_collect": (ci, [vp, vp]),
     "za_prove_h_device": (ci, [vp, vp, vp, vp]),
+    "za_ctx_set_h_scatter": (ci, [vp, ci, vp, vp]),
     "za_prove_msm_partials": (ci, [vp, vp, vp, vp, vp, ci, ci, vp]),
     "za_prove_assemble": (ci, [vp, vp, ci, vp, vp, vp]),
     "za_bases_generate": (ci, [vp, ci, sz, ctypes.c_uint64, ctypes.POINTER(vp)]),

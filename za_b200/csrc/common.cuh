@@ -107,6 +107,15 @@ struct MsmSlot {
 enum { PROF_ACC_G1 = 0, PROF_ACC_G2 = 1, PROF_NTT = 2, PROF_MSM_SORT = 3, PROF_MSM_REDUCE = 4, PROF_R1CS = 5, PROF_POINTWISE = 6, PROF_OTHER = 7, PROF_NCAT = 8 };
 struct ProfSpan { cudaEvent_t a, b; int cat; };
 
+// Where the last store of the H pipeline puts h[k]: the first part j with k < hi[j] receives it at out[j] + k (out[j] may be
+// memory of a peer device — the h slices of a multi-GPU proof travel as the stores of the last NTT pass, not as copies).
+#define ZA_H_SCATTER_MAX 16
+struct HScatter {
+    int n = 0;
+    Fr* out[ZA_H_SCATTER_MAX];
+    uint32_t hi[ZA_H_SCATTER_MAX];
+};
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;      // stream all work of this context is issued on
@@ -126,6 +135,7 @@ struct Ctx {
     cudaEvent_t dbg_t0 = nullptr;       // ZA_DEBUG_TIMELINE: start of the current proof on this device
     bool dbg_t0_valid = false;
     bool witness_merged = false;        // the last prove enqueued B (G1), L and A as one multiexp in slot 3
+    HScatter h_scatter;                 // n > 0: destinations of the next H pipeline's output (prove_h consumes and clears it)
     bool ntt_attr_set = false;          // the > 48 KiB shared-memory attribute of the NTT kernels is set on this context's device
     // optional per-kernel-class timing with CUDA events on `stream` (bench.py roofline numbers)
     bool profile = false;

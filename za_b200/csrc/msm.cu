@@ -1435,6 +1435,11 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
         // so G1 keeps the single-pass XYZZ accumulation.
         const double load = (double)Emax / (double)nkeys;
         if (sizeof(F) == sizeof(Fq2)) rounds = load >= 12 ? 4 : load >= 6 ? 3 : load >= 3 ? 1 : 0;
+        // a round is one full pass of launches (rescan + round kernel); below ~1.5 waves of its CTAs it costs more than
+        // the products it saves.  One rank's share of a 2^20 proof, stage 2 alone on a B200 (profiles/r02_shards.md):
+        // 1/8: 4 rounds 5.35 ms, 3 rounds 4.98, 2 rounds 5.1, none 5.4; 1/4: 7.97 / 7.55 / 7.62; 1/2: 13.47 / 13.17;
+        // the whole multiexp (13.6 M entries) takes the same time with 3 or 4 rounds.
+        if (rounds > 3) rounds = 3;
         if (Emax < (1u << 16)) rounds = 0;
         if (const char* e = getenv("ZA_MSM_ROUNDS")) { int v = atoi(e); if (v >= 0 && v <= PAIR_MAX_ROUNDS) rounds = v; }
         if (nparts > 1) rounds = 0;

@@ -57,6 +57,7 @@ struct NttPass {
     int LOGT;             // 2^LOGT columns per CTA
     int inverse;
     int first;            // first pass of the transform (apply `pre`)
+    HScatter sc;          // last pass: output index k goes to sc.out[j] + k, j the first part with k < sc.hi[j] (sc.n == 0: to `out`)
 };
 
 static __device__ __forceinline__ unsigned rotr3(unsigned j, unsigned r) { return ((j >> r) | (j << (3 - r))) & 7u; }
@@ -64,8 +65,11 @@ static __device__ __forceinline__ unsigned rotr3(unsigned j, unsigned r) { retur
 // LAST = false: in-place style pass, columns are the low LOGT index bits (contiguous in memory).
 // LAST = true : final pass (lo = 0), columns are the top LOGT index bits, output is written at the
 //               bit-reversed index so the transform result is in natural order.
+#ifndef ZA_NTT_MINB
+#define ZA_NTT_MINB 2          // two CTAs of 64 KiB per SM: <= 128 registers (ptxas takes 188 for the last pass if allowed; 3 CTAs spill and lose, profiles/r02_ntt.md)
+#endif
 template <bool LAST>
-__global__ void __launch_bounds__(256) ntt_pass_kernel(NttPass p) {
+__global__ void __launch_bounds__(256, ZA_NTT_MINB) ntt_pass_kernel(NttPass p) {
     extern __shared__ uint4 smem_raw[];
     Fr* sm = reinterpret_cast<Fr*>(smem_raw);
     const int n = p.n, lo = p.lo, K = p.K, LOGT = p.LOGT, L = K + LOGT;
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(NttPass p) {
                 x[2] = y1; x[4] = y2; x[6] = y3; x[1] = y4; x[3] = y5; x[5] = y6;
             }
         } else
-#pragma unroll 1
+#pragma unroll 1      // measured: fully unrolled stages (no register rotation) run 30 % slower (instruction cache), profiles/r02_ntt.md
         for (int k = 0; k < nb; k++) {
             const int b = lo + wb + 2 - k;
 #pragma unroll
@@ -181,7 +185,13 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(NttPass p) {
             Fr v = ld_fr(sm + ((col << K) | kap));
             if (p.post) v = v * ldg_fr(p.post + kidx);
             else if (p.post_const) v = v * ldg_fr(p.post_const);
-            st_fr(out + kidx, v);
+            Fr* dst = out;
+            if (p.sc.n) {
+                int j = 0;
+                while (j + 1 < p.sc.n && kidx >= p.sc.hi[j]) j++;
+                dst = p.sc.out[j];
+            }
+            st_fr(dst + kidx, v);
         }
     }
 }
@@ -342,6 +352,7 @@ struct NttFuse {
     const Fr* sub_c = nullptr;
     const Fr* pre_const = nullptr;
     Fr* out = nullptr;               // the result goes here instead of back into `buf` (batch 1)
+    const HScatter* scatter = nullptr; // ... or to several destinations by output index (batch 1, two or more passes)
 };
 
 // One transform (batch vectors, `stride` elements apart), data in `buf` (Montgomery), result back in `buf`.
@@ -375,6 +386,11 @@ static void ntt_run(Ctx* ctx, Fr* buf, Fr* scratch, int n, int batch, size_t str
         p.tw = tw; p.pre = f.pre; p.post = f.post; p.post_const = f.post_const;
         p.mul_b = f.mul_b; p.sub_c = f.sub_c; p.pre_const = f.pre_const;
         p.n = n; p.lo = lo; p.K = K; p.inverse = inverse ? 1 : 0; p.first = pi == 0;
+        p.sc.n = 0;
+        if (pi == P - 1 && f.scatter && f.scatter->n) {
+            if (P < 2 || batch != 1) throw ZaError(ZA_ERR_INVALID, "internal: scattered NTT output needs one vector and two or more passes");
+            p.sc = *f.scatter;
+        }
         int logt = NTT_L - K;
         if (last) { if (logt > n - K) logt = n - K; } else { if (logt > lo) logt = lo; }
         p.LOGT = logt;
@@ -470,6 +486,10 @@ void h_poly_device(Ctx* ctx, Fr* a, Fr* b, Fr* c, int log_m, Fr* h_out) {
         last.mul_b = b; last.sub_c = c; last.pre_const = d->consts.as<Fr>() + 1;
         last.post = d->pow_ginv_minv_canon.as<Fr>();
         last.out = h_out;
+        if (ctx->h_scatter.n) {
+            if (log_m <= NTT_L) throw ZaError(ZA_ERR_INVALID, "internal: scattered h output needs a domain of more than one NTT tile");
+            last.scatter = &ctx->h_scatter;
+        }
         ntt_run(ctx, a, scratch.as<Fr>(), log_m, 1, m, true, tw, last);
     } else {
         {

@@ -58,6 +58,18 @@ static G2XYZZ g2_xyzz_from_le(const uint8_t* p) {
 
 // Window size of the fixed-base table: with one bucket space for all windows the bucket count is 2^(c-1)
 // regardless of W, so c grows with log2(n) up to 20 (13 windows).  0 = no table (small or too large).
+// Upper bound of ONE query's table: 64 GiB (a 2^26-point G1 query at c = 20 is 56 GB of the 180 GB) and never more than
+// 45 % of the memory that is free when the table is built — the queries of a large key are built one after the other, so
+// the later ones fall back to the table-free path by themselves once the card fills up (there used to be a fixed 24 GiB
+// cap that dropped the table of every 2^26 query).  ZA_MSM_TABLE_CAP_GB overrides the 64.
+static size_t table_cap_bytes() {
+    size_t cap = (size_t)64 << 30;
+    if (const char* e = getenv("ZA_MSM_TABLE_CAP_GB")) { long v = atol(e); if (v >= 0 && v <= 1024) cap = (size_t)v << 30; }
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) cap = std::min(cap, (size_t)((double)free_b * 0.45));
+    else cudaGetLastError();
+    return cap;
+}
 static int table_window_bits(size_t n, size_t point_bytes) {
     if (const char* e = getenv("ZA_MSM_TABLE")) { int v = atoi(e); if (v == 0) return 0; if (v >= 8 && v <= 22) return v; }
     if (n < 4096) return 0;
@@ -65,17 +77,16 @@ static int table_window_bits(size_t n, size_t point_bytes) {
     // measured on B200 (scratch/sweep_c.py): 2^16 -> 16, 2^18 -> 17, 2^20 and up -> 20
     int c = lg >= 20 ? 20 : lg >= 18 ? 17 : lg >= 15 ? 16 : lg + 1;
     size_t W = (255 + c - 1) / c;
-    if (n * W * point_bytes > ((size_t)24 << 30)) return 0;     // keep one query's table under 24 GiB (TABLE_CAP_BYTES)
+    if (n * W * point_bytes > table_cap_bytes()) return 0;
     return c;
 }
-static const size_t TABLE_CAP_BYTES = (size_t)24 << 30;
 // Build the table for bases [lo, lo + n) (default: the whole array); the window size follows n unless `c_forced` > 0.
 static void bases_build_table(Ctx* ctx, Bases* b, size_t lo = 0, size_t n = (size_t)-1, int c_forced = 0) {
     if (n == (size_t)-1) n = b->n - lo;
     const size_t pb = b->group == 1 ? sizeof(G1Affine) : sizeof(G2Affine);
     b->table.release(); b->tab_c = 0; b->tab_W = 0; b->tab_lo = 0; b->tab_n = 0;
     int c = table_window_bits(n, pb);
-    if (c_forced > 0 && n > 64 && n * (size_t)((255 + c_forced - 1) / c_forced) * pb <= TABLE_CAP_BYTES) c = c_forced;
+    if (c_forced > 0 && n > 64 && n * (size_t)((255 + c_forced - 1) / c_forced) * pb <= table_cap_bytes()) c = c_forced;
     if (!c || b->has_infinity) return;
     const int W = (255 + c - 1) / c;
     b->table.alloc(n * (size_t)W * pb);
@@ -961,6 +972,7 @@ struct Prover {
     std::condition_variable h_cv;
     uint64_t h_issued = 0, generation = 0;           // device 0 has issued the h copies of proof `generation`
     bool h_failed = false;
+    bool peers_mapped = false;                       // device 0 can store into every other device's memory
     uint32_t rank0_weight = 1000;
     std::vector<Partials> partials;
     ~Prover();
@@ -1096,11 +1108,27 @@ static void prover_device_step(Prover* P, int k, uint64_t gen, const uint8_t* in
         if (k == 0) {
             try {
                 canonical_check_enqueue(cx, d_wit, (size_t)c->ni + c->na, CHK_WITNESS);
-                prove_h(cx, c, d_wit, d_h, nullptr);
+                // The h slice of device j is WRITTEN into j's memory by the last pass of the last transform (stores over
+                // NVLink through the peer mapping): no copy sits between the H pipeline and the peers' H multiexps.
+                // Without peer access to every device (or ZA_PROVER_H_COPY=1) the slices travel as copies afterwards.
+                static const bool force_copy = getenv("ZA_PROVER_H_COPY") != nullptr;
+                int log_m = 0; domain_size(c, &log_m);
+                const bool direct = !force_copy && P->peers_mapped && n <= ZA_H_SCATTER_MAX && log_m > 11;
+                if (direct) {
+                    cx->h_scatter.n = n;
+                    for (int j = 0; j < n; j++) {
+                        size_t lo, hi;
+                        share(m - 1, j, n, lo, hi);
+                        cx->h_scatter.out[j] = P->h[j].as<Fr>();
+                        cx->h_scatter.hi[j] = (uint32_t)hi;
+                    }
+                }
+                try { prove_h(cx, c, d_wit, d_h, nullptr); } catch (...) { cx->h_scatter.n = 0; throw; }
+                cx->h_scatter.n = 0;
                 for (int j = 1; j < n; j++) {
                     size_t lo, hi;
                     share(m - 1, j, n, lo, hi);
-                    if (hi > lo) ZA_CUDA(cudaMemcpyPeerAsync(P->h[j].as<Fr>() + lo, P->devices[j], d_h + lo, P->devices[0], (hi - lo) * sizeof(Fr), cx->stream));
+                    if (!direct && hi > lo) ZA_CUDA(cudaMemcpyPeerAsync(P->h[j].as<Fr>() + lo, P->devices[j], d_h + lo, P->devices[0], (hi - lo) * sizeof(Fr), cx->stream));
                     ZA_CUDA(cudaEventRecord(P->h_ready[j], cx->stream));
                 }
             } catch (...) { announce(true); throw; }
@@ -1526,10 +1554,24 @@ int za_prove_h_device(za_ctx* ctx, const za_circuit* circuit, const void* d_witn
     ZA_TRY
     ZA_CUDA(cudaSetDevice(ctx->c.device));
     const Circuit* c = circuit->c.get();
+    struct Clear { Ctx* c; ~Clear() { c->h_scatter.n = 0; } } clear{&ctx->c};
+    if (ctx->c.h_scatter.n) {
+        int log_m = 0; domain_size(c, &log_m);
+        if (log_m <= 11) throw ZaError(ZA_ERR_INVALID, "za_ctx_set_h_scatter needs a domain of 2^12 or more elements");
+    }
     canonical_check_enqueue(&ctx->c, d_witness, (size_t)c->ni + c->na, CHK_WITNESS);      // verdict: za_prove_msm_collect / _partials
     prove_h(&ctx->c, c, (const uint8_t*)d_witness, (Fr*)d_h, nullptr);
     return ZA_OK;
     ZA_CATCH
+}
+int za_ctx_set_h_scatter(za_ctx* ctx, int n, void* const* outs, const uint64_t* his) {
+    if (!ctx || n < 0 || n > ZA_H_SCATTER_MAX || (n && (!outs || !his))) return fail(ZA_ERR_INVALID, "bad argument");
+    for (int j = 0; j < n; j++) {
+        if (!outs[j] || his[j] > 0xffffffffull || (j && his[j] < his[j - 1])) return fail(ZA_ERR_INVALID, "h scatter: NULL destination or bounds not ascending");
+    }
+    ctx->c.h_scatter.n = n;
+    for (int j = 0; j < n; j++) { ctx->c.h_scatter.out[j] = (Fr*)outs[j]; ctx->c.h_scatter.hi[j] = (uint32_t)his[j]; }
+    return ZA_OK;
 }
 
 // verdicts of the range checks the staged entry points enqueued on this context (after a synchronisation)
@@ -1636,14 +1678,17 @@ int za_prover_create(const int* devices, int n_devices, za_prover** out) {
     ZA_CUDA(cudaSetDevice(devices[0]));
     for (int k = 0; k < n_devices; k++) ZA_CUDA(cudaEventCreateWithFlags(&P->h_ready[k], cudaEventDisableTiming));
     // device 0 writes the h slices straight into its peers' memory
+    P->peers_mapped = n_devices > 1;
     for (int k = 1; k < n_devices; k++) {
         int can = 0;
+        bool ok = false;
         if (cudaDeviceCanAccessPeer(&can, devices[0], devices[k]) == cudaSuccess && can) {
             cudaSetDevice(devices[0]);
             cudaError_t e = cudaDeviceEnablePeerAccess(devices[k], 0);
-            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { /* the copy falls back to staging through the host */ }
+            ok = e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;      // otherwise the h slices travel as (host-staged) copies
             cudaGetLastError();
         }
+        if (!ok) P->peers_mapped = false;
     }
     for (int k = 0; k < n_devices; k++) {
         P->workers.emplace_back(new ProverWorker());

@@ -355,7 +355,8 @@ static std::string do_setup(const std::string& circuit_path, const std::string& 
     std::string out;
     if (solidity) {
         size_t need = 0;
-        za_vk_to_solidity(vk.data(), counts[0], names.data(), names.size(), nullptr, nullptr, 0, &need);
+        char probe = 0;                                  // a first call that only sizes the text
+        za_vk_to_solidity(vk.data(), counts[0], names.data(), names.size(), nullptr, &probe, 0, &need);
         out.resize(need + 1);
         zcheck(za_vk_to_solidity(vk.data(), counts[0], names.data(), names.size(), nullptr, &out[0], out.size(), &need), "generate_solidity");
         out.resize(strlen(out.c_str()));

@@ -451,6 +451,15 @@ def prove_h_device(ctx, circuit, d_witness, d_h):
     check(lib().za_prove_h_device(ctx.h, circuit.h, ctypes.c_void_p(d_witness), ctypes.c_void_p(d_h)))
 
 
+def set_h_scatter(ctx, outs, his):
+    """Destinations of the next prove_h_device on ctx: h[k] goes to outs[j] + 32 k for the first j with k < his[j]
+    (device pointers, possibly of peer devices; za_ctx_set_h_scatter)."""
+    n = len(outs)
+    po = (ctypes.c_void_p * max(n, 1))(*[ctypes.c_void_p(int(o)) for o in outs])
+    ph = (ctypes.c_uint64 * max(n, 1))(*[int(x) for x in his])
+    check(lib().za_ctx_set_h_scatter(ctx.h, n, po, ph))
+
+
 def prove_msm_partials(ctx, params, circuit, d_witness, d_h, rank, world):
     """Stage 2 (every GPU): the eight multiexps over this rank's point range -> PARTIALS_BYTES record."""
     out = np.zeros(PARTIALS_BYTES, np.uint8)
