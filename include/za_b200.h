@@ -185,6 +185,19 @@ int za_pk_partition(za_ctx *ctx, za_pk *pk, const za_circuit *circuit, int rank,
 int za_share_weighted(uint64_t count, int rank, int world, uint32_t rank0_weight_permille, uint64_t *lo, uint64_t *hi);
 int za_pk_partition_weighted(za_ctx *ctx, za_pk *pk, const za_circuit *circuit, int rank, int world,
                              uint32_t rank0_weight_permille);
+/* Explicit point ranges instead of (rank, world): this device adds up [lo[q], hi[q]) of query q, q = 0 H (over the m - 1
+ * coefficients), 1 L (over the aux), 2 A (over the A exponent list: all inputs, then the aux of a_aux_density), 3 B in G1,
+ * 4 B in G2 (both over the B exponent list).  Builds the fixed-base tables of exactly these ranges; afterwards the rank /
+ * world arguments of za_prove_msm_enqueue / _partials are ignored for this key.  A proof is the sum of the partial records of
+ * any set of devices whose ranges tile every query.  lo = hi = NULL: back to the whole queries.
+ * za_prover_plan: the ranges za_prover gives each of n_devices devices (lo_out / hi_out: 5 entries per device): the four
+ * witness queries laid end to end in units of estimated time and cut into ONE contiguous piece per device (a device then
+ * runs one or two long multiexps instead of a slice of all five), H split evenly, device 0 (which runs the H pipeline
+ * first) a shorter piece. */
+int za_pk_partition_ranges(za_ctx *ctx, za_pk *pk, const za_circuit *circuit, const uint64_t *lo, const uint64_t *hi);
+int za_prover_plan(const za_circuit *circuit, int n_devices, uint64_t *lo_out, uint64_t *hi_out);
+/* the same from the five query lengths (H, L, A, B, B) and the domain size alone: host only, no device needed */
+int za_prover_plan_counts(const uint64_t *counts, uint64_t domain, int n_devices, uint64_t *lo_out, uint64_t *hi_out);
 int za_prove_h_device(za_ctx *ctx, const za_circuit *circuit, const void *d_witness, void *d_h);
 /* Destinations of the NEXT za_prove_h_device on this context: h[k] is stored at (char *)outs[j] + 32 k for the first j with
  * k < his[j] (the last part takes the rest) instead of d_h.  outs[j] may be memory of a peer device this context's device

@@ -16,7 +16,13 @@ circ = za_b200.Circuit(ctx, ni, na, ptr, var, coeff)
 pk = za_b200.Parameters.synthetic(ctx, counts["ic"], counts["h"], counts["l"], counts["a"], counts["b_g1"], counts["b_g2"])
 rho = 0.115
 w0 = max(0.05, min(1.0, (1.0 - rho * (world - 1)) / (1.0 + rho))) if world > 1 else 1.0
-pk.partition(circ, rank, world, w0)
+plan = os.environ.get("ZA_SHARD_PLAN")          # "1": the device `rank` of za_prover_plan(world) instead of the weighted slices
+if plan:
+    lo, hi = za_b200.prover_plan(circ, world)[rank]
+    pk.partition_ranges(circ, lo, hi)
+    print("plan ranges", lo, hi, flush=True)
+else:
+    pk.partition(circ, rank, world, w0)
 wit = torch.from_numpy(np.concatenate([inputs, aux])).cuda()
 h = torch.from_numpy(synthetic.random_scalars(1 << log_m, 5)).cuda()
 torch.cuda.synchronize()
@@ -24,7 +30,9 @@ ctx.profile(True)
 ts = []
 for i in range(8):
     torch.cuda.synchronize(); t = time.perf_counter()
-    za_b200.prove_msm_partials(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), rank, world)
+    za_b200.prove_msm_enqueue(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), rank, world, za_b200.MSM_WITNESS)
+    za_b200.prove_msm_enqueue(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), rank, world, za_b200.MSM_H)
+    za_b200.prove_msm_collect(ctx)
     torch.cuda.synchronize(); ts.append((time.perf_counter() - t) * 1e3)
     if i == 2: ctx.profile_read()
 prof = ctx.profile_read()

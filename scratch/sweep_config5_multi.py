@@ -82,7 +82,8 @@ def sweep(N, lg, reference):
 
 print("| log2 n | GPUs | table c (per device) | G1 MSM ms (uniform 253-bit) | Mpts/s | witness-like ms | Mpts/s | sum equals 1-GPU result |")
 print("|---|---|---|---|---|---|---|---|")
-for lg in range(min_log, max_log + 1, 2):
+sizes = [int(x) for x in os.environ['ZA_SWEEP_SIZES'].split(',')] if os.environ.get('ZA_SWEEP_SIZES') else list(range(min_log, max_log + 1, 2))
+for lg in sizes:
     ref = None
     for N in Ns:
         out, c, ok = sweep(N, lg, ref)

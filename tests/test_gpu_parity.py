@@ -413,6 +413,26 @@ def test_staged_prove_equals_single_call(ctx):
             za_b200.prove_msm_enqueue(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), k, world, za_b200.MSM_H)
             parts.append(za_b200.prove_msm_collect(ctx))
         assert za_b200.prove_assemble(pk, np.stack(parts), 5, 6) == ref, (world, w0)
+    # explicit query ranges (za_pk_partition_ranges) with the plans za_prover makes (za_prover_plan): the witness queries
+    # cut as one work line, one contiguous piece per device — emulated device by device on this GPU
+    counts = {"h": m - 1, "l": na}
+    for world in (2, 3, 5, 8):
+        plans = za_b200.prover_plan(circ, world)
+        for q in range(5):                                   # the ranges tile every query
+            ivs = sorted((lo[q], hi[q]) for lo, hi in plans if hi[q] > lo[q])
+            assert ivs and ivs[0][0] == 0 and all(a[1] == b[0] for a, b in zip(ivs, ivs[1:]))
+        assert sorted(hi[0] for lo, hi in plans)[-1] == m - 1 and sorted(hi[1] for lo, hi in plans)[-1] == na
+        parts = []
+        for lo, hi in plans:
+            pk.partition_ranges(circ, lo, hi)
+            za_b200.prove_msm_enqueue(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), 0, 1, za_b200.MSM_WITNESS)
+            za_b200.prove_msm_enqueue(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), 0, 1, za_b200.MSM_H)
+            parts.append(za_b200.prove_msm_collect(ctx))
+        assert za_b200.prove_assemble(pk, np.stack(parts), 5, 6) == ref, world
+    with pytest.raises(za_b200.ZaError):                     # a range beyond its query
+        pk.partition_ranges(circ, [0, 0, 0, 0, 0], [m, 0, 0, 0, 0])
+    pk.partition_ranges(circ)                                # the whole queries again
+    assert za_b200.create_proof_device(ctx, pk, circ, wit.data_ptr(), 5, 6) == ref
     with pytest.raises(za_b200.ZaError):                     # collect without the H multiexp enqueued
         za_b200.prove_msm_enqueue(ctx, pk, circ, wit.data_ptr(), h.data_ptr(), 0, 2, za_b200.MSM_WITNESS)
         za_b200.prove_msm_collect(ctx)

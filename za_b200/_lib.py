@@ -79,6 +79,9 @@ SYMBOLS = {
     "za_circuit_info": (ci, [vp, vp]),
     "za_pk_partition": (ci, [vp, vp, vp, ci, ci]),
     "za_pk_partition_weighted": (ci, [vp, vp, vp, ci, ci, ctypes.c_uint32]),
+    "za_pk_partition_ranges": (ci, [vp, vp, vp, vp, vp]),
+    "za_prover_plan": (ci, [vp, ci, vp, vp]),
+    "za_prover_plan_counts": (ci, [vp, ctypes.c_uint64, ci, vp, vp]),
     "za_share_weighted": (ci, [ctypes.c_uint64, ci, ci, ctypes.c_uint32, vp, vp]),
     "za_prove_msm_enqueue": (ci, [vp, vp, vp, vp, vp, ci, ci, ci]),
     "za_prove_msm_collect": (ci, [vp, vp]),

@@ -29,7 +29,13 @@ struct Pk {
     std::vector<G1Affine> ic;
     std::unique_ptr<Bases> h, l, a, b_g1, b_g2;
     uint32_t rank0_weight = 1000;   // per mille: rank 0's share of the witness multiexps relative to the other ranks
+    // Explicit point ranges of this device (za_pk_partition_ranges): which part of each of the five queries it adds up.
+    // Order: H (over m - 1 coefficients), L (over the aux), A (over the A exponent list), B in G1, B in G2 (both over the B
+    // exponent list).  Not set: the ranges follow (rank, world, rank0_weight) of the call.
+    bool plan_set = false;
+    size_t plan_lo[5] = {0, 0, 0, 0, 0}, plan_hi[5] = {0, 0, 0, 0, 0};
 };
+enum { Q_H = 0, Q_L = 1, Q_A = 2, Q_B1 = 3, Q_B2 = 4 };
 
 
 // ------------------------------------------------------------------ circuit (R1CS on device)

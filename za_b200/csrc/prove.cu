@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "api_internal.cuh"
 #include "objects.cuh"
+#include <math.h>
 #include <string.h>
 #include <stdlib.h>
 #include <memory>
@@ -603,18 +604,39 @@ static void check_query_lengths(const Pk* pk, const Circuit* c, size_t m) {
 // uses).  Five multiexps are in flight: H, L, A, B(G1), B(G2) — the last two share one digit sort.  Each query
 // is cut by point range across ranks.
 enum { MSM_WITNESS = 1, MSM_H = 2 };     // za_prove_msm_enqueue `which`
+// The point ranges of the five queries this device adds up: the key's explicit plan (za_pk_partition_ranges) or, without
+// one, the (weighted) contiguous shares of `rank` of `world`.
+struct QueryRanges { size_t lo[5], hi[5]; };
+static QueryRanges query_ranges(const Pk* pk, const Circuit* c, size_t m, int rank, int world) {
+    QueryRanges q;
+    if (pk->plan_set) {
+        for (int i = 0; i < 5; i++) { q.lo[i] = pk->plan_lo[i]; q.hi[i] = pk->plan_hi[i]; }
+        return q;
+    }
+    const uint32_t w0 = world > 1 ? pk->rank0_weight : 1000u;
+    share(m - 1, rank, world, q.lo[Q_H], q.hi[Q_H]);
+    share_weighted(c->na, rank, world, w0, q.lo[Q_L], q.hi[Q_L]);
+    share_weighted(c->a_cat_total, rank, world, w0, q.lo[Q_A], q.hi[Q_A]);
+    share_weighted(c->b_cat_total, rank, world, w0, q.lo[Q_B1], q.hi[Q_B1]);
+    q.lo[Q_B2] = q.lo[Q_B1]; q.hi[Q_B2] = q.hi[Q_B1];
+    return q;
+}
 static void prove_msms_enqueue(Ctx* ctx, const Pk* pk, const Circuit* c, const uint8_t* d_wit, const Fr* d_h, int rank, int world,
                                int which = MSM_WITNESS | MSM_H) {
     const uint32_t ni = c->ni, na = c->na;
     const size_t m = domain_size(c, nullptr);
     check_query_lengths(pk, c, m);
     const uint8_t* d_aux = d_wit + (size_t)ni * 32;
-    const uint32_t w0 = world > 1 ? pk->rank0_weight : 1000u;
+    const QueryRanges qr = query_ranges(pk, c, m, rank, world);
     size_t lo, hi;
     if (which & MSM_WITNESS) {
         // G2 first: its (longest) bucket reduction then overlaps the G1 accumulations on the side stream
-        share_weighted(c->b_cat_total, rank, world, w0, lo, hi);
+        lo = qr.lo[Q_B1]; hi = qr.hi[Q_B1];
+        const size_t lo2 = qr.lo[Q_B2], hi2 = qr.hi[Q_B2];
+        const bool same_b = lo2 == lo && hi2 == hi;
         const uint32_t* sb = gather_range(ctx, d_wit, c->b_cat_idx, c->b_cat_total, lo, hi, ctx->scratch[13]);
+        // B in G2 over a different range than B in G1 (explicit plans): its exponents are gathered on their own
+        const uint32_t* sb2 = same_b ? sb : gather_range(ctx, d_wit, c->b_cat_idx, c->b_cat_total, lo2, hi2, ctx->scratch[15]);
         // The G2 multiexp goes to its own (high-priority) stream.  Its kernels hold 2 CTAs of 190+ registers per SM and
         // are latency bound (8 warps/SM, multiply pipe ~60 % busy); the registers they leave fit exactly one CTA of the
         // G1 accumulation, so the G1 multiexps on the main stream run next to it and fill the pipe
@@ -636,9 +658,7 @@ static void prove_msms_enqueue(Ctx* ctx, const Pk* pk, const Circuit* c, const u
         // reduction chain instead of three of each — when all three ranges have fixed-base tables of the same window layout
         // (pk_build_tables chooses the window jointly for exactly that reason).  ZA_MSM_MERGE=0: three multiexps as before.
         static const bool merge_on = !(getenv("ZA_MSM_MERGE") && atoi(getenv("ZA_MSM_MERGE")) == 0) && !(getenv("ZA_MSM_ACC_SM") && atoi(getenv("ZA_MSM_ACC_SM")) == 0);
-        size_t l_lo, l_hi, a_lo, a_hi;
-        share_weighted(na, rank, world, w0, l_lo, l_hi);
-        share_weighted(c->a_cat_total, rank, world, w0, a_lo, a_hi);
+        const size_t l_lo = qr.lo[Q_L], l_hi = qr.hi[Q_L], a_lo = qr.lo[Q_A], a_hi = qr.hi[Q_A];
         const Affine<Fq>* tb = table_for<Fq>(pk->b_g1.get(), lo, hi - lo);
         const Affine<Fq>* tl = table_for<Fq>(pk->l.get(), l_lo, l_hi - l_lo);
         const Affine<Fq>* ta = table_for<Fq>(pk->a.get(), a_lo, a_hi - a_lo);
@@ -658,28 +678,35 @@ static void prove_msms_enqueue(Ctx* ctx, const Pk* pk, const Circuit* c, const u
         // same bucket layout: with a fixed-base table on one side only (the G2 table is twice the size and may be over
         // the memory cap when the G1 table is not) or tables of different window sizes, G2 sorts for itself.
         int share = -1;
-        if (hi - lo > 64) {
+        if (same_b && hi - lo > 64) {
             const bool t1 = table_for<Fq>(pk->b_g1.get(), lo, hi - lo) != nullptr, t2 = table_for<Fq2>(pk->b_g2.get(), lo, hi - lo) != nullptr;
             if (t1 == t2 && (!t1 || (pk->b_g1->tab_c == pk->b_g2->tab_c && pk->b_g1->tab_W == pk->b_g2->tab_W))) share = 3;
         }
         if (!g2_inline) ctx->stream = ctx->g2_stream;
-        try { multiexp_enqueue<Fq2>(ctx, 4, pk->b_g2.get(), lo, sb + lo * 8, hi - lo, share); }
+        try { multiexp_enqueue<Fq2>(ctx, 4, pk->b_g2.get(), lo2, sb2 + lo2 * 8, hi2 - lo2, share); }
         catch (...) { ctx->stream = main_st; throw; }
         ctx->stream = main_st;
     }
     if ((which & MSM_H) && (which & MSM_WITNESS)) {
-        share(m - 1, rank, world, lo, hi);
+        lo = qr.lo[Q_H]; hi = qr.hi[Q_H];
         multiexp_enqueue<Fq>(ctx, 0, pk->h.get(), lo, (const uint32_t*)(d_h + lo), hi - lo);
     }
     if ((which & MSM_WITNESS) && !ctx->witness_merged) {
-        share_weighted(na, rank, world, w0, lo, hi);
+        lo = qr.lo[Q_L]; hi = qr.hi[Q_L];
         multiexp_enqueue<Fq>(ctx, 1, pk->l.get(), lo, (const uint32_t*)(d_aux + lo * 32), hi - lo);
-        share_weighted(c->a_cat_total, rank, world, w0, lo, hi);
+        lo = qr.lo[Q_A]; hi = qr.hi[Q_A];
         const uint32_t* sa = gather_range(ctx, d_wit, c->a_cat_idx, c->a_cat_total, lo, hi, ctx->scratch[12]);
         multiexp_enqueue<Fq>(ctx, 2, pk->a.get(), lo, sa + lo * 8, hi - lo);
     }
     if ((which & MSM_H) && !(which & MSM_WITNESS)) {
-        share(m - 1, rank, world, lo, hi);
+        lo = qr.lo[Q_H]; hi = qr.hi[Q_H];
+        // ZA_H_AFTER_G2=1: the H multiexp starts behind the G2 accumulation of this device instead of next to it, so that
+        // the (long, latency-bound) G2 bucket reduction runs under the H accumulation instead of after it
+        // (measured per device of an 8-GPU plan: 4.47 -> 4.25 ms, 4 GPUs: 7.33 -> 7.02; on ONE GPU, where the G1 multiexps
+        // fill the card next to G2, it costs 0.4 ms — so it follows the explicit plan of a multi-device key unless set)
+        static const int h_after_env = getenv("ZA_H_AFTER_G2") ? atoi(getenv("ZA_H_AFTER_G2")) : -1;
+        const bool h_after_g2 = h_after_env >= 0 ? h_after_env != 0 : pk->plan_set;
+        if (h_after_g2 && ctx->slots[4].busy && ctx->slots[4].kind == 2 && ctx->slots[4].acc_done) ZA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->slots[4].acc_done, 0));
         multiexp_enqueue<Fq>(ctx, 0, pk->h.get(), lo, (const uint32_t*)(d_h + lo), hi - lo);
     }
 }
@@ -1039,21 +1066,206 @@ Prover::~Prover() {
     for (int k = 0; k < (int)ctx.size(); k++) if (ctx[k]) za_ctx_destroy(ctx[k]);
 }
 
+// Which part of which query every device adds up (one proof = the sum over the devices).
+// Round 1 gave every device one (weighted) slice of EVERY query: five short multiexps per device, each with its own sort,
+// launch chain and bucket-reduction tail — on 8 GPUs one rank's share took 5.3 ms of which about 3 ms were bulk work
+// (profiles/r02_shards.md).  The plan below works on estimated time instead (a cost model, ms per 2^20 points on B200:
+// H pipeline hp, G1 multiexp g1, G2 multiexp g2, plus a latency-bound tail per device after its last accumulation):
+//   * devices 1 .. n2 are "pure G2" devices: they split the front of the B (G2) query evenly and run nothing else — the G2
+//     kernels do not share an SM well with anything (§4.4 of DESIGN.md), and the h exponents they would have to wait for
+//     do not exist before hp;
+//   * the other devices share what is left of B (G2), then B (G1), A and L laid end to end (one contiguous piece each, so a
+//     device touches one or two queries with long ranges) and the H query, each in proportion to the time it has: device 0
+//     runs the H pipeline first and gets less;
+//   * n2 and the common finish time T are found by trying every n2 and bisecting T.
+// ZA_PROVER_COSTS="hp,g1,g2,tail_g1,tail_g2" overrides the model (defaults 2.1, 3.7, 9.5, 0.8, 1.3: a device's share of a
+// query costs more per point than the whole query — smaller window, shorter waves);
+// ZA_PROVER_PLAN=0 restores the slices, ZA_PROVER_PLAN=1 the first version of the line (no pure G2 devices, H split evenly).
+struct DevicePlan { size_t lo[5], hi[5]; };
+struct PlanModel { double hp = 2.1, g1 = 3.7, g2 = 9.5, t1 = 0.8, t2 = 1.3; };      // fitted to profiles/r02_shards.md (per-device times of the plan)
+static PlanModel plan_model() {
+    PlanModel pm;
+    if (const char* e = getenv("ZA_PROVER_COSTS")) {
+        double v[5];
+        const int n = sscanf(e, "%lf,%lf,%lf,%lf,%lf", &v[0], &v[1], &v[2], &v[3], &v[4]);
+        if (n >= 3 && v[0] >= 0 && v[1] > 0 && v[2] > 0) { pm.hp = v[0]; pm.g1 = v[1]; pm.g2 = v[2]; }
+        if (n == 5 && v[3] >= 0 && v[4] >= 0) { pm.t1 = v[3]; pm.t2 = v[4]; }
+    }
+    return pm;
+}
+// cut `cnt` items of a query that occupies [start, start + len) of a line at position x
+static size_t line_index(double start, double len, size_t cnt, double x) {
+    if (len <= 0 || x <= start) return 0;
+    if (x >= start + len) return cnt;
+    const size_t v = (size_t)((x - start) / len * (double)cnt);
+    return v > cnt ? cnt : v;
+}
+static std::vector<DevicePlan> prover_make_plans_v1(const size_t* cnt, size_t m, int N);
+static std::vector<DevicePlan> prover_make_plans(const size_t* cnt, size_t m, int N) {
+    static const int version = getenv("ZA_PROVER_PLAN") ? atoi(getenv("ZA_PROVER_PLAN")) : 2;
+    if (version == 1 || N < 2) return prover_make_plans_v1(cnt, m, N);
+    const PlanModel pm = plan_model();
+    const double unit = 1.0 / 1048576.0, scale = (double)m * unit;          // tails and the pipeline scale with the domain
+    const double c_b2 = pm.g2 * cnt[Q_B2] * unit, c_b1 = pm.g1 * cnt[Q_B1] * unit, c_a = pm.g1 * cnt[Q_A] * unit, c_l = pm.g1 * cnt[Q_L] * unit;
+    const double c_h = pm.g1 * cnt[Q_H] * unit, hp = pm.hp * scale, t1 = pm.t1 * scale, t2 = pm.t2 * scale;
+    const double w_g1 = c_b1 + c_a + c_l;
+    struct Trial { double T; int n2; double pure; };        // pure: bulk of B (G2) on each pure device
+    // shared devices in line order: n2 + 1, ..., N - 1, 0
+    auto line_order = [&](int n2) { std::vector<int> o; for (int k = n2 + 1; k < N; k++) o.push_back(k); o.push_back(0); return o; };
+    // capacities (time left for witness + H work) of the shared devices if everything is to finish by T: T minus the tail of
+    // the device's last multiexp (the G2 tail for every device whose piece of the line reaches into B (G2): found by
+    // iterating, the pieces depend on the capacities) minus the H pipeline on device 0
+    auto shared_caps = [&](double T, int n2, double g2_left, std::vector<double>& cap) -> double {
+        const std::vector<int> order = line_order(n2);
+        std::vector<double> tail(N, t1);
+        double total = 0;
+        for (int it = 0; it < 4; it++) {
+            cap.assign(N, 0.0);
+            total = 0;
+            for (int k : order) { const double v = T - tail[k] - (k == 0 ? hp : 0.0); cap[k] = v > 0 ? v : 0; total += cap[k]; }
+            if (total <= 0 || g2_left <= 0) break;
+            const double w_line = g2_left + w_g1;
+            double x = 0;
+            for (int k : order) { tail[k] = x < g2_left - 1e-12 && cap[k] > 0 ? t2 : t1; x += w_line * cap[k] / total; }
+        }
+        return total;
+    };
+    Trial best{1e300, 0, 0};
+    std::vector<double> cap;
+    for (int n2 = 0; n2 <= N - 2; n2++) {
+        double lo = 0, hi = hp + c_b2 + w_g1 + c_h + t1 + t2 + 1.0;
+        for (int it = 0; it < 60; it++) {
+            const double T = 0.5 * (lo + hi);
+            double pure = n2 ? std::min(std::max(T - t2, 0.0), c_b2 / n2) : 0.0;
+            const double g2_left = c_b2 - n2 * pure;
+            const double need = g2_left + w_g1 + c_h;
+            const double total = shared_caps(T, n2, g2_left, cap);
+            bool ok = total >= need;
+            // a device other than 0 must have witness work until the h exponents exist (its H share would idle otherwise)
+            if (ok && c_h > 0) {
+                const double frac_w = (g2_left + w_g1) / need;
+                for (int k = 1; k < N && ok; k++) if (cap[k] > 0 && cap[k] * frac_w < hp * 0.9) ok = false;
+            }
+            if (ok) hi = T; else lo = T;
+        }
+        if (hi < best.T - 1e-9) { best.T = hi; best.n2 = n2; best.pure = n2 ? std::min(std::max(hi - t2, 0.0), c_b2 / n2) : 0.0; }
+    }
+    const int n2 = best.n2;
+    const double g2_pure_total = n2 * best.pure, g2_left = c_b2 - g2_pure_total;
+    shared_caps(best.T, n2, g2_left, cap);
+    double cap_total = 0; for (int k = 0; k < N; k++) cap_total += cap[k];
+    // H ranges go in device order (0 first): the scatter of the last NTT pass needs ascending bounds
+    const std::vector<int> order = line_order(n2);
+    const double w_line = g2_left + w_g1;                       // the shared witness line: [rest of B2 | B1 | A | L]
+    const double st_b2 = -g2_pure_total, st_b1 = g2_left, st_a = st_b1 + c_b1, st_l = st_a + c_a;      // B2 starts before 0: its front is the pure part
+    std::vector<double> bound(order.size() + 1, 0.0);
+    for (size_t i = 0; i < order.size(); i++) bound[i + 1] = bound[i] + (cap_total > 0 ? w_line * cap[order[i]] / cap_total : 0.0);
+    bound[order.size()] = w_line;
+    const double qs[3] = {st_b1, st_a, st_l}, ql[3] = {c_b1, c_a, c_l};
+    const size_t qc[3] = {cnt[Q_B1], cnt[Q_A], cnt[Q_L]};
+    for (size_t i = 1; i < order.size(); i++)                   // no slivers (a piece has a fixed cost): snap to query ends within 8 %
+        for (int q = 0; q < 3; q++) {
+            const double thr = 0.08 * pm.g1 * qc[q] * unit;
+            if (fabs(bound[i] - qs[q]) < thr) bound[i] = qs[q];
+            if (fabs(bound[i] - (qs[q] + ql[q])) < thr) bound[i] = qs[q] + ql[q];
+        }
+    std::vector<DevicePlan> plans(N);
+    for (int k = 0; k < N; k++) for (int i = 0; i < 5; i++) { plans[k].lo[i] = 0; plans[k].hi[i] = 0; }
+    for (int j = 1; j <= n2; j++) {                             // pure devices: even pieces of the front of B (G2)
+        plans[j].lo[Q_B2] = line_index(st_b2, c_b2, cnt[Q_B2], st_b2 + (j - 1) * best.pure);
+        plans[j].hi[Q_B2] = line_index(st_b2, c_b2, cnt[Q_B2], st_b2 + j * best.pure);
+    }
+    const size_t b2_pure_end = n2 ? plans[n2].hi[Q_B2] : 0;
+    for (size_t i = 0; i < order.size(); i++) {
+        DevicePlan& d = plans[order[i]];
+        const double x0 = bound[i], x1 = bound[i + 1];
+        const bool last = i + 1 == order.size();
+        d.lo[Q_B2] = std::max(b2_pure_end, line_index(st_b2, c_b2, cnt[Q_B2], x0));
+        d.hi[Q_B2] = last ? cnt[Q_B2] : std::max(d.lo[Q_B2], line_index(st_b2, c_b2, cnt[Q_B2], x1));
+        if (i == 0) d.lo[Q_B2] = b2_pure_end;
+        const int qq[3] = {Q_B1, Q_A, Q_L};
+        for (int q = 0; q < 3; q++) {
+            d.lo[qq[q]] = line_index(qs[q], ql[q], qc[q], x0);
+            d.hi[qq[q]] = last ? qc[q] : line_index(qs[q], ql[q], qc[q], x1);
+            if (d.hi[qq[q]] < d.lo[qq[q]]) d.hi[qq[q]] = d.lo[qq[q]];
+        }
+    }
+    // H in proportion to the same capacities, in device order
+    {
+        double acc = 0;
+        size_t prev = 0;
+        for (int k = 0; k < N; k++) {
+            acc += cap[k];
+            size_t hi = cap_total > 0 ? (size_t)((double)cnt[Q_H] * (acc / cap_total)) : (k == N - 1 ? cnt[Q_H] : 0);
+            if (k == N - 1 || hi > cnt[Q_H]) hi = cnt[Q_H];
+            if (hi < prev) hi = prev;
+            plans[k].lo[Q_H] = prev; plans[k].hi[Q_H] = hi;
+            prev = hi;
+        }
+        // the last device with a share takes the rounding rest
+        for (int k = N - 1; k >= 0; k--) if (cap[k] > 0) { for (int j = k; j < N; j++) { plans[j].hi[Q_H] = cnt[Q_H]; if (j > k) plans[j].lo[Q_H] = cnt[Q_H]; } break; }
+    }
+    return plans;
+}
+static std::vector<DevicePlan> prover_make_plans_v1(const size_t* cnt, size_t m, int N) {
+    double hp = 2.0, g1 = 3.0, g2 = 8.3;
+    if (const char* e = getenv("ZA_PROVER_COSTS")) { double a, b, d; if (sscanf(e, "%lf,%lf,%lf", &a, &b, &d) == 3 && a >= 0 && b > 0 && d > 0) { hp = a; g1 = b; g2 = d; } }
+    const int line[4] = {Q_B2, Q_B1, Q_A, Q_L};                     // order on the work line
+    double len[4], start[4], total = 0;
+    for (int i = 0; i < 4; i++) { len[i] = (line[i] == Q_B2 ? g2 : g1) * (double)cnt[line[i]]; start[i] = total; total += len[i]; }
+    const double c_h = g1 * (double)cnt[Q_H], c_pipe = hp * (double)m;
+    // every device: h share c_h / N; device 0 additionally the pipeline; equal finish times
+    double w0 = (c_pipe + total + c_h) / N - c_pipe - c_h / N;
+    if (w0 < 0) w0 = 0;
+    if (N == 1) w0 = total;
+    const double wk = N > 1 ? (total - w0) / (N - 1) : 0;
+    std::vector<double> bound(N + 1, 0.0);                          // device k >= 1 owns [bound[k-1], bound[k]); device 0 the rest
+    for (int k = 1; k < N; k++) bound[k] = bound[k - 1] + wk;
+    bound[N] = total;
+    // no slivers: a cut closer than 8 % of a G1 query's time to an end of a query moves to that end (a piece has a fixed cost of
+    // a few hundred microseconds: sort, launch chain, reduction tail)
+    for (int k = 1; k < N; k++)
+        for (int i = 0; i < 4; i++) {
+            if (len[i] <= 0) continue;
+            const double thr = 0.08 * g1 * (double)cnt[line[i]];        // 8 % of a G1 query of that length, also for the G2 query
+            if (fabs(bound[k] - start[i]) < thr) bound[k] = start[i];
+            if (fabs(bound[k] - (start[i] + len[i])) < thr) bound[k] = start[i] + len[i];
+        }
+    auto index_at = [&](int i, double x, bool last) -> size_t {
+        const size_t n = cnt[line[i]];
+        if (last || x >= start[i] + len[i]) return n;
+        if (x <= start[i] || len[i] <= 0) return 0;
+        size_t v = (size_t)((x - start[i]) / len[i] * (double)n);
+        return v > n ? n : v;
+    };
+    std::vector<DevicePlan> plans(N);
+    for (int k = 0; k < N; k++) {
+        DevicePlan& d = plans[k];
+        share(cnt[Q_H], k, N, d.lo[Q_H], d.hi[Q_H]);
+        const double x0 = k == 0 ? bound[N - 1] : bound[k - 1], x1 = k == 0 ? bound[N] : bound[k];
+        for (int i = 0; i < 4; i++) {
+            d.lo[line[i]] = index_at(i, x0, false);
+            d.hi[line[i]] = index_at(i, x1, k == 0);
+            if (d.hi[line[i]] < d.lo[line[i]]) d.hi[line[i]] = d.lo[line[i]];
+        }
+        if (N == 1) for (int i = 0; i < 5; i++) { d.lo[i] = 0; d.hi[i] = cnt[i]; }
+    }
+    return plans;
+}
+
 // witness positions device k reads: the aux range of its L share and the spans of its A and B index ranges (merged)
 static void prover_plan_spans(Prover* P) {
     const Circuit* c = P->circ[0]->c.get();
+    const size_t m = domain_size(c, nullptr);
     P->spans.assign(P->n, {});
     for (int k = 0; k < P->n; k++) {
         std::vector<std::pair<size_t, size_t>> iv;
         if (k == 0) { iv.push_back({0, (size_t)c->ni + c->na}); P->spans[k] = iv; continue; }      // device 0 evaluates the constraints
-        const uint32_t w0 = P->rank0_weight;
-        size_t lo, hi;
-        share_weighted(c->na, k, P->n, w0, lo, hi);
-        if (hi > lo) iv.push_back({c->ni + lo, c->ni + hi});
-        share_weighted(c->a_cat_total, k, P->n, w0, lo, hi);
-        if (hi > lo) iv.push_back({c->h_a_cat[lo], (size_t)c->h_a_cat[hi - 1] + 1});
-        share_weighted(c->b_cat_total, k, P->n, w0, lo, hi);
-        if (hi > lo) iv.push_back({c->h_b_cat[lo], (size_t)c->h_b_cat[hi - 1] + 1});
+        const QueryRanges q = query_ranges(P->pk[k]->p.get(), c, m, k, P->n);
+        if (q.hi[Q_L] > q.lo[Q_L]) iv.push_back({c->ni + q.lo[Q_L], c->ni + q.hi[Q_L]});
+        if (q.hi[Q_A] > q.lo[Q_A]) iv.push_back({c->h_a_cat[q.lo[Q_A]], (size_t)c->h_a_cat[q.hi[Q_A] - 1] + 1});
+        if (q.hi[Q_B1] > q.lo[Q_B1]) iv.push_back({c->h_b_cat[q.lo[Q_B1]], (size_t)c->h_b_cat[q.hi[Q_B1] - 1] + 1});
+        if (q.hi[Q_B2] > q.lo[Q_B2]) iv.push_back({c->h_b_cat[q.lo[Q_B2]], (size_t)c->h_b_cat[q.hi[Q_B2] - 1] + 1});
         std::sort(iv.begin(), iv.end());
         std::vector<std::pair<size_t, size_t>> merged;
         for (auto& x : iv) {
@@ -1116,18 +1328,17 @@ static void prover_device_step(Prover* P, int k, uint64_t gen, const uint8_t* in
                 const bool direct = !force_copy && P->peers_mapped && n <= ZA_H_SCATTER_MAX && log_m > 11;
                 if (direct) {
                     cx->h_scatter.n = n;
-                    for (int j = 0; j < n; j++) {
-                        size_t lo, hi;
-                        share(m - 1, j, n, lo, hi);
+                    for (int j = 0; j < n; j++) {                  // the plan's H ranges ascend with the device index
+                        const QueryRanges qj = query_ranges(P->pk[j]->p.get(), c, m, j, n);
                         cx->h_scatter.out[j] = P->h[j].as<Fr>();
-                        cx->h_scatter.hi[j] = (uint32_t)hi;
+                        cx->h_scatter.hi[j] = (uint32_t)qj.hi[Q_H];
                     }
                 }
                 try { prove_h(cx, c, d_wit, d_h, nullptr); } catch (...) { cx->h_scatter.n = 0; throw; }
                 cx->h_scatter.n = 0;
                 for (int j = 1; j < n; j++) {
-                    size_t lo, hi;
-                    share(m - 1, j, n, lo, hi);
+                    const QueryRanges qj = query_ranges(P->pk[j]->p.get(), c, m, j, n);
+                    const size_t lo = qj.lo[Q_H], hi = qj.hi[Q_H];
                     if (!direct && hi > lo) ZA_CUDA(cudaMemcpyPeerAsync(P->h[j].as<Fr>() + lo, P->devices[j], d_h + lo, P->devices[0], (hi - lo) * sizeof(Fr), cx->stream));
                     ZA_CUDA(cudaEventRecord(P->h_ready[j], cx->stream));
                 }
@@ -1227,10 +1438,26 @@ static void prover_finish_setup(Prover* P) {
         P->rank0_weight = (uint32_t)(w * 1000.0 + 0.5);
         if (P->rank0_weight < 1) P->rank0_weight = 1;
     } else P->rank0_weight = 1000;
+    static const bool use_plan = !(getenv("ZA_PROVER_PLAN") && atoi(getenv("ZA_PROVER_PLAN")) == 0);
+    std::vector<DevicePlan> plans;
+    if (P->n > 1 && use_plan) {
+        const size_t qcnt[5] = {m - 1, c0->na, c0->a_cat_total, c0->b_cat_total, c0->b_cat_total};
+        plans = prover_make_plans(qcnt, m, P->n);
+        const double l0 = (double)(plans[0].hi[Q_L] - plans[0].lo[Q_L]) + (plans[0].hi[Q_A] - plans[0].lo[Q_A]) + (plans[0].hi[Q_B1] - plans[0].lo[Q_B1]) +
+                          2.8 * (double)(plans[0].hi[Q_B2] - plans[0].lo[Q_B2]);
+        const double l1 = (double)(plans[1].hi[Q_L] - plans[1].lo[Q_L]) + (plans[1].hi[Q_A] - plans[1].lo[Q_A]) + (plans[1].hi[Q_B1] - plans[1].lo[Q_B1]) +
+                          2.8 * (double)(plans[1].hi[Q_B2] - plans[1].lo[Q_B2]);
+        P->rank0_weight = (uint32_t)std::max(1.0, std::min(1000.0, l1 > 0 ? 1000.0 * l0 / l1 : 1000.0));      // reported by za_prover_info only
+    }
     prover_run_all(P, [&](int k) {
         ZA_CUDA(cudaSetDevice(P->devices[k]));
         const Circuit* c = P->circ[k]->c.get();
-        if (P->n > 1) {
+        if (P->n > 1 && use_plan) {
+            uint64_t lo[5], hi[5];
+            for (int i = 0; i < 5; i++) { lo[i] = plans[k].lo[i]; hi[i] = plans[k].hi[i]; }
+            int rc = za_pk_partition_ranges(P->ctx[k], P->pk[k], P->circ[k], lo, hi);
+            if (rc != ZA_OK) throw ZaError(rc, last_error());
+        } else if (P->n > 1) {
             int rc = za_pk_partition_weighted(P->ctx[k], P->pk[k], P->circ[k], k, P->n, P->rank0_weight);
             if (rc != ZA_OK) throw ZaError(rc, last_error());
         } else check_query_lengths(P->pk[k]->p.get(), c, m);
@@ -1482,6 +1709,7 @@ int za_pk_partition_weighted(za_ctx* ctx, za_pk* pk, const za_circuit* circuit, 
     const size_t m = domain_size(c, nullptr);
     check_query_lengths(p, c, m);
     p->rank0_weight = rank0_weight_permille;
+    p->plan_set = false;
     const uint32_t w0 = world > 1 ? rank0_weight_permille : 1000u;
     size_t lo, hi;
     share(m - 1, rank, world, lo, hi); bases_build_table(&ctx->c, p->h.get(), lo, hi - lo);
@@ -1490,6 +1718,56 @@ int za_pk_partition_weighted(za_ctx* ctx, za_pk* pk, const za_circuit* circuit, 
     share_weighted(c->a_cat_total, rank, world, w0, lo, hi); los[1] = lo; ns[1] = hi - lo;
     share_weighted(c->b_cat_total, rank, world, w0, lo, hi); los[2] = lo; ns[2] = hi - lo;
     pk_build_witness_tables(&ctx->c, p, los, ns);
+    return ZA_OK;
+    ZA_CATCH
+}
+int za_pk_partition_ranges(za_ctx* ctx, za_pk* pk, const za_circuit* circuit, const uint64_t* lo, const uint64_t* hi) {
+    if (!ctx || !pk || !circuit) return fail(ZA_ERR_INVALID, "NULL argument");
+    ZA_TRY
+    ZA_CUDA(cudaSetDevice(ctx->c.device));
+    Pk* p = pk->p.get();
+    const Circuit* c = circuit->c.get();
+    const size_t m = domain_size(c, nullptr);
+    check_query_lengths(p, c, m);
+    if (!lo || !hi) {                               // back to the whole queries
+        p->plan_set = false;
+        return za_pk_partition_weighted(ctx, pk, circuit, 0, 1, 1000);
+    }
+    const size_t total[5] = {m - 1, c->na, c->a_cat_total, c->b_cat_total, c->b_cat_total};
+    for (int i = 0; i < 5; i++)
+        if (lo[i] > hi[i] || hi[i] > total[i]) return fail(ZA_ERR_INVALID, "za_pk_partition_ranges: range %d is [%llu, %llu) of %zu", i, (unsigned long long)lo[i], (unsigned long long)hi[i], total[i]);
+    for (int i = 0; i < 5; i++) { p->plan_lo[i] = (size_t)lo[i]; p->plan_hi[i] = (size_t)hi[i]; }
+    p->plan_set = true;
+    bases_build_table(&ctx->c, p->h.get(), p->plan_lo[Q_H], p->plan_hi[Q_H] - p->plan_lo[Q_H]);
+    // L, A and B (G1) get a joint window when their ranges are of similar size (pk_build_witness_tables); B (G2) follows
+    // the B (G1) window when it covers the same range (shared digit sort) and gets its own otherwise
+    size_t los[3] = {p->plan_lo[Q_L], p->plan_lo[Q_A], p->plan_lo[Q_B1]};
+    size_t ns[3] = {p->plan_hi[Q_L] - p->plan_lo[Q_L], p->plan_hi[Q_A] - p->plan_lo[Q_A], p->plan_hi[Q_B1] - p->plan_lo[Q_B1]};
+    pk_build_witness_tables(&ctx->c, p, los, ns);
+    if (p->plan_lo[Q_B2] != p->plan_lo[Q_B1] || p->plan_hi[Q_B2] != p->plan_hi[Q_B1])
+        bases_build_table(&ctx->c, p->b_g2.get(), p->plan_lo[Q_B2], p->plan_hi[Q_B2] - p->plan_lo[Q_B2]);
+    return ZA_OK;
+    ZA_CATCH
+}
+int za_prover_plan(const za_circuit* circuit, int n_devices, uint64_t* lo_out, uint64_t* hi_out) {
+    if (!circuit || !lo_out || !hi_out || n_devices < 1 || n_devices > 64) return fail(ZA_ERR_INVALID, "bad argument");
+    ZA_TRY
+    const Circuit* c = circuit->c.get();
+    const size_t m = domain_size(c, nullptr);
+    const size_t qcnt[5] = {m - 1, c->na, c->a_cat_total, c->b_cat_total, c->b_cat_total};
+    const std::vector<DevicePlan> plans = prover_make_plans(qcnt, m, n_devices);
+    for (int k = 0; k < n_devices; k++)
+        for (int i = 0; i < 5; i++) { lo_out[5 * k + i] = plans[k].lo[i]; hi_out[5 * k + i] = plans[k].hi[i]; }
+    return ZA_OK;
+    ZA_CATCH
+}
+int za_prover_plan_counts(const uint64_t* counts, uint64_t domain, int n_devices, uint64_t* lo_out, uint64_t* hi_out) {
+    if (!counts || !lo_out || !hi_out || n_devices < 1 || n_devices > 64 || domain < 2) return fail(ZA_ERR_INVALID, "bad argument");
+    ZA_TRY
+    const size_t qcnt[5] = {(size_t)counts[0], (size_t)counts[1], (size_t)counts[2], (size_t)counts[3], (size_t)counts[4]};
+    const std::vector<DevicePlan> plans = prover_make_plans(qcnt, (size_t)domain, n_devices);
+    for (int k = 0; k < n_devices; k++)
+        for (int i = 0; i < 5; i++) { lo_out[5 * k + i] = plans[k].lo[i]; hi_out[5 * k + i] = plans[k].hi[i]; }
     return ZA_OK;
     ZA_CATCH
 }

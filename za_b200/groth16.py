@@ -219,6 +219,15 @@ class Parameters:
         w = max(1, min(1000, int(round(rank0_weight * 1000))))
         check(lib().za_pk_partition_weighted(self.ctx.h, self.h, circuit.h, rank, world, w))
 
+    def partition_ranges(self, circuit, lo=None, hi=None):
+        """Explicit point ranges [lo[q], hi[q]) of the five queries (H, L, A, B in G1, B in G2) for this device
+        (za_pk_partition_ranges); None = the whole queries again."""
+        if lo is None:
+            check(lib().za_pk_partition_ranges(self.ctx.h, self.h, circuit.h, None, None))
+            return
+        a = (ctypes.c_uint64 * 5)(*[int(x) for x in lo]); b = (ctypes.c_uint64 * 5)(*[int(x) for x in hi])
+        check(lib().za_pk_partition_ranges(self.ctx.h, self.h, circuit.h, a, b))
+
     def counts(self):
         c = (ctypes.c_uint32 * 6)()
         check(lib().za_pk_counts(self.h, c))
@@ -488,6 +497,21 @@ def prove_assemble(params, partials, r, s):
     proof = np.zeros(256, np.uint8)
     check(lib().za_prove_assemble(params.h, _p(partials), partials.shape[0], _p(_scalar(r)), _p(_scalar(s)), _p(proof)))
     return proof.tobytes()
+
+
+def prover_plan(circuit, n_devices):
+    """The query ranges za_prover gives each device: list of (lo[5], hi[5]) (za_prover_plan)."""
+    lo = (ctypes.c_uint64 * (5 * n_devices))(); hi = (ctypes.c_uint64 * (5 * n_devices))()
+    check(lib().za_prover_plan(circuit.h, n_devices, lo, hi))
+    return [(list(lo[5 * k:5 * k + 5]), list(hi[5 * k:5 * k + 5])) for k in range(n_devices)]
+
+
+def prover_plan_counts(counts, domain, n_devices):
+    """prover_plan from the five query lengths (H, L, A, B in G1, B in G2) and the domain size; host only."""
+    c = (ctypes.c_uint64 * 5)(*[int(x) for x in counts])
+    lo = (ctypes.c_uint64 * (5 * n_devices))(); hi = (ctypes.c_uint64 * (5 * n_devices))()
+    check(lib().za_prover_plan_counts(c, int(domain), n_devices, lo, hi))
+    return [(list(lo[5 * k:5 * k + 5]), list(hi[5 * k:5 * k + 5])) for k in range(n_devices)]
 
 
 def share(count, rank, world):
