@@ -81,6 +81,7 @@ struct MsmSlot {
     DevBuf red;                          // row / column bucket reduction: stage buffers, row sums, six results per bucket space
     int red_mode = 0, red_k = 0;         // 1: row / column reduction (K6'), host_win holds 6 points per bucket space
     uint32_t red_H = 0, red_Lw = 0;
+    int red_sR = 0, red_sC = 0;          // K6'c: the row / column arrays are split once more; the host scales the outer part by 2^shift
     DevBuf pair_pts[2], pair_offs;       // batched-affine pair rounds: ping-pong point buffers, per-round bucket offsets
     int rounds = 0;
     void* host_win = nullptr;            // pinned: window sums (+ entry count when profiling)

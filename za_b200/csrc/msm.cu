@@ -1129,6 +1129,61 @@ __global__ void __launch_bounds__(256, 1) msm_small_weighted_kernel(const XYZZ<F
     }
 }
 
+// K6'c: the same weighted sums with a shorter chain.  The array of n = a x b points (b = min(32, n) the low index bits) is
+// itself reduced by rows and columns: sum_i i X_i = b * sum_hi hi R_hi + sum_lo lo C_lo with R_hi = sum_lo X, C_lo = sum_hi X.
+// First kernel: one WARP per row sum and per column sum (a + b <= 64 warps per array, five shuffle steps each).  Second
+// kernel: one warp per weighted sum of <= 32 points (suffix scan + reduction, ten steps).  Fifteen dependent additions
+// instead of the ~27 of msm_small_weighted_kernel (which took 1.0 ms over Fq2 — the largest part of the tail behind a G2
+// multiexp).  Results per array: out3[0] = sum_lo lo C_lo, out3[1] = U = sum of all points, out3[2] = sum_hi hi R_hi; the
+// host adds 2^log2(b) * out3[2] (msm_finish).
+template <class F>
+__global__ void __launch_bounds__(128) msm_w2d_sums_kernel(const XYZZ<F>* __restrict__ inR, uint32_t nR, const XYZZ<F>* __restrict__ inC, uint32_t nC,
+                                                           uint32_t Wr, XYZZ<F>* tmp /* 64 per array */) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // global warp
+    const uint32_t arr = gw >> 6, o = gw & 63;
+    if (arr >= 2 * Wr) return;
+    const bool is_c = arr >= Wr;
+    const uint32_t w = is_c ? arr - Wr : arr;
+    const uint32_t n = is_c ? nC : nR;
+    if (n == 0) return;
+    const XYZZ<F>* in = is_c ? inC + (size_t)w * nC : inR + (size_t)w * nR;
+    const uint32_t b = n < 32 ? n : 32, a = n / b;
+    if (o >= a + b) return;
+    XYZZ<F> v = XYZZ<F>::inf();
+    if (o < a) { if (lane < b) v = ld_vec(in + (size_t)o * b + lane); }             // row sum R_o
+    else { const uint32_t lo = o - a; if (lane < a) v = ld_vec(in + (size_t)lane * b + lo); }      // column sum C_lo
+    v = warp_reduce_xyzz<F>(v, lane);
+    if (lane == 0) st_vec(tmp + (size_t)arr * 64 + o, v);
+}
+template <class F>
+__global__ void __launch_bounds__(64) msm_w2d_final_kernel(const XYZZ<F>* __restrict__ tmp, uint32_t nR, uint32_t nC, uint32_t Wr, XYZZ<F>* out3) {
+    const uint32_t arr = blockIdx.x;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;      // warp 0: rows (and U), warp 1: columns
+    const bool is_c = arr >= Wr;
+    const uint32_t n = is_c ? nC : nR;
+    if (n == 0) {
+        if (threadIdx.x < 3) st_vec(out3 + (size_t)arr * 3 + threadIdx.x, XYZZ<F>::inf());
+        return;
+    }
+    const uint32_t b = n < 32 ? n : 32, a = n / b;
+    const uint32_t cnt = warp == 0 ? a : b;
+    const XYZZ<F>* src = tmp + (size_t)arr * 64 + (warp == 0 ? 0 : a);
+    XYZZ<F> S = lane < cnt ? ld_vec(src + lane) : XYZZ<F>::inf();
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {                       // suffix sums S_j = sum_{j' >= j} Y_j'
+        XYZZ<F> o = shfl_down_xyzz<F>(S, d, lane, 32);
+        xyzz_add<F>(S, o);
+    }
+    const XYZZ<F> U = S;                                     // lane 0: the sum of all
+    XYZZ<F> t = lane >= 1 ? S : XYZZ<F>::inf();              // sum_j j Y_j = sum_{j >= 1} S_j
+    t = warp_reduce_xyzz<F>(t, lane);
+    if (lane == 0) {
+        st_vec(out3 + (size_t)arr * 3 + (warp == 0 ? 2 : 0), t);
+        if (warp == 0) st_vec(out3 + (size_t)arr * 3 + 1, U);
+    }
+}
+
 // Small inputs (public-input queries have a handful of points): thread per point, double-and-add,
 // then a single-warp tree.  Also an independent on-device check of the bucket pipeline (tests).
 template <class F>
@@ -1664,7 +1719,7 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
             const uint32_t fan = (fan_env == 2 || fan_env == 4 || fan_env == 8) ? fan_env : 4u;      // measured 8 / 4 / 2: G2 reduction 1.98 / 1.89 / 1.85 ms, G1 0.77 / 0.71 / 0.71
             const size_t stage_elems = (size_t)Wr * (B / fan > Lw ? B / fan : Lw);
             const size_t r_elems = H > 1 ? (size_t)Wr * H : 0;
-            sl.red.ensure((4 * stage_elems + r_elems + (size_t)6 * Wr) * sizeof(XYZZ<F>));
+            sl.red.ensure((4 * stage_elems + r_elems + (size_t)6 * Wr + (size_t)128 * Wr) * sizeof(XYZZ<F>));      // ... + 64 partial sums per array (K6'c)
             XYZZ<F>* d_stage[2] = {sl.red.as<XYZZ<F>>(), sl.red.as<XYZZ<F>>() + stage_elems};
             XYZZ<F>* d_rstage[2] = {d_stage[1] + stage_elems, d_stage[1] + 2 * stage_elems};
             XYZZ<F>* d_r = d_rstage[1] + stage_elems;
@@ -1714,8 +1769,20 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
                 d_c = cur;
                 ZA_CUDA(cudaStreamWaitEvent(side, sl.red_join, 0));
             }
-            msm_small_weighted_kernel<F><<<2 * Wr, 256, 0, side>>>(d_r, H > 1 ? H : 0, d_c, Lw, (uint32_t)Wr, d_out3);
-            ctx->launches++;
+            static const bool w2d = !(getenv("ZA_MSM_W2D") && atoi(getenv("ZA_MSM_W2D")) == 0);
+            sl.red_sR = sl.red_sC = 0;
+            if (w2d) {
+                XYZZ<F>* d_tmp = d_out3 + (size_t)6 * Wr;
+                const uint32_t warps = 2u * (uint32_t)Wr * 64u;
+                msm_w2d_sums_kernel<F><<<nblk((size_t)warps * 32, 128), 128, 0, side>>>(d_r, H > 1 ? H : 0, d_c, Lw, (uint32_t)Wr, d_tmp);
+                msm_w2d_final_kernel<F><<<2 * Wr, 64, 0, side>>>(d_tmp, H > 1 ? H : 0, Lw, (uint32_t)Wr, d_out3);
+                ctx->launches += 2;
+                auto lg_b = [](uint32_t n) { int s = 0; const uint32_t b = n < 32 ? n : 32; while ((1u << s) < b) s++; return s; };
+                sl.red_sR = H > 1 ? lg_b(H) : 0; sl.red_sC = lg_b(Lw);
+            } else {
+                msm_small_weighted_kernel<F><<<2 * Wr, 256, 0, side>>>(d_r, H > 1 ? H : 0, d_c, Lw, (uint32_t)Wr, d_out3);
+                ctx->launches++;
+            }
             sl.red_k = (int)k; sl.red_H = H; sl.red_Lw = Lw;
             d_win = d_out3;
             win_points = 6 * (size_t)Wr;
@@ -1790,16 +1857,19 @@ XYZZ<F> msm_finish(Ctx* ctx, int slot_id, XYZZ<F>* parts_out) {
     // row / column reduction: the six partial results of bucket space w -> sum_b (b + 1) S_b  (K6')
     std::vector<XYZZ<F>> spaces;
     if (sl.red_mode == 1) {
-        auto weighted = [](const XYZZ<F>* o, uint32_t, bool plus_one) {          // sum_i i X_i (+ sum_i X_i)
-            XYZZ<F> r = o[0];
+        // o[0] + 2^shift o[2] = sum_i i X_i (K6'c splits the array once more; shift = 0 and o[2] = infinity otherwise), o[1] = sum_i X_i
+        auto weighted = [](const XYZZ<F>* o, int shift, bool plus_one) {
+            XYZZ<F> r = o[2];
+            for (int k = 0; k < shift; k++) r = xyzz_dbl<F>(r);
+            xyzz_add<F>(r, o[0]);
             if (plus_one) xyzz_add<F>(r, o[1]);
             return r;
         };
         spaces.resize(sl.W);
         for (int w = 0; w < sl.W; w++) {
-            XYZZ<F> t = weighted(win + 3 * (size_t)(sl.W + w), sl.red_Lw, true);
+            XYZZ<F> t = weighted(win + 3 * (size_t)(sl.W + w), sl.red_sC, true);
             if (sl.red_H > 1) {
-                XYZZ<F> hi = weighted(win + 3 * (size_t)w, sl.red_H, false);
+                XYZZ<F> hi = weighted(win + 3 * (size_t)w, sl.red_sR, false);
                 for (int k = 0; k < sl.red_k; k++) hi = xyzz_dbl<F>(hi);
                 xyzz_add<F>(t, hi);
             }
