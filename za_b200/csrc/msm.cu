@@ -1945,12 +1945,17 @@ template void xyzz_normalise<Fq2>(Ctx*, const XYZZ<Fq2>*, Affine<Fq2>*, size_t);
 template <class F>
 void bases_table_build(Ctx* ctx, const Affine<F>* d_pts, size_t n, int c, int W, Affine<F>* d_table) {
     if (!n) return;
-    const size_t total = n * (size_t)W;
-    DevBuf tmp(total * sizeof(XYZZ<F>));
-    bases_table_kernel<F><<<nblk(n, 128), 128, 0, ctx->stream>>>(d_pts, n, c, W, tmp.as<XYZZ<F>>());
-    size_t threads = (total + GEN_CHUNK - 1) / GEN_CHUNK;
-    bases_gen_normalise_kernel<F><<<nblk(threads, 128), 128, 0, ctx->stream>>>(tmp.as<XYZZ<F>>(), d_table, total);
-    ctx->launches += 2;
+    // in pieces of 2^21 points: the projective staging buffer is twice the size of the table part it becomes (a 2^26-point
+    // table is 56 GB; staged in one piece it needed 168 GB)
+    const size_t piece = (size_t)1 << 21;
+    DevBuf tmp(std::min(n, piece) * (size_t)W * sizeof(XYZZ<F>));
+    for (size_t i0 = 0; i0 < n; i0 += piece) {
+        const size_t ni = std::min(piece, n - i0), total = ni * (size_t)W;
+        bases_table_kernel<F><<<nblk(ni, 128), 128, 0, ctx->stream>>>(d_pts + i0, ni, c, W, tmp.as<XYZZ<F>>());
+        size_t threads = (total + GEN_CHUNK - 1) / GEN_CHUNK;
+        bases_gen_normalise_kernel<F><<<nblk(threads, 128), 128, 0, ctx->stream>>>(tmp.as<XYZZ<F>>(), d_table + i0 * (size_t)W, total);
+        ctx->launches += 2;
+    }
     ZA_CUDA(cudaGetLastError());
     ZA_CUDA(cudaStreamSynchronize(ctx->stream));
 }

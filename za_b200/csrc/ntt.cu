@@ -196,6 +196,139 @@ __global__ void __launch_bounds__(256, ZA_NTT_MINB) ntt_pass_kernel(NttPass p) {
     }
 }
 
+// ---- the same pass with the tile's butterflies working OUT OF shared memory -----------------------------------------------
+// ntt_pass_kernel keeps 8 elements (64 registers) per thread and needs 118-128 registers: two CTAs = 15 warps per SM, where a
+// chain of field products reaches ~0.6 of the integer pipe (profiles/r02_ntt.md).  Here a butterfly loads its two operands
+// and its twiddle, and stores its two results, through one non-inlined routine (LDS.128 / STS.128 on the otherwise idle LSU,
+// the scheme of msm_accumulate_g1_sm_kernel): ~80 registers, three CTAs = 24 warps per SM.  Same tile geometry, same rounds
+// (a thread still owns 8 elements for up to three stages, so there is one barrier per round, not per stage), same fused
+// first-load / last-store work, bit-identical results.  Shared-memory layout: the low and the high 16 bytes of element l
+// in two planes (a warp's LDS.128 over consecutive l is conflict free), l swizzled by its own bits 3..5 so that the last
+// rounds (a thread's 8 elements adjacent: stride-8 accesses across the warp) are conflict free as well.
+static __device__ __forceinline__ uint32_t ntt_phys(uint32_t l) { return l ^ ((l >> 3) & 7u); }
+static __device__ __forceinline__ Fr ntt_sm_ld(uint32_t base, uint32_t plane, uint32_t l) {
+    const uint32_t a = base + ntt_phys(l) * 16u;
+    Fr r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]) : "r"(a) : "memory");
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "r"(a + plane) : "memory");
+    return r;
+}
+static __device__ __forceinline__ void ntt_sm_st(uint32_t base, uint32_t plane, uint32_t l, const Fr& r) {
+    const uint32_t a = base + ntt_phys(l) * 16u;
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a + plane), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7]) : "memory");
+}
+// one butterfly in place: (a, b) <- (a + b, (a - b) w)   [inverse: (b - a) w: the sign of w^-e = -w^(N/2 - e)];  w == nullptr: no product
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ void ntt_bfly_sm(uint32_t base, uint32_t plane, uint32_t la, uint32_t lb, const Fr* w, int inverse) {
+    const Fr a = ntt_sm_ld(base, plane, la), b = ntt_sm_ld(base, plane, lb);
+    ntt_sm_st(base, plane, la, a + b);
+    if (!w) { ntt_sm_st(base, plane, lb, a - b); return; }
+    const Fr d = inverse ? b - a : a - b;
+    ntt_sm_st(base, plane, lb, d * ldg_fr(w));
+}
+#else
+static inline void ntt_bfly_sm(uint32_t, uint32_t, uint32_t, uint32_t, const Fr*, int) {}
+#endif
+
+#ifndef ZA_NTT_SM_MINB
+#define ZA_NTT_SM_MINB 3
+#endif
+template <bool LAST>
+__global__ void __launch_bounds__(256, ZA_NTT_SM_MINB) ntt_pass_sm_kernel(NttPass p) {
+    extern __shared__ uint4 smem_raw[];
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const int n = p.n, lo = p.lo, K = p.K, LOGT = p.LOGT, L = K + LOGT;
+    const uint32_t plane = (16u << L);
+    const unsigned t = threadIdx.x, nthreads = blockDim.x;
+    const size_t blk = blockIdx.x;
+    const Fr* in = p.in + (size_t)blockIdx.y * p.batch_stride;
+    Fr* out = p.out + (size_t)blockIdx.y * p.batch_stride;
+    const size_t half_n = (size_t)1 << (n - 1);
+    size_t g_base;
+    if (!LAST) {
+        const int s = lo - LOGT;
+        size_t blo = blk & (((size_t)1 << s) - 1), bhi = blk >> s;
+        g_base = (bhi << (lo + K)) | (blo << LOGT);
+    } else {
+        g_base = blk << K;
+    }
+    auto gidx = [&](unsigned l) -> size_t {
+        if (!LAST) return g_base | ((size_t)(l >> LOGT) << lo) | (l & ((1u << LOGT) - 1));
+        return g_base | ((size_t)(l >> K) << (n - LOGT)) | (l & ((1u << K) - 1));
+    };
+    const int tshift = LAST ? 0 : LOGT;
+    // the tile into shared memory (fused first-load work as in ntt_pass_kernel)
+#pragma unroll 1
+    for (unsigned l = t; l < (1u << L); l += nthreads) {
+        const size_t g = gidx(l);
+        Fr x = ld_fr(in + g);
+        if (p.first && p.pre) x = x * ldg_fr(p.pre + g);
+        if (p.first && p.mul_b) x = (x * ldg_fr(p.mul_b + (size_t)blockIdx.y * p.batch_stride + g) - ldg_fr(p.sub_c + (size_t)blockIdx.y * p.batch_stride + g)) * ldg_fr(p.pre_const);
+        ntt_sm_st(base, plane, l, x);
+    }
+    __syncthreads();
+    bool first_round = true;
+    for (int top = K; top > 0;) {
+        const int nb = first_round ? (K - 1) % 3 + 1 : 3;
+        const int rb = top - nb;
+        const int wb = nb < 3 ? top - 3 : rb;
+        const int pbit = wb + tshift;
+        const unsigned lbase = ((t >> pbit) << (pbit + 3)) | (t & ((1u << pbit) - 1));
+        const bool fixed8 = LAST && rb == 0 && nb == 3;          // the constant 8-point network on the three lowest bits
+        const size_t e8 = (size_t)1 << (n - 3);
+#pragma unroll 1
+        for (int k = 0; k < nb; k++) {
+            const unsigned bitj = 4u >> k;                       // the stage pairs the elements whose 3-bit index differs in this bit
+            const int b = lo + wb + 2 - k;
+#pragma unroll 1
+            for (unsigned q = 0; q < 4; q++) {
+                // q enumerates the 3-bit indices j with bit `bitj` clear
+                const unsigned j = bitj == 4u ? q : bitj == 2u ? ((q & 2u) << 1) | (q & 1u) : q << 1;
+                const unsigned la = lbase | (j << pbit), lb = lbase | ((j | bitj) << pbit);
+                const Fr* w;
+                if (fixed8) {
+                    // stage 0: w8^j for the pair (j, j + 4); stage 1: 1, w4 by bit 0 of the pair's position; stage 2: all 1
+                    const unsigned ex = k == 0 ? j : k == 1 ? (j & 1u) * 2u : 0u;       // exponent in units of N / 8
+                    w = ex ? p.tw + (p.inverse ? half_n - ex * e8 : ex * e8) : nullptr;
+                } else {
+                    const size_t i0 = gidx(la);
+                    const size_t e = (i0 & (((size_t)1 << b) - 1)) << (n - b - 1);
+                    w = p.tw + (p.inverse ? half_n - e : e);
+                }
+                ntt_bfly_sm(base, plane, la, lb, w, p.inverse);
+            }
+        }
+        __syncthreads();
+        top = rb;
+        first_round = false;
+    }
+    if (!LAST) {
+#pragma unroll 1
+        for (unsigned l = t; l < (1u << L); l += nthreads) st_fr(out + gidx(l), ntt_sm_ld(base, plane, l));
+    } else {
+        const int nblkbits = n - K - LOGT;
+        const size_t blk_rev = nblkbits ? (size_t)(__brevll((unsigned long long)blk) >> (64 - nblkbits)) : 0;
+#pragma unroll 1
+        for (unsigned o = t; o < (1u << L); o += nthreads) {
+            unsigned cp = o & ((1u << LOGT) - 1), kp = o >> LOGT;
+            unsigned col = LOGT ? (__brev(cp) >> (32 - LOGT)) : 0;
+            unsigned kap = __brev(kp) >> (32 - K);
+            size_t kidx = ((size_t)kp << (n - K)) | (blk_rev << LOGT) | cp;
+            Fr v = ntt_sm_ld(base, plane, (col << K) | kap);
+            if (p.post) v = v * ldg_fr(p.post + kidx);
+            else if (p.post_const) v = v * ldg_fr(p.post_const);
+            Fr* dst = out;
+            if (p.sc.n) {
+                int j = 0;
+                while (j + 1 < p.sc.n && kidx >= p.sc.hi[j]) j++;
+                dst = p.sc.out[j];
+            }
+            st_fr(dst + kidx, v);
+        }
+    }
+}
+
 // N <= 4: the definition, one thread per output
 __global__ void ntt_tiny_kernel(const Fr* in, Fr* out, size_t batch_stride, const Fr* tw, const Fr* pre, const Fr* post,
                                 const Fr* post_const, int n, int inverse) {
@@ -363,6 +496,8 @@ static void ntt_run(Ctx* ctx, Fr* buf, Fr* scratch, int n, int batch, size_t str
     if (!ctx->ntt_attr_set) {          // per device: a context belongs to one device, a process may hold several contexts
         ZA_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_L) * 32));
         ZA_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_L) * 32));
+        ZA_CUDA(cudaFuncSetAttribute(ntt_pass_sm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_L) * 32));
+        ZA_CUDA(cudaFuncSetAttribute(ntt_pass_sm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_L) * 32));
         ctx->ntt_attr_set = true;
     }
     if (n < 3) {
@@ -403,7 +538,11 @@ static void ntt_run(Ctx* ctx, Fr* buf, Fr* scratch, int n, int batch, size_t str
         dim3 grid((unsigned)(N >> L), batch);
         unsigned threads = 1u << (L - 3);
         size_t smem = ((size_t)1 << L) * sizeof(Fr);
-        if (last) ntt_pass_kernel<true><<<grid, threads, smem, ctx->stream>>>(p);
+        static const bool use_sm = getenv("ZA_NTT_SM") && atoi(getenv("ZA_NTT_SM")) != 0;
+        if (use_sm) {
+            if (last) ntt_pass_sm_kernel<true><<<grid, threads, smem, ctx->stream>>>(p);
+            else ntt_pass_sm_kernel<false><<<grid, threads, smem, ctx->stream>>>(p);
+        } else if (last) ntt_pass_kernel<true><<<grid, threads, smem, ctx->stream>>>(p);
         else ntt_pass_kernel<false><<<grid, threads, smem, ctx->stream>>>(p);
         ctx->launches++;
         ZA_CUDA(cudaGetLastError());
