@@ -910,6 +910,241 @@ __global__ void __launch_bounds__(LPK_NT, 4) msm_pair_round_g2lp_kernel(const Af
 // by one thread; long chains (one bucket holding a large share of all entries — witness vectors full of
 // ones) are queued and folded warp-cooperatively by msm_fixup_long_kernel.
 #define FIXUP_SHORT 6
+// K5a'' — the single-thread pair rounds over Fq2 with the WORKING SET IN SHARED MEMORY.
+// msm_pair_round_kernel<Fq2> needs 224 registers: two CTAs = 8 warps per SM, `wait` stalls with nothing else to issue and a
+// fifth of the time in long-scoreboard stalls behind the gathers (profiles/r02_g2_lanepair.md).  The lane-pair kernel above
+// bought 16 warps with 4 wide products per Fq2 product and an inversion per 512 outputs, and lost.  This kernel keeps one
+// thread per output stream (3 wide products per Fq2 product, one inversion per 1024 outputs) and moves the six Fq2 values a
+// thread works on into shared memory, the scheme of msm_accumulate_g1_sm_kernel: the Fq2 product, the squaring and the
+// inversion are non-inlined routines that take shared-memory addresses (LDS.128 into the registers they read, STS.128 from
+// the registers they produce, no argument marshalling), so the kernel body holds addresses and counters only: <= 128
+// registers, 48 KB per CTA, four CTAs = 16 warps per SM.  Prefix products and operand indices stay in local memory as before.
+#define G2SM_NT 128
+// operands of a later output on their way while the current one is computed.  With four CTAs of 48 KB the L1 that is left
+// (~64 KB for 512 threads x 2 points x 128 B) does not hold them: ZA_G2SM_PF = 1 / 2 prefetches into L2, one / two outputs ahead
+#ifndef ZA_G2SM_PF
+#define ZA_G2SM_PF 0
+#endif
+#define G2SM_PF_AHEAD (ZA_G2SM_PF == 2 ? 2u : 1u)
+static __device__ __forceinline__ void g2sm_prefetch(const void* p) {
+#if ZA_G2SM_PF == 0
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+enum { GV_I = 0, GV_P, GV_D, GV_X, GV_N, GV_A, GV_COUNT };      // Fq2 slots, see the kernel
+#define G2SM_BYTES (GV_COUNT * 64 * G2SM_NT)
+static_assert(G2SM_NT == ACC_SM_NT, "sm_ld / sm_st address the second half of a value ACC_SM_NT * 16 bytes further");
+#define G2SM_C1 (2u * G2SM_NT * 16u)                            /* from the c0 component of a slot to its c1 component */
+static __device__ __forceinline__ Fq2 g2sm_ld(uint32_t a) { Fq2 r; r.c0 = sm_ld(a); r.c1 = sm_ld(a + G2SM_C1); return r; }
+static __device__ __forceinline__ void g2sm_st(uint32_t a, const Fq2& v) { sm_st(a, v.c0); sm_st(a + G2SM_C1, v.c1); }
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ void fq2_mul_sm(uint32_t d, uint32_t a, uint32_t b) { g2sm_st(d, fq2_mul_lazy(g2sm_ld(a), g2sm_ld(b))); }
+static __device__ __noinline__ void fq2_sqr_sm(uint32_t d, uint32_t a) {
+    const Fq2 v = g2sm_ld(a);
+    Fq2 r;
+    r.c0 = fp_mul<FqParams>(v.c0 + v.c1, v.c0 - v.c1);
+    r.c1 = dbl(fp_mul<FqParams>(v.c0, v.c1));
+    g2sm_st(d, r);
+}
+static __device__ __noinline__ void fq2_inv_sm(uint32_t d, uint32_t a) {          // once per thread and round
+    const Fq2 v = g2sm_ld(a);
+    const Fq n = fp_inv_kaliski<FqParams>(fp_sqr<FqParams>(v.c0) + fp_sqr<FqParams>(v.c1));
+    Fq2 r;
+    r.c0 = fp_mul<FqParams>(v.c0, n);
+    r.c1 = -fp_mul<FqParams>(v.c1, n);
+    g2sm_st(d, r);
+}
+// the rare operands of the forward pass (equal x, or a coordinate that is zero): classify, and for a doubling put 2 y into slot d
+static __device__ __noinline__ uint32_t g2sm_classify(const Affine<Fq2>* pts, uint32_t r0, uint32_t r1, uint32_t d_slot) {
+    const Fq2 x0 = ldg_vec(&pair_ptr<Fq2>(pts, r0)->x), x1 = ldg_vec(&pair_ptr<Fq2>(pts, r1)->x);
+    Fq2 y0 = ldg_vec(&pair_ptr<Fq2>(pts, r0)->y), y1 = ldg_vec(&pair_ptr<Fq2>(pts, r1)->y);
+    if (r0 >> 31) y0 = -y0;
+    if (r1 >> 31) y1 = -y1;
+    const Fq2 d = x1 - x0;
+    if (x0.is_zero() && y0.is_zero()) return PR_COPY1;
+    if (x1.is_zero() && y1.is_zero()) return PR_COPY0;
+    if (d.is_zero()) {
+        if (y0 == y1 && !y0.is_zero()) { g2sm_st(d_slot, dbl(y0)); return PR_DBL; }
+        return PR_INF;
+    }
+    g2sm_st(d_slot, d);
+    return PR_ADD;
+}
+// backward pass, doubling: d = 2 y, num = 3 x^2, xs = 2 x  (slots D, N, X; A = x)
+static __device__ __noinline__ void g2sm_dbl_setup(const Affine<Fq2>* pts, uint32_t r0, uint32_t sD, uint32_t sN, uint32_t sX, uint32_t sA) {
+    const Fq2 ax = ldg_vec(&pair_ptr<Fq2>(pts, r0)->x);
+    Fq2 ay = ldg_vec(&pair_ptr<Fq2>(pts, r0)->y);
+    if (r0 >> 31) ay = -ay;
+    g2sm_st(sA, ax);
+    g2sm_st(sD, dbl(ay));
+    g2sm_st(sX, dbl(ax));
+    fq2_sqr_sm(sN, sA);
+    const Fq2 xx = g2sm_ld(sN);
+    g2sm_st(sN, dbl(xx) + xx);
+}
+#else
+static inline void fq2_mul_sm(uint32_t, uint32_t, uint32_t) {}
+static inline void fq2_sqr_sm(uint32_t, uint32_t) {}
+static inline void fq2_inv_sm(uint32_t, uint32_t) {}
+static inline uint32_t g2sm_classify(const Affine<Fq2>*, uint32_t, uint32_t, uint32_t) { return 0; }
+static inline void g2sm_dbl_setup(const Affine<Fq2>*, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t) {}
+#endif
+
+template <bool FIRST, int LP>
+__global__ void __launch_bounds__(G2SM_NT, 4) msm_pair_round_g2sm_kernel(const Affine<Fq2>* __restrict__ pts, const uint32_t* __restrict__ entries,
+                                                                        const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out,
+                                                                        uint32_t nkeys, Affine<Fq2>* __restrict__ out) {
+    extern __shared__ uint4 g2sm_raw[];
+    const uint32_t n_out = off_out[nkeys];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t cta_first = (uint64_t)blockIdx.x * (G2SM_NT * LP);
+    if (cta_first + (uint64_t)(tid & ~31u) * LP >= n_out) return;       // the whole warp is past the end
+    const uint64_t q0_64 = cta_first + (uint64_t)tid * LP;
+    const uint32_t q0 = (uint32_t)q0_64;
+    const uint32_t cnt = q0_64 < n_out ? (n_out - q0 < (uint32_t)LP ? n_out - q0 : (uint32_t)LP) : 0u;
+    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(g2sm_raw) + tid * 16u;
+    // slot V (an Fq2 value): c0 at sl(V), c1 at sl(V) + G2SM_C1.  I: running product, later the running inverse; P: prefix
+    // product of the output, later 1 / d; D: x difference, later lambda^2, later lambda (ax - rx); X: x sum, later the result's
+    // x; N: numerator, later lambda; A: the first operand's x
+    auto sl = [&](int v) { return sm0 + (uint32_t)v * (2u * G2SM_C1); };
+    uint32_t ref0[LP], ref1[LP];
+    uint8_t flags[LP];
+    Fq2 pre[LP];
+    g2sm_st(sl(GV_I), Fq2::one());
+    if (cnt) {
+        uint32_t lo = 0, hi = nkeys;
+        while (lo + 1 < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (off_out[mid] <= q0) lo = mid; else hi = mid;
+        }
+        uint32_t key = lo;
+        uint32_t obase = off_out[key], oend = off_out[key + 1], ibase = off_in[key], icnt = off_in[key + 1] - ibase;
+#pragma unroll 4
+        for (uint32_t j = 0; j < (uint32_t)LP; j++) {
+            uint32_t r0 = 0, r1 = 0xffffffffu;
+            if (j < cnt) {
+                const uint32_t q = q0 + j;
+                if (q == oend) {
+                    do { key++; } while (off_out[key + 1] <= q);
+                    obase = off_out[key]; oend = off_out[key + 1]; ibase = off_in[key]; icnt = off_in[key + 1] - ibase;
+                }
+                const uint32_t k = q - obase;
+                const uint32_t s0 = ibase + 2 * k;
+                r0 = FIRST ? entries[s0] : s0;
+                if (2 * k + 1 < icnt) r1 = FIRST ? entries[s0 + 1] : s0 + 1;
+            }
+            ref0[j] = r0; ref1[j] = r1;
+        }
+        // ---- forward: running product of the x differences.  Software pipelined: the operand indices (local memory) are
+        // read two outputs ahead and the points of the next output are prefetched while the current product runs
+        uint32_t c0 = ref0[0], c1 = ref1[0];
+        uint32_t n0 = cnt > 1 ? ref0[1] : 0u, n1 = cnt > 1 ? ref1[1] : 0xffffffffu;
+#pragma unroll 1
+        for (uint32_t j = 0; j < cnt; j++) {
+            const uint32_t r0 = c0, r1 = c1;
+            c0 = n0; c1 = n1;
+            if (j + 2 < cnt) { n0 = ref0[j + 2]; n1 = ref1[j + 2]; }
+            if (j + 1 < cnt) {
+                g2sm_prefetch(pair_ptr<Fq2>(pts, c0));
+                if (c1 != 0xffffffffu) g2sm_prefetch(pair_ptr<Fq2>(pts, c1));
+            }
+            uint32_t fl = PR_COPY0;
+            if (r1 != 0xffffffffu) {
+                const Fq2 x0 = ldg_vec(&pair_ptr<Fq2>(pts, r0)->x), x1 = ldg_vec(&pair_ptr<Fq2>(pts, r1)->x);
+                const Fq2 d = x1 - x0;
+                fl = PR_ADD;
+                if (d.is_zero() || x0.is_zero() || x1.is_zero()) fl = g2sm_classify(pts, r0, r1, sl(GV_D));
+                else g2sm_st(sl(GV_D), d);
+                if (fl >= PR_ADD) {
+                    pre[j] = g2sm_ld(sl(GV_I));
+                    fq2_mul_sm(sl(GV_I), sl(GV_I), sl(GV_D));
+                }
+            }
+            flags[j] = (uint8_t)fl;
+        }
+    }
+    // ---- one inversion per warp (as in msm_pair_round_kernel): prefix products in slot P, suffix products in slot X
+    {
+        const unsigned lane = tid & 31;
+        const Fq2 run = g2sm_ld(sl(GV_I));
+        g2sm_st(sl(GV_P), run);
+        g2sm_st(sl(GV_X), run);
+#pragma unroll 1
+        for (int d = 1; d < 32; d <<= 1) {
+            Fq2 up = shfl_up_vec(g2sm_ld(sl(GV_P)), d);
+            if (lane < (unsigned)d) up = Fq2::one();
+            g2sm_st(sl(GV_D), up);
+            Fq2 dn = shfl_down_vec(g2sm_ld(sl(GV_X)), d);
+            if (lane + d >= 32) dn = Fq2::one();
+            g2sm_st(sl(GV_N), dn);
+            fq2_mul_sm(sl(GV_P), sl(GV_P), sl(GV_D));
+            fq2_mul_sm(sl(GV_X), sl(GV_X), sl(GV_N));
+        }
+        g2sm_st(sl(GV_N), shfl_idx_vec(g2sm_ld(sl(GV_P)), 31));
+        fq2_inv_sm(sl(GV_N), sl(GV_N));                                   // the same value in every lane: convergent
+        Fq2 e = shfl_up_vec(g2sm_ld(sl(GV_P)), 1), sfx = shfl_down_vec(g2sm_ld(sl(GV_X)), 1);
+        if (lane == 0) e = Fq2::one();
+        if (lane == 31) sfx = Fq2::one();
+        g2sm_st(sl(GV_D), e);
+        g2sm_st(sl(GV_A), sfx);
+        fq2_mul_sm(sl(GV_I), sl(GV_N), sl(GV_D));
+        fq2_mul_sm(sl(GV_I), sl(GV_I), sl(GV_A));                         // I = 1 / (this lane's product)
+    }
+    if (!cnt) return;
+    // ---- backward, software pipelined the same way (indices and flag two outputs ahead, points and the prefix product of
+    // the next output prefetched)
+    uint32_t b0 = ref0[cnt - 1], b1 = ref1[cnt - 1], bf = flags[cnt - 1];
+    uint32_t m0 = cnt > 1 ? ref0[cnt - 2] : 0u, m1 = cnt > 1 ? ref1[cnt - 2] : 0xffffffffu, mf = cnt > 1 ? flags[cnt - 2] : 0u;
+#pragma unroll 1
+    for (uint32_t j = cnt; j-- > 0;) {
+        const uint32_t r0 = b0, r1 = b1, fl = bf;
+        b0 = m0; b1 = m1; bf = mf;
+        if (j >= 2) { m0 = ref0[j - 2]; m1 = ref1[j - 2]; mf = flags[j - 2]; }
+        if (j >= 1) {
+            g2sm_prefetch(pair_ptr<Fq2>(pts, b0));
+            if (b1 != 0xffffffffu) g2sm_prefetch(pair_ptr<Fq2>(pts, b1));
+            asm volatile("prefetch.L1 [%0];" ::"l"(&pre[j - 1]));      // generic address of the local array
+        }
+        Affine<Fq2> R;
+        if (fl >= PR_ADD) {
+            g2sm_st(sl(GV_P), pre[j]);
+            if (fl == PR_DBL) {
+                g2sm_dbl_setup(pts, r0, sl(GV_D), sl(GV_N), sl(GV_X), sl(GV_A));
+            } else {
+                {
+                    const Fq2 ax = ldg_vec(&pair_ptr<Fq2>(pts, r0)->x), bx = ldg_vec(&pair_ptr<Fq2>(pts, r1)->x);
+                    g2sm_st(sl(GV_D), bx - ax);
+                    g2sm_st(sl(GV_X), ax + bx);
+                    g2sm_st(sl(GV_A), ax);
+                }
+                Fq2 ay = ldg_vec(&pair_ptr<Fq2>(pts, r0)->y), by = ldg_vec(&pair_ptr<Fq2>(pts, r1)->y);
+                if (r0 >> 31) ay = -ay;
+                if (r1 >> 31) by = -by;
+                g2sm_st(sl(GV_N), by - ay);
+            }
+            fq2_mul_sm(sl(GV_P), sl(GV_I), sl(GV_P));                     // 1 / d = I * prefix
+            fq2_mul_sm(sl(GV_I), sl(GV_I), sl(GV_D));                     // I *= d
+            fq2_mul_sm(sl(GV_N), sl(GV_N), sl(GV_P));                     // lambda
+            fq2_sqr_sm(sl(GV_D), sl(GV_N));                               // lambda^2
+            R.x = g2sm_ld(sl(GV_D)) - g2sm_ld(sl(GV_X));
+            g2sm_st(sl(GV_D), g2sm_ld(sl(GV_A)) - R.x);
+            fq2_mul_sm(sl(GV_D), sl(GV_N), sl(GV_D));                     // lambda (ax - rx)
+            Fq2 ay = ldg_vec(&pair_ptr<Fq2>(pts, r0)->y);                 // again (L1): it was not kept across the products
+            if (r0 >> 31) ay = -ay;
+            R.y = g2sm_ld(sl(GV_D)) - ay;
+        } else if (fl == PR_INF) {
+            R = Affine<Fq2>::inf();
+        } else {
+            const uint32_t r = fl == PR_COPY1 ? r1 : r0;
+            R = ldg_vec(pair_ptr<Fq2>(pts, r));
+            if (r >> 31) R.y = -R.y;
+        }
+        st_vec(out + q0 + j, R);
+    }
+}
+
 template <class F>
 __global__ void __launch_bounds__(128) msm_fixup_kernel(const uint32_t* __restrict__ offsets, uint32_t nkeys, uint32_t Lc, uint32_t nchunks,
                                                         const XYZZ<F>* part_head, const XYZZ<F>* part_tail, const uint32_t* tail_owner_key,
@@ -1656,6 +1891,23 @@ void msm_enqueue(Ctx* ctx, int slot_id, const Affine<F>* d_bases, const uint32_t
                     if (r == 0) { if (lp == 64) ZA_LPK_LAUNCH(true, 64); else if (lp == 32) ZA_LPK_LAUNCH(true, 32); else if (lp == 16) ZA_LPK_LAUNCH(true, 16); else ZA_LPK_LAUNCH(true, 8); }
                     else { if (lp == 64) ZA_LPK_LAUNCH(false, 64); else if (lp == 32) ZA_LPK_LAUNCH(false, 32); else if (lp == 16) ZA_LPK_LAUNCH(false, 16); else ZA_LPK_LAUNCH(false, 8); }
 #undef ZA_LPK_LAUNCH
+                    lp_done = true;
+                }
+            }
+            if constexpr (sizeof(F) == sizeof(Fq2)) {
+                // single-thread rounds with the working set in shared memory (K5a''): 16 warps per SM
+                // MEASURED (profiles/r02_g2_lanepair.md): G2 accumulation at 2^20 7.60 -> 7.04 ms, same results; ZA_G2_SM=0 restores
+                // the register-resident rounds
+                static const bool g2sm = !(getenv("ZA_G2_SM") && atoi(getenv("ZA_G2_SM")) == 0);
+                if (g2sm && !lp_done) {
+                    const bool small = pair_lp == 16 || cap < (uint64_t)ctx->sm_count * 4 * G2SM_NT * 32;
+                    const unsigned grid = nblk(cap, G2SM_NT * (small ? 16 : 32));
+                    const Affine<Fq2>* in_pts = cur_pts;
+                    Affine<Fq2>* out_pts = nxt_pts;
+                    if (r == 0) { if (small) msm_pair_round_g2sm_kernel<true, 16><<<grid, G2SM_NT, G2SM_BYTES, st>>>(in_pts, d_entries, cur_off, nxt_off, nkeys, out_pts);
+                                  else msm_pair_round_g2sm_kernel<true, 32><<<grid, G2SM_NT, G2SM_BYTES, st>>>(in_pts, d_entries, cur_off, nxt_off, nkeys, out_pts); }
+                    else { if (small) msm_pair_round_g2sm_kernel<false, 16><<<grid, G2SM_NT, G2SM_BYTES, st>>>(in_pts, nullptr, cur_off, nxt_off, nkeys, out_pts);
+                           else msm_pair_round_g2sm_kernel<false, 32><<<grid, G2SM_NT, G2SM_BYTES, st>>>(in_pts, nullptr, cur_off, nxt_off, nkeys, out_pts); }
                     lp_done = true;
                 }
             }
