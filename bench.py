@@ -252,6 +252,7 @@ def run_gpu(args):
     # event times of the step overlap and are not per-kernel durations.  For the roofline objects the two accumulation
     # kernels are therefore also timed ALONE, in this process, on the same workload size (2^log_m points, fixed-base
     # table, uniform scalars): that duration is what `achieved` uses; the in-step figure is reported beside it.
+    iso_other = {}      # per group: digit sort and bucket reduction of one query-sized multiexp, alone (ms)
     def isolated_accumulation(group):
         n_iso = 1 << log_m
         bases_iso = za_b200.Bases.generate(ctx, group, n_iso, 1)
@@ -266,6 +267,7 @@ def run_gpu(args):
         p_iso = ctx.profile_read()
         ctx.profile(False)
         del bases_iso, sc_iso
+        iso_other[group] = {k: p_iso[k]["ms"] / 5.0 for k in ("msm_sort", "msm_reduce")}
         return p_iso["msm_accumulate_g1" if group == 1 else "msm_accumulate_g2"]
 
     def isolated_ntt():
@@ -353,6 +355,18 @@ def run_gpu(args):
                         "timing": ("the seven transforms of one proof as the H pipeline runs them (a, b, c batched), alone on the GPU; in a single-GPU proof the pipeline runs next to the witness multiexps and stretches" if iso_ntt is not None else "in-step CUDA events"),
                         "in_step_ms_per_proof": ntt_in_step_ms,
                         "imad_frac": (IMAD_PER_MODMUL * (nttp["work"] / 2) * log_m / (nttp["ms"] * 1e-3)) / imad_peak if nttp["ms"] > 0 else None}
+        # the same classes timed ALONE (one query-sized multiexp per group, the H pipeline): their serial sum is what the step
+        # costs, because every hot kernel fills the SMs by itself and concurrent streams only time-slice
+        alone = None
+        if iso1 is not None and world == 1 and 1 in iso_other and 2 in iso_other:
+            alone = {"msm_accumulate_g1": round(per1 * g1_equiv, 4), "msm_accumulate_g2": round(per2, 4),
+                     "ntt": round(nttp["ms"] / 5.0, 4),
+                     "msm_sort": round(iso_other[1]["msm_sort"] * g1_equiv, 4),
+                     "msm_reduce": round(iso_other[1]["msm_reduce"] * g1_equiv + iso_other[2]["msm_reduce"], 4),
+                     "note": "stand-alone CUDA-event times scaled to one proof: G1 figures x the number of query-sized G1 multiexps of a proof "
+                             "(the G2 multiexp shares the B digit sort); an upper bound for the merged B/L/A multiexp, whose three bucket "
+                             "spaces share one reduction chain"}
+            alone["sum"] = round(sum(v for k, v in alone.items() if k != "note"), 4)
         breakdown = {k: round(v["ms"] / steps_profiled, 4) for k, v in prof.items() if v["ms"] > 0}
         breakdown["note"] = "event time per kernel class per step; the classes run on concurrent streams, so the sum exceeds the step"
         # uploaded per proof: the whole witness on device 0 and, on every other device, the span its point ranges read;
@@ -383,7 +397,7 @@ def run_gpu(args):
                                        "(bases = known multiples of the generators), r and s fixed",
                            "log_m": log_m, "parallelism": f"one process drives {world} GPUs (za_prover_create_proof): msm point-range x{world}, device 0 (H pipeline) takes {rank0_weight:.3f} of a share of the witness multiexps; torchrun ranks > 0 only take part in the barriers" if world > 1 else "single GPU",
                            "l2": "inputs larger than L2: proving key 470 MB + witness 32 MB per step"},
-                "roofline": roofline, "roofline_g2": roofline_g2, "roofline_ntt": roofline_ntt, "roofline_step": roofline_step, "kernel_ms_per_step": breakdown,
+                "roofline": roofline, "roofline_g2": roofline_g2, "roofline_ntt": roofline_ntt, "roofline_step": roofline_step, "kernel_ms_per_step": breakdown, "kernel_ms_alone_per_step": alone,
                 "proof_sha256": hashlib.sha256(proof).hexdigest(),
                 "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": D2H_BYTES},
                 "gpu_launches": int(launches), "clocks": clocks, "imad_peak_timads": imad_peak / 1e12,
