@@ -288,3 +288,46 @@ def test_za_test_runs_the_reference_circomlib_tests(name):
     etc.) pass through this front-end."""
     got = za2c.run_tests(os.path.join(REF, "interop", "circuits", "circomlib", "za_test", name))
     assert {t["name"]: (t["signals"], t["constraints"]) for t in got} == ZA_TEST_COUNTS[name]
+
+
+# ---- algebra (compiler/src/algebra/{fs,lc,qeq}.rs tests, through the evaluator) ------------------------------------------
+def test_field_scalar_arithmetic():
+    """fs.rs:375-436: + * neg += % << >> / on field scalars (a scope value prints through Display: the full residue)."""
+    scope = za2c.evaluate(source="""
+        function f() { var aa = 1 + 1; aa += 1; return aa; }
+        var six = (1+1+1) * (1+1);
+        var m1 = -1;
+        var two = -(m1 + m1);
+        var three = f();
+        var md = 1012 % 1000;
+        var shl = 10 << 2;
+        var shr = 40 >> 1;
+        var dv = 6 * (1 / 2);
+    """)["scope"]
+    r = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    assert scope == {"six": "Algebra(6)", "m1": "Algebra(%d)" % (r - 1), "two": "Algebra(2)", "three": "Algebra(3)", "md": "Algebra(12)",
+                     "shl": "Algebra(40)", "shr": "Algebra(20)", "dv": "Algebra(3)"}
+
+
+def test_linear_combinations_and_quadratic_equations():
+    """lc.rs:152-221, qeq.rs:150-172: LC + FS, LC * FS, -LC, LC + LC cancelling to zero, LC * LC -> QEQ, in the text form of
+    qeq.rs:20-32 ([a]*[b]+[c], negative coefficients as -k)."""
+    r = za2c.evaluate(source="""
+        template t() {
+            signal s1; signal s2;
+            (2*s1 + s2) * s2 === 0;
+            (s1 + 1 + 1) * 2 === 0;
+            -(-s1 + s2) === 0;
+            (-s1 + s2) + (s1 - s2) === 0;
+            (s1 + 1) * (s2 + 2) === s1 * 3;
+        }
+        component main = t();""")
+    assert r["constraints"] == ["[2main.s1+1main.s2]*[1main.s2]+[ ]", "[ ]*[ ]+[2main.s1+4one]", "[ ]*[ ]+[1main.s1-1main.s2]", "[ ]*[ ]+[ ]",
+                                "[1main.s1+1one]*[1main.s2+2one]+[-3main.s1]"]
+
+
+def test_top_level_statements_are_declarations_only():
+    """lang.lalrpop: a body element is include / function / template / var / component / signal — an assignment is not."""
+    with pytest.raises(TypeError) as e:
+        za2c.evaluate(source="var a = 1; a += 1;")
+    assert "UnrecognizedToken" in str(e.value)
