@@ -53,8 +53,10 @@ def test_plan_at_the_benchmark_size(n):
     for lo, hi in plans:
         pieces = [(hi[q] - lo[q]) / cnt[q] for q in range(1, 5) if hi[q] > lo[q]]
         assert 1 <= len(pieces) <= 3 and min(pieces) > 0.05
-    shares = [(hi[0] - lo[0]) for lo, hi in plans]
-    assert shares[0] == min(shares)
+        if hi[0] == lo[0]:                                   # no H share: a device that runs nothing but its piece of B (G2)
+            assert [q for q in range(1, 5) if hi[q] > lo[q]] == [4]
+    shares = [(hi[0] - lo[0]) for lo, hi in plans if hi[0] > lo[0]]
+    assert plans[0][1][0] - plans[0][0][0] == min(shares)   # device 0 (H pipeline first) takes the smallest H share
 
 
 def test_bad_arguments():

@@ -1078,11 +1078,11 @@ Prover::~Prover() {
 //     device touches one or two queries with long ranges) and the H query, each in proportion to the time it has: device 0
 //     runs the H pipeline first and gets less;
 //   * n2 and the common finish time T are found by trying every n2 and bisecting T.
-// ZA_PROVER_COSTS="hp,g1,g2,tail_g1,tail_g2" overrides the model (defaults 2.1, 3.7, 9.5, 0.8, 1.3: a device's share of a
+// ZA_PROVER_COSTS="hp,g1,g2,tail_g1,tail_g2" overrides the model (defaults 2.1, 3.9, 8.6, 0.9, 1.2: a device's share of a
 // query costs more per point than the whole query — smaller window, shorter waves);
 // ZA_PROVER_PLAN=0 restores the slices, ZA_PROVER_PLAN=1 the first version of the line (no pure G2 devices, H split evenly).
 struct DevicePlan { size_t lo[5], hi[5]; };
-struct PlanModel { double hp = 2.1, g1 = 3.7, g2 = 9.5, t1 = 0.8, t2 = 1.3; };      // fitted to profiles/r02_shards.md (per-device times of the plan)
+struct PlanModel { double hp = 2.1, g1 = 3.9, g2 = 8.6, t1 = 0.9, t2 = 1.2; };      // fitted to profiles/r02_shards.md (per-device times; 8 GPUs: 4.67 -> 4.37 ms against 3.7 / 9.5 / 0.8 / 1.3)
 static PlanModel plan_model() {
     PlanModel pm;
     if (const char* e = getenv("ZA_PROVER_COSTS")) {
@@ -1137,6 +1137,7 @@ static std::vector<DevicePlan> prover_make_plans(const size_t* cnt, size_t m, in
         for (int it = 0; it < 60; it++) {
             const double T = 0.5 * (lo + hi);
             double pure = n2 ? std::min(std::max(T - t2, 0.0), c_b2 / n2) : 0.0;
+            if (n2 && c_b2 - n2 * pure < 0.05 * c_b2) pure = c_b2 / n2;      // no sliver of B (G2) for the shared devices
             const double g2_left = c_b2 - n2 * pure;
             const double need = g2_left + w_g1 + c_h;
             const double total = shared_caps(T, n2, g2_left, cap);
@@ -1148,7 +1149,10 @@ static std::vector<DevicePlan> prover_make_plans(const size_t* cnt, size_t m, in
             }
             if (ok) hi = T; else lo = T;
         }
-        if (hi < best.T - 1e-9) { best.T = hi; best.n2 = n2; best.pure = n2 ? std::min(std::max(hi - t2, 0.0), c_b2 / n2) : 0.0; }
+        if (hi < best.T - 1e-9) {
+            best.T = hi; best.n2 = n2; best.pure = n2 ? std::min(std::max(hi - t2, 0.0), c_b2 / n2) : 0.0;
+            if (n2 && c_b2 - n2 * best.pure < 0.05 * c_b2) best.pure = c_b2 / n2;
+        }
     }
     const int n2 = best.n2;
     const double g2_pure_total = n2 * best.pure, g2_left = c_b2 - g2_pure_total;
@@ -1189,6 +1193,14 @@ static std::vector<DevicePlan> prover_make_plans(const size_t* cnt, size_t m, in
             d.hi[qq[q]] = last ? qc[q] : line_index(qs[q], ql[q], qc[q], x1);
             if (d.hi[qq[q]] < d.lo[qq[q]]) d.hi[qq[q]] = d.lo[qq[q]];
         }
+    }
+    // a leftover of B (G2) too short to be worth a multiexp of its own (rounding): the last pure device takes it
+    if (n2) {
+        const int first_shared = order[0];
+        DevicePlan& f = plans[first_shared];
+        bool only_first = true;
+        for (size_t i = 1; i < order.size(); i++) if (plans[order[i]].hi[Q_B2] > plans[order[i]].lo[Q_B2]) only_first = false;
+        if (only_first && f.hi[Q_B2] > f.lo[Q_B2] && f.hi[Q_B2] - f.lo[Q_B2] < 4096) { plans[n2].hi[Q_B2] = f.hi[Q_B2]; f.lo[Q_B2] = f.hi[Q_B2]; }
     }
     // H in proportion to the same capacities, in device order
     {
