@@ -159,3 +159,25 @@ def test_solidity_with_the_reference_template_when_present():
     vk_inf = dict(vk); vk_inf["alpha_g1"] = bytes(64)
     with pytest.raises(za_b200.ZaError):                           # "non-infinite point expected" (ethereum.rs:224)
         za_b200.vk_to_solidity(vk_inf, ["main.r"], tmpl)
+
+
+def test_untrusted_json_cannot_exhaust_the_stack_and_trailing_bytes_are_refused():
+    """Round-1 review: proof / vk JSON comes from untrusted parties.  serde_json (what the reference parses with) stops at 128
+    levels of nesting and refuses trailing characters; so does this parser — an error, never a crash."""
+    import json
+    import za_b200
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "groth16_example.json")))
+    vk = {k: bytes.fromhex(v) for k, v in g["vk"].items() if k != "ic"}
+    vk["ic"] = [bytes.fromhex(x) for x in g["vk"]["ic"]]
+    vk_json = za_b200.vk_to_json(vk, ["main.r"])
+    assert za_b200.verify(vk_json, g["proof_json"]) is True
+    for bad in ("[" * 100000, '{"a":' * 5000 + "1" + "}" * 5000):
+        with pytest.raises(za_b200.ZaError) as e:
+            za_b200.verify(vk_json, bad)
+        assert "recursion limit" in str(e.value)
+        with pytest.raises(za_b200.ZaError):
+            za_b200.verify(bad, g["proof_json"])
+    with pytest.raises(za_b200.ZaError) as e:
+        za_b200.verify(vk_json, g["proof_json"] + " x")
+    assert "trailing" in str(e.value)
+    assert za_b200.verify(vk_json, g["proof_json"] + "  \n") is True          # trailing whitespace is fine
