@@ -139,3 +139,18 @@ def test_two_contexts_in_one_process():
         assert np.array_equal(c1.fft(d), exp)
     finally:
         c0.close(); c1.close()
+
+
+def test_circuit_satisfied_refuses_a_null_aux(ctx):
+    """Round-1 review: za_circuit_satisfied with num_aux > 0 and aux == NULL returns ZA_ERR_INVALID instead of dereferencing it."""
+    import ctypes
+    import za_b200
+    from za_b200 import _lib
+    ni, na, ptr, var, coeff, inputs, aux = circuits.mul_chain_fast(300, x0=3)
+    circ = za_b200.Circuit(ctx, ni, na, ptr, var, coeff)
+    assert circ.first_unsatisfied(inputs, aux) is None
+    bad = ctypes.c_int64(0)
+    inp = np.ascontiguousarray(inputs, np.uint8)
+    rc = _lib.lib().za_circuit_satisfied(ctx.h, circ.h, inp.ctypes.data_as(ctypes.c_void_p), None, ctypes.byref(bad))
+    assert rc == -2 and b"aux" in _lib.lib().za_last_error()
+    assert circ.first_unsatisfied(inputs, aux) is None       # the context is still usable
