@@ -304,6 +304,7 @@ def run_gpu(args):
         in_step = {"g1": acc1["ms"] / max(acc1["spans"], 1), "g2": acc2["ms"] / max(acc2["spans"], 1)}
         n_g1_launches = acc1["spans"] / max(steps_profiled, 1)
         g1_work_per_step = acc1["work"] / max(steps_profiled, 1)
+        g2_work_per_step = acc2["work"] / max(steps_profiled, 1)
         ntt_in_step_ms = nttp["ms"] / max(steps_profiled, 1)
         if iso1 is not None:
             acc1, acc2, nttp = iso1, iso2, iso_ntt
@@ -313,7 +314,9 @@ def run_gpu(args):
         # to (the merged B/L/A multiexp is ONE launch over three queries: 4 query-sized launches per proof at N = 1)
         g1_equiv = g1_work_per_step / max(acc1["work"] / max(acc1["spans"], 1), 1.0) if iso1 is not None else n_g1_launches
         in_step["g1"] = prof["msm_accumulate_g1"]["ms"] / max(steps_profiled, 1) / max(g1_equiv, 1.0)      # per query-sized launch
-        dom = acc1 if per1 * max(g1_equiv, 1.0) >= per2 else acc2
+        # the same for G2: device 0's share of the B (G2) query at N > 1 (0 when the plan gives it none)
+        g2_equiv = g2_work_per_step / max(acc2["work"] / max(acc2["spans"], 1), 1.0) if iso1 is not None else 1.0
+        dom = acc1 if per1 * g1_equiv >= per2 * g2_equiv else acc2
         dom_name = "msm_accumulate_g1_sm_kernel (G1 bucket accumulation, XYZZ mixed additions)" if dom is acc1 else "msm_pair_round_kernel<Fq2> x3 + msm_accumulate_kernel<Fq2>"
         traffic = ntt_traffic = None
         tfile = {}
@@ -337,15 +340,15 @@ def run_gpu(args):
                     "launch_ms": dom["ms"] / max(dom["spans"], 1),
                     "timing": ("kernel timed alone in this process (CUDA events), same size and table as in the proof; in the proof it shares the SMs with the G2 multiexp's kernels by design" if iso1 is not None else "in-step CUDA events"),
                     "in_step_launch_ms": in_step["g1" if dom is acc1 else "g2"],
-                    "share_of_step": (dom["ms"] / max(dom["spans"], 1)) * (g1_equiv if dom is acc1 else 1.0) / prove_ms,
-                    "launches_per_step": (g1_equiv if dom is acc1 else 1.0),
+                    "share_of_step": (dom["ms"] / max(dom["spans"], 1)) * (g1_equiv if dom is acc1 else g2_equiv) / prove_ms,
+                    "launches_per_step": (g1_equiv if dom is acc1 else g2_equiv),
                     "note": "tensor cores not applicable (multiprecision integer); HBM needs 96 B/point, two orders below compute"}
         g2_t = acc2["work"] * IMAD_PER_G2_UNIT / (acc2["ms"] * 1e-3) / 1e12 if acc2["ms"] > 0 else 0.0
         roofline_g2 = {"bound": "imad", "kernel": "G2 bucket accumulation: msm_pair_round_kernel<Fq2> (batched-affine rounds) + msm_accumulate_kernel<Fq2>",
                        "achieved": g2_t, "peak": imad_peak / 1e12, "unit": "TIMAD/s", "frac": g2_t / (imad_peak / 1e12) if imad_peak else None,
                        "algorithmic": f"{int(acc2['work'] / max(acc2['spans'], 1))} Fq products (17 per batched-affine addition, 28 per XYZZ mixed addition over Fq2) x {IMAD_PER_G2_UNIT:.0f} IMAD (an Fq2 product = 3 units = 656 IMAD lazily reduced, an Fq2 squaring = 2 units = 528) per multiexp",
                        "launch_ms": acc2["ms"] / max(acc2["spans"], 1), "in_step_launch_ms": in_step["g2"],
-                       "share_of_step": acc2["ms"] / max(acc2["spans"], 1) / prove_ms}
+                       "share_of_step": acc2["ms"] / max(acc2["spans"], 1) * g2_equiv / prove_ms, "launches_per_step": g2_equiv}
         ntt_bytes = 64.0 * nttp["work"]
         ntt_gbs = ntt_bytes / (nttp["ms"] * 1e-3) / 1e9 if nttp["ms"] > 0 else 0.0
         roofline_ntt = {"bound": "hbm", "kernel": "ntt_pass_kernel (one transform = 2 passes at 2^20; a, b, c batched)", "achieved": ntt_gbs, "peak": hbm_peak, "unit": "GB/s",
