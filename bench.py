@@ -3,12 +3,19 @@
   "Groth16 prove ms @2^20 constraints; G1 MSM Mpts/s; Fr NTT GElem/s".
 
 One step = one create_proof over the synthetic 2^20-domain multiplication-chain circuit (SURVEY §8d
-config 4).  `value` = device-timed ms per proof with the witness resident in HBM; `e2e` = the same
-through the public host-buffer call (za_create_proof: witness H2D and proof D2H inside the timed
-region).  Sub-metrics: 2^24-point G1 MSM and 2^24-point Fr NTT (config 5), each with its roofline.
-N > 1 (one process per GPU under torchrun): every query of every multiexp is cut by point range across
-ranks, rank 0 runs the H-polynomial NTTs and scatters the h scalars over NCCL, partial sums are
-gathered and combined on the host — total work is fixed, so scaling is "strong".
+config 4).  `value` = device-timed ms per proof with the witness resident in HBM (per-class profiling
+events off); `e2e` = the same through the public host-buffer call (za_prover_create_proof: witness H2D
+and the partial results D2H inside the timed region).  Every line carries `proof_sha256` and, from the
+oracle run after the timed region, `cpu_baseline.proof_matches_gpu`.  Rooflines: `roofline` (dominant
+kernel, IMAD bound, stand-alone launch time, ncu DRAM traffic), `roofline_g2`, `roofline_ntt` (against
+HBM, IMAD fraction beside it), `roofline_step` (all field products of a proof at their IMAD cost / step);
+`kernel_ms_per_step` are the overlapping in-step class times, `kernel_ms_alone_per_step` the stand-alone
+ones whose serial sum the step is.  Sub-metrics: 2^24-point G1 MSM and Fr NTT (config 5), a real key at
+2^20 through Parameters::read(checked), the EdDSA-MiMC statement (config 3).
+N > 1: torchrun launches one rank per GPU as the contract demands; rank 0 drives ALL N devices through ONE
+za_prover_create_proof (a host thread per device inside the library, planned point ranges, h slices
+stored into the peers' memory by the last NTT pass, host combine: no NCCL on the data path), the other
+ranks only join the barriers — total work is fixed, so scaling is "strong".
 
 `--impl reference`: the CPU restatement of bellman's algorithm (oracle/, multi-threaded) on the same
 workload; it is also what `cpu_baseline` reports.  The oracle is never on the GPU arm's timed path.
