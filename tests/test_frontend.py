@@ -331,3 +331,35 @@ def test_top_level_statements_are_declarations_only():
     with pytest.raises(TypeError) as e:
         za2c.evaluate(source="var a = 1; a += 1;")
     assert "UnrecognizedToken" in str(e.value)
+
+
+# ---- error texts (the bindings hand the Debug text of the error enum to their caller, lib.rs:59,75,99) -----------------------
+ERRORS = [
+    # eval.rs:386-390
+    ("component main = Nope();", 'Evaluator(InvalidType("component main only can be initialized with existingtemplate"))'),
+    ("var k = nope(1);", 'Evaluator(NotFound("function nope"))'),                                        # eval.rs:325
+    ("template t() { signal a; signal a; }\ncomponent main = t();", 'Evaluator(AlreadyExists("signal main.a"))'),   # eval.rs:851
+    ("var a = 1;\nvar a = 2;", 'Evaluator(AlreadyExists("a"))'),                                         # eval.rs:882
+    ("var a = b;", 'Evaluator(NotFound("b"))'),                                                          # eval.rs:1008
+    ("function f(a) { return a; }\nvar k = f(1,2);", 'Evaluator(InvalidParameter("f"))'),               # eval.rs:334
+    ("function f(a) { var b = a; }\nvar k = f(1);", 'Evaluator(BadFunctionReturn("f"))'),               # eval.rs:361
+    # a constraint between two known scalars cannot be generated (eval.rs:1226): "left===right" through signals.format
+    ("template t() { signal a; a <-- 2; a === 3; }\ncomponent main = t();", 'Evaluator(CannotGenerateConstrain("2===3"))'),
+    # a product of three signals is not a quadratic equation (algebra/value.rs: InvalidOperation)
+    ("template t() { signal a; signal b; a*a*a === b; }\ncomponent main = t();",
+     'Evaluator(Algebra(InvalidOperation("Cannot apply operator * on [1s1]*[1s1]+[ ] over 1s1")))'),
+]
+
+
+@pytest.mark.parametrize("source,text", ERRORS)
+def test_error_debug_text(source, text):
+    with pytest.raises(TypeError) as e:
+        za2c.evaluate(source=source)
+    assert str(e.value) == text
+
+
+def test_failed_witness_check_names_both_sides():
+    """eval.rs:1213-1219: CannotTestConstrain("{lhe:?}==={rhe:?} => {left}==={right}")."""
+    with pytest.raises(TypeError) as e:
+        za2c.evaluate(source="template t() { signal a; a <-- 2; a === 3; }\ncomponent main = t();", witness=True)
+    assert str(e.value) == 'Evaluator(CannotTestConstrain("a===3 => 2===3"))'
