@@ -277,6 +277,12 @@ ZA_TEST_COUNTS = {      # name -> (signals, constraints) as this front-end count
                        "test_IsZero_true": (4, 4)},
     "eddsamimc.za": {"test_eddsamimc_verifier": (21736, 21744)},
     "eddsaposeidon.za": {"test_eddsaposeidon_verifier": (21879, 21887)},
+    "sha256.za": {"test_sha256_2": (204151, 204465)},
+    "smtprocessor.za": {"test_smtprocessor_delete": (46894, 46903), "test_smtprocessor_insert": (46894, 46903),
+                        "test_smtprocessor_update": (46894, 46903)},
+    "smtverifier.za": {"test_smtverify_exclusion": (26851, 26860), "test_smtverify_inclusion_1": (26851, 26860),
+                       "test_smtverify_inclusion_2": (26851, 26860), "test_smtverify_inclusion_adr1": (26851, 26860),
+                       "test_smtverify_inclusion_adr2": (26851, 26860)},
 }
 
 
