@@ -181,3 +181,58 @@ def test_untrusted_json_cannot_exhaust_the_stack_and_trailing_bytes_are_refused(
         za_b200.verify(vk_json, g["proof_json"] + " x")
     assert "trailing" in str(e.value)
     assert za_b200.verify(vk_json, g["proof_json"] + "  \n") is True          # trailing whitespace is fine
+
+
+def test_fast_final_exponentiation_chain_is_a_valid_exponent():
+    """verify.cu `final_exponentiation_fast`: the addition chain in u (three exponentiations by -u, squarings, products,
+    Frobenius maps, conjugations) restated over exponents modulo the order q^4 - q^2 + 1 of the cyclotomic subgroup — the
+    total is a multiple of (q^4 - q^2 + 1) / r by a factor coprime to r, so `== 1` decides the same as the plain power
+    (q^12 - 1) / r; and the (q^k - 1) / 6 constants of the Frobenius maps are what the source holds."""
+    import re
+    from math import gcd
+    p, r, u = P.Q_MOD, P.R_MOD, 4965661367192848881
+    n = p ** 4 - p ** 2 + 1
+    assert n % r == 0 and (p ** 12 - 1) % ((p ** 6 - 1) * (p ** 2 + 1) * n) == 0
+    neg_u = lambda e: (-u * e) % n
+    sq = lambda e: (2 * e) % n
+    frob = lambda e, k: (p ** k * e) % n
+    conj = lambda e: (-e) % n
+    f = 1
+    y0 = neg_u(f); y1 = sq(y0); y2 = sq(y1); y3 = (y2 + y1) % n
+    y4 = neg_u(y3); y5 = sq(y4); y6 = neg_u(y5)
+    y3, y6 = conj(y3), conj(y6)
+    y7 = (y6 + y4) % n; y8 = (y7 + y3) % n; y9 = (y8 + y1) % n; y10 = (y8 + y4) % n; y11 = (y10 + f) % n
+    y13 = (frob(y9, 1) + y11) % n
+    y14 = (frob(y8, 2) + y13) % n
+    y15 = frob((conj(f) + y9) % n, 3)
+    e = (y15 + y14) % n
+    h = n // r
+    assert e % h == 0 and gcd(e // h, r) == 1
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "za_b200", "csrc", "verify.cu")).read()
+    for k in (1, 2, 3):
+        m = re.search(r"EXP_Q%dM1_6\[\d+\] = \{([^}]*)\}" % k, src)
+        limbs = [int(x.strip().rstrip("UL"), 16) for x in m.group(1).split(",")]
+        assert sum(v << (64 * i) for i, v in enumerate(limbs)) == (p ** k - 1) // 6 and (p ** k - 1) % 6 == 0
+
+
+def test_fast_and_plain_final_exponentiation_give_the_same_verdicts():
+    """The plain square-and-multiply by (q^12 - 1) / r (ZA_VERIFY_PLAIN_EXP=1, read once per process) against the default."""
+    import subprocess
+    import sys
+    code = r"""
+import json, os, sys
+sys.path.insert(0, %r)
+import za_b200
+g = json.load(open(%r))
+vk = {k: bytes.fromhex(v) for k, v in g["vk"].items() if k != "ic"}
+vk["ic"] = [bytes.fromhex(x) for x in g["vk"]["ic"]]
+vkj = za_b200.vk_to_json(vk, ["main.r"])
+bad = json.loads(g["proof_json"]); bad["public_inputs"] = ["7"]
+swap = json.loads(g["proof_json"]); swap["a"], swap["c"] = swap["c"], swap["a"]
+print(za_b200.verify(vkj, g["proof_json"]), za_b200.verify(vkj, json.dumps(bad)), za_b200.verify(vkj, json.dumps(swap)))
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "groth16_example.json"))
+    outs = []
+    for plain in ("0", "1"):
+        env = dict(os.environ, ZA_VERIFY_PLAIN_EXP=plain)
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.strip())
+    assert outs[0] == outs[1] == "True False False"
