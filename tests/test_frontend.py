@@ -369,3 +369,19 @@ def test_failed_witness_check_names_both_sides():
     with pytest.raises(TypeError) as e:
         za2c.evaluate(source="template t() { signal a; a <-- 2; a === 3; }\ncomponent main = t();", witness=True)
     assert str(e.value) == 'Evaluator(CannotTestConstrain("a===3 => 2===3"))'
+
+
+def test_division_is_the_field_inverse():
+    """fs.rs:234-254: a / b = a * b^-1 mod r.  The inverse is a binary extended Euclid here (not b^(r-2)): checked against
+    python's pow(b, -1, r) on small, large and random operands, and 1 / 0 is the reference's InvalidOperation."""
+    import random
+    r = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    rnd = random.Random(7)
+    bs = [1, 2, 3, r - 1, r - 2, (r - 1) // 2, (r + 1) // 2, 1 << 253] + [rnd.randrange(1, r) for _ in range(40)]
+    src = "\n".join("var q%d = 5 / %d;" % (i, b) for i, b in enumerate(bs))
+    scope = za2c.evaluate(source=src)["scope"]
+    for i, b in enumerate(bs):
+        assert scope["q%d" % i] == "Algebra(%d)" % (5 * pow(b, -1, r) % r), b
+    with pytest.raises(TypeError) as e:
+        za2c.evaluate(source="var z = 1 / 0;")
+    assert "Cannot find inv" in str(e.value)
